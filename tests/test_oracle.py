@@ -1,0 +1,137 @@
+"""CPU: the oracle restatement (oracle/sarssl_oracle.py) against fixtures produced by the real reference."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sarssl_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def test_stft_is_windowed_dft_known_answer():
+    # explicit O(N^2) DFT in float64 on a tiny signal: the definition, independent of torch.fft
+    sig = O.synthetic_waveforms(1, 3 * 256, 2, seed=3)
+    S = O.stft(sig)
+    n = torch.arange(512, dtype=torch.float64)
+    w = 0.5 - 0.5 * torch.cos(2 * math.pi * n / 512)
+    k = torch.arange(257, dtype=torch.float64)[:, None]
+    E = torch.exp(-2j * math.pi * k * n[None, :] / 512)
+    for t in range(2):
+        for ch in range(2):
+            fr = sig[0, t * 256:t * 256 + 512, ch].double() * w
+            X = (E * fr[None, :]).sum(1)
+            assert (S[0, :, t, ch].to(torch.complex128) - X).abs().max() < 1e-5
+
+
+def test_stft_preprocess_match_reference_fixture():
+    g = load("tiny_nt16_b3")
+    sig = O.synthetic_waveforms(int(g["nb"]), (int(g["nt"]) + 1) * 256, 2, seed=int(g["sig_seed"]))
+    S = O.stft(sig)
+    ref = torch.complex(torch.from_numpy(g["stft_re"]), torch.from_numpy(g["stft_im"]))
+    assert (S - ref).abs().max() <= 1e-4 * ref.abs().max()
+    x = O.preprocess(sig)
+    xr = torch.from_numpy(g["x"])
+    assert x.shape == xr.shape
+    assert (x - xr).norm() <= 1e-5 * xr.norm()
+
+
+def test_istft_roundtrip_rectangular():
+    sig = O.synthetic_waveforms(2, 9 * 256, 2, seed=9)
+    # reference STFT analysis is Hann, synthesis rectangular: istft(stft(x)) == x * hann-OLA / count
+    y = O.istft(O.stft(sig))
+    assert y.shape == (2, 9 * 256, 2)
+    w = O.hann_periodic(512)
+    # interior samples are covered by two frames whose Hann windows sum to 1 -> y = x / 2
+    assert (y[:, 256:8 * 256] - 0.5 * sig[:, 256:8 * 256]).abs().max() < 1e-6
+
+
+def test_mask_stream_matches_cpython_fixture():
+    g = load("mask_streams")
+    for key in g.files:
+        if not key.startswith("p/"):
+            continue
+        parts = key.split("/")
+        seed, nb, npatch = int(parts[1]), int(parts[2]), int(parts[3])
+        nmic = 5 if key.endswith("nmic5") else 2
+        random.seed(seed)
+        p, c = O.draw_masks(nb, npatch, npatch // 2, nmic)
+        assert np.array_equal(p.numpy(), g[key])
+        assert np.array_equal(c.numpy(), g["c/" + key[2:]])
+
+
+def test_relative_shift_is_the_pad_view_trick():
+    T = 7
+    pos = torch.randn(2, 3, T, T)
+    z = torch.cat([pos.new_zeros(2, 3, T, 1), pos], dim=-1).view(2, 3, T + 1, T)[:, :, 1:].reshape(2, 3, T, T)
+    assert torch.equal(O.relative_shift(pos), z)
+
+
+def test_lr_schedule_fixture():
+    g = load("lr_schedule")
+    mine = np.array([O.cosine_lr(e) for e in range(1, 31)])
+    assert np.allclose(mine, g["lr"], rtol=1e-6, atol=1e-12)
+
+
+def _run_oracle(g):
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"]))
+    x = O.preprocess(sig)
+    sd = O.synthetic_state_dict(int(g["sd_seed"]))
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k and not k.endswith(".pe"):
+            v.requires_grad_(True)
+    random.seed(int(g["mask_seed"]))
+    pidx, cidx = O.draw_masks(nb, nt, nt // 2, 2)
+    taps = {}
+    loss, diff, vis = O.pretrain_forward(x, sd, pidx, cidx, training=True, taps=taps)
+    loss.backward()
+    return x, sd, pidx, cidx, loss, diff, vis, taps
+
+
+@pytest.mark.parametrize("name", ["tiny_nt16_b3", "full_nt256_b2"])
+def test_forward_backward_match_reference_fixture(name):
+    g = load(name)
+    x, sd, pidx, cidx, loss, diff, vis, taps = _run_oracle(g)
+    assert np.array_equal(pidx.numpy(), g["mask_patch_idx"]) and np.array_equal(cidx.numpy(), g["mask_ch_idx"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert abs(float(diff) - float(g["diff"])) <= 1e-5 * abs(float(g["diff"]))
+    if "pred" in g.files:
+        pr = torch.from_numpy(g["pred"])
+        assert (vis["pred"] - pr).norm() <= 1e-4 * pr.norm()
+    else:
+        got = vis["pred"].reshape(-1)[torch.from_numpy(g["pred_sample_idx"])]
+        assert np.abs(got.numpy() - g["pred_sample"]).max() <= 1e-4 * float(g["pred_norm"]) / math.sqrt(got.numel())
+    # gradients: norm-wise per tensor, with an absolute floor for analytically-zero grads (key_proj bias)
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    for k in g.files:
+        if not k.startswith("grad_norm/"):
+            continue
+        key = k[len("grad_norm/"):]
+        mine = sd[key].grad.reshape(-1)
+        ref_norm = float(g[k])
+        assert abs(float(mine.norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-7 * gmax, key
+        samp = mine[torch.from_numpy(g["grad_idx/" + key])].numpy()
+        assert np.abs(samp - g["grad_val/" + key]).max() <= 5e-3 * np.abs(g["grad_val/" + key]).max() + 1e-6 * gmax, key
+    for k in g.files:
+        if k.startswith("bn/"):
+            assert np.allclose(sd[k[3:]].detach().numpy(), g[k], rtol=1e-4, atol=1e-6), k
+
+
+def test_eval_mode_matches_reference_fixture():
+    g = load("tiny_nt16_b3")
+    x, sd, *_ = _run_oracle(g)          # one training step updates the running statistics first, as in the fixture
+    sd = {k: v.detach() for k, v in sd.items()}
+    random.seed(int(g["mask_seed"]) + 1)
+    pidx, cidx = O.draw_masks(int(g["nb"]), int(g["nt"]), int(g["nt"]) // 2, 2)
+    with torch.no_grad():
+        le, de, _ = O.pretrain_forward(x, sd, pidx, cidx, training=False)
+    assert abs(float(le) - float(g["eval_loss"])) <= 1e-5 * float(g["eval_loss"])
+    assert abs(float(de) - float(g["eval_diff"])) <= 1e-5 * float(g["eval_diff"])
