@@ -1,0 +1,341 @@
+// Multi-channel STFT front-end for sm_100a.
+//
+// Replaces (reference, paths under /root/reference/code):
+//   STFT.forward                      common/utils_module.py:49-72    -> sarssl_stft_spectrum
+//   STFTLearner.data_preprocess       learner.py:525-572 (+ AddChToBatch utils_module.py:124-148)
+//                                                                      -> sarssl_stft_frontend
+// Both are HBM-bound (about 6 MFLOP per 1.5 MB clip).  Design:
+//   * frames are 512 samples every 256; the two channels of a pair are interleaved in memory exactly like
+//     one complex sample, so a frame block is staged into shared memory with ONE 1-D bulk TMA copy
+//     (cp.async.bulk + mbarrier) and ONE complex 512-point FFT (fft512.cuh, 64 lanes) gives both spectra;
+//   * output is written frame-major ("patch layout" [clip][frame][bin][re/im][mic], 4 KB contiguous per
+//     frame) - the layout PatchSplit would produce (utils_module.py:196-205) and the one the encoder stem and
+//     the loss kernel consume - with 16-byte streaming stores;
+//   * the per-clip normalisation (divide by mean |X_ch0| over all 257 x nt bins) needs a clip-wide reduction
+//     before anything can be written.  The fused kernel is persistent: CTAs pull (clip, frame-block) items
+//     from an atomic queue, keep their un-scaled spectra in shared memory, publish a partial magnitude sum,
+//     rendezvous on a per-clip arrival counter in global memory, then scale and write.  HBM traffic is the
+//     algorithmic minimum (read the waveform once, write the spectra once).  Items are handed out in order,
+//     so all peers of a clip are resident whenever grid >= items-per-clip (checked on the host; otherwise the
+//     generic three-kernel path below is used).
+//   * generic path (any channel count, any length): spectrum kernel -> clip scale kernel -> pair/normalise.
+#include "common.cuh"
+#include "fft512.cuh"
+#include "../../include/sarssl_b200.h"
+
+namespace sarssl {
+
+constexpr int kFPI = 8;            // frames per work item
+constexpr int kGroups = 4;         // 64-lane FFT groups per CTA
+constexpr int kThreads = kGroups * kFftLanes;
+constexpr int kHop = 256;
+constexpr int kBins = 257;
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kFftLanes) : "memory"); }
+
+// One frame: windowed load from the staged samples, 3 radix-8 passes, split.  On return v[] holds Z and the
+// group's scratch holds Z for split_bin(); the caller must group_bar() again before reusing the scratch.
+__device__ __forceinline__ void fft_frame(const float2* frame, const FftLane& c, float* sre, float* sim, int l, int g,
+                                          float2 (&v)[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float2 s = frame[l + 64 * r];
+        v[r] = make_float2(s.x * c.win[r], s.y * c.win[r]);
+    }
+    fft_pass1(v, c, sre, sim, l);
+    group_bar(g);
+    fft_pass2_load(v, sre, sim, l);
+    group_bar(g);
+    fft_pass2_store(v, c, sre, sim, l);
+    group_bar(g);
+    fft_pass3(v, sre, sim, l);
+    group_bar(g);
+    split_store(v, sre, sim, l);
+    group_bar(g);
+}
+
+struct FusedSmem {
+    float2 in[(kFPI + 1) * kHop];                 // 18 KB   staged samples (ch0, ch1)
+    float4 out[kFPI * kHop];                      // 32 KB   un-scaled bins 1..256, (re0, re1, im0, im1)
+    float scratch[kGroups][kFftScratchFloats];    // 18 KB
+    float red[32];
+    uint64_t bar;
+    int item;
+    float scale;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// counters[0] = work queue head, counters[1] = error flag, counters[2 + b] = arrivals for clip b
+__global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const float* __restrict__ sig, float4* __restrict__ out,
+                                                                     float* partials, unsigned* counters, int nb,
+                                                                     long long nsample, int nt, int ipc, float eps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+    const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
+    FftLane lane;
+    lane.init(l);
+    float* sre = sm.scratch[g];
+    float* sim = sre + kFftPlane;
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int nitems = nb * ipc;
+    for (;;) {
+        if (tid == 0) sm.item = (int)atomicAdd(&counters[0], 1u);
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= nitems) break;
+        const int b = item / ipc, fb = item - b * ipc;
+        const int f0 = fb * kFPI;
+        const int nfr = min(kFPI, nt - f0);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(nfr + 1) * kHop * sizeof(float2);
+            mbar_expect_tx(&sm.bar, bytes);
+            tma_bulk_g2s(sm.in, sig + ((size_t)b * nsample + (size_t)f0 * kHop) * 2, bytes, &sm.bar);
+        }
+        mbar_wait(&sm.bar, phase);
+        phase ^= 1u;
+
+        float part = 0.f;
+        for (int fr = g; fr < nfr; fr += kGroups) {
+            float2 v[8];
+            fft_frame(sm.in + fr * kHop, lane, sre, sim, l, g, v);
+            float4* orow = sm.out + fr * kHop;
+#pragma unroll
+            for (int k3 = 0; k3 < 4; ++k3) {
+                const float4 o = split_bin(v, sre, sim, l, k3);
+                part += sqrtf(o.x * o.x + o.z * o.z);
+                const int k = l + 64 * k3;
+                if (k >= 1) orow[k - 1] = o;
+            }
+            if (l == 0) {
+                const float4 o = split_bin(v, sre, sim, 0, 4);
+                part += sqrtf(o.x * o.x + o.z * o.z);
+                orow[255] = o;
+            }
+            group_bar(g);
+        }
+        const float total = block_sum(part, sm.red);
+        if (tid == 0) {
+            partials[(size_t)b * ipc + fb] = total;
+            __threadfence();
+            atomicAdd(&counters[2 + b], 1u);
+            unsigned spins = 0;
+            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)ipc) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) {          // ~ seconds: never expected; report instead of hanging
+                    atomicExch(&counters[1], 1u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {                              // fixed-order (deterministic) sum of the clip's partials
+            float s = 0.f;
+            for (int i = tid; i < ipc; i += 32) s += __ldcg(&partials[(size_t)b * ipc + i]);
+            s = warp_sum(s);
+            if (tid == 0) sm.scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
+        }
+        __syncthreads();
+        const float scale = sm.scale;
+        float4* dst = out + ((size_t)b * nt + f0) * kHop;
+        for (int i = tid; i < nfr * kHop; i += kThreads) {
+            float4 o = sm.out[i];
+            o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+            st_stream_f4(dst + i, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------- generic path ----------------
+// grid.x = nb * ipc * npair.  Pair p covers channels (2p, 2p+1) (second one zero if absent).
+// spec: complex64 [nb][nt][257][nch] (interleaved re, im);  partials: |X_ch0| sums per (clip, frame block).
+__global__ void __launch_bounds__(kThreads) stft_spectrum_kernel(const float* __restrict__ sig, float2* __restrict__ spec,
+                                                               float* __restrict__ partials, int nb, long long nsample, int nch,
+                                                               int nt, int ipc, int npair) {
+    __shared__ __align__(16) float2 in_s[(kFPI + 1) * kHop];
+    __shared__ float scratch[kGroups][kFftScratchFloats];
+    __shared__ float red[32];
+    const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
+    int item = blockIdx.x;
+    const int p = item % npair; item /= npair;
+    const int fb = item % ipc;
+    const int b = item / ipc;
+    const int f0 = fb * kFPI, nfr = min(kFPI, nt - f0);
+    const int c0 = 2 * p, c1 = 2 * p + 1;
+    const float* src = sig + ((size_t)b * nsample + (size_t)f0 * kHop) * nch;
+    for (int i = tid; i < (nfr + 1) * kHop; i += kThreads)
+        in_s[i] = make_float2(src[(size_t)i * nch + c0], c1 < nch ? src[(size_t)i * nch + c1] : 0.f);
+    __syncthreads();
+    FftLane lane;
+    lane.init(l);
+    float* sre = scratch[g];
+    float* sim = sre + kFftPlane;
+    float part = 0.f;
+    for (int fr = g; fr < nfr; fr += kGroups) {
+        float2 v[8];
+        fft_frame(in_s + fr * kHop, lane, sre, sim, l, g, v);
+        float2* orow = spec + ((size_t)b * nt + f0 + fr) * kBins * nch;
+#pragma unroll
+        for (int k3 = 0; k3 < 5; ++k3) {
+            if (k3 == 4 && l != 0) break;
+            const float4 o = split_bin(v, sre, sim, l, k3);
+            const int k = l + 64 * k3;
+            orow[(size_t)k * nch + c0] = make_float2(o.x, o.z);
+            if (c1 < nch) orow[(size_t)k * nch + c1] = make_float2(o.y, o.w);
+            if (p == 0) part += sqrtf(o.x * o.x + o.z * o.z);
+        }
+        group_bar(g);
+    }
+    if (partials != nullptr && p == 0) {
+        const float total = block_sum(part, red);
+        if (tid == 0) partials[(size_t)b * ipc + fb] = total;
+    }
+}
+
+__global__ void clip_scale_kernel(const float* __restrict__ partials, float* __restrict__ scale, int nb, int ipc, int nt, float eps) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= nb) return;
+    float s = 0.f;
+    for (int i = lane; i < ipc; i += 32) s += partials[(size_t)b * ipc + i];
+    s = warp_sum(s);
+    if (lane == 0) scale[b] = 1.0f / (s / (float)((long long)kBins * nt) + eps);
+}
+
+// spec [nb][nt][257][nch] -> patches [(b*(nch-1) + j-1)][nt][256] float4 (re0, re_j, im0, im_j), bins 1..256, scaled
+__global__ void pair_normalize_kernel(const float2* __restrict__ spec, const float* __restrict__ scale, float4* __restrict__ out,
+                                      int nb, int nt, int nch) {
+    const size_t total = (size_t)nb * (nch - 1) * nt * 256;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i & 255);
+        size_t r = i >> 8;
+        const int t = (int)(r % nt); r /= nt;
+        const int j = (int)(r % (nch - 1)) + 1;
+        const int b = (int)(r / (nch - 1));
+        const float s = scale[b];
+        const float2* row = spec + (((size_t)b * nt + t) * kBins + (f + 1)) * nch;
+        const float2 a = row[0], c = row[j];
+        st_stream_f4(out + i, make_float4(a.x * s, c.x * s, a.y * s, c.y * s));
+    }
+}
+
+static int items_per_clip(int nt) { return (nt + kFPI - 1) / kFPI; }
+
+}  // namespace sarssl
+
+using namespace sarssl;
+
+extern "C" int sarssl_stft_num_frames(long long nsample, int win_len, int hop) {
+    if (nsample < win_len || hop <= 0) return 0;
+    return (int)((nsample - win_len) / hop + 1);
+}
+
+extern "C" size_t sarssl_stft_workspace_bytes(int nb, long long nsample, int nch, int generic) {
+    const int nt = sarssl_stft_num_frames(nsample, 512, 256);
+    const int ipc = items_per_clip(nt > 0 ? nt : 1);
+    size_t bytes = 256;                                            // counters: head, error, pad
+    bytes += ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;    // per-clip arrivals
+    bytes += ((size_t)nb * ipc * sizeof(float) + 255) / 256 * 256; // partial sums
+    bytes += ((size_t)nb * sizeof(float) + 255) / 256 * 256;       // per-clip scale (generic path)
+    if (nch != 2 || generic) bytes += (size_t)nb * (nt > 0 ? nt : 1) * kBins * nch * sizeof(float2);   // spectrum temp
+    return bytes;
+}
+
+static int check_stft_args(const void* sig, const void* out, int nb, long long nsample, int nch, int win_len, int hop, int nfft) {
+    SARSSL_CHECK_ARG(sig && out, "stft: null pointer");
+    SARSSL_CHECK_ARG(nb > 0 && nch > 0, "stft: nb=%d nch=%d must be positive", nb, nch);
+    if (win_len != 512 || nfft != 512 || hop != 256) {
+        set_last_error("stft: only win_len = nfft = 512, hop = 256 is implemented (run_pretrain.py:67-72); got %d/%d/%d", win_len, nfft, hop);
+        return SARSSL_ERR_UNSUPPORTED;
+    }
+    SARSSL_CHECK_ARG(nsample >= win_len, "stft: nsample=%lld shorter than one frame", nsample);
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stft_spectrum(const float* sig, float* spec, int nb, long long nsample, int nch, int win_len, int hop,
+                                    int nfft, cudaStream_t stream) {
+    int rc = check_stft_args(sig, spec, nb, nsample, nch, win_len, hop, nfft);
+    if (rc) return rc;
+    const int nt = sarssl_stft_num_frames(nsample, win_len, hop), ipc = items_per_clip(nt), npair = (nch + 1) / 2;
+    stft_spectrum_kernel<<<nb * ipc * npair, kThreads, 0, stream>>>(sig, reinterpret_cast<float2*>(spec), nullptr, nb, nsample, nch, nt, ipc, npair);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, long long nsample, int nch, int win_len, int hop,
+                                    int nfft, float eps, int force_generic, void* workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
+    int rc = check_stft_args(sig, patches, nb, nsample, nch, win_len, hop, nfft);
+    if (rc) return rc;
+    SARSSL_CHECK_ARG(nch >= 2, "stft_frontend: needs at least 2 microphones (got %d)", nch);
+    SARSSL_CHECK_ARG(workspace != nullptr, "stft_frontend: null workspace");
+    if (workspace_bytes < sarssl_stft_workspace_bytes(nb, nsample, nch, 0)) {
+        set_last_error("stft_frontend: workspace %zu < required %zu", workspace_bytes, sarssl_stft_workspace_bytes(nb, nsample, nch, 0));
+        return SARSSL_ERR_WORKSPACE;
+    }
+    SARSSL_CHECK_ARG(aligned16(sig) && aligned16(patches) && aligned16(workspace), "stft_frontend: buffers must be 16-byte aligned");
+    const int nt = sarssl_stft_num_frames(nsample, win_len, hop), ipc = items_per_clip(nt);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    unsigned* counters = reinterpret_cast<unsigned*>(ws);
+    size_t off = 256 + ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;
+    float* partials = reinterpret_cast<float*>(ws + off);
+    off += ((size_t)nb * ipc * sizeof(float) + 255) / 256 * 256;
+    float* scale = reinterpret_cast<float*>(ws + off);
+    off += ((size_t)nb * sizeof(float) + 255) / 256 * 256;
+
+    static int max_ctas_per_sm = -1;
+    const size_t smem = sizeof(FusedSmem);
+    if (max_ctas_per_sm < 0) {
+        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0;
+        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_fused_kernel, kThreads, smem));
+        max_ctas_per_sm = n;
+    }
+    const long long resident = (long long)max_ctas_per_sm * sm_count();
+    // the bulk-TMA staging needs 16-byte aligned clip starts: nsample * 2 floats * 4 B -> nsample even
+    const bool fused_ok = !force_generic && nch == 2 && (nsample % 2 == 0) && resident >= ipc && max_ctas_per_sm > 0;
+    if (fused_ok) {
+        SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
+        const long long items = (long long)nb * ipc;
+        const int grid = (int)(items < resident ? items : resident);
+        stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb,
+                                                                     nsample, nt, ipc, eps);
+        SARSSL_LAUNCH_CHECK();
+        return SARSSL_OK;
+    }
+    // generic: spectrum (+ partial sums) -> per-clip scale -> pair + normalise
+    float2* spec = reinterpret_cast<float2*>(ws + off);
+    if (workspace_bytes < sarssl_stft_workspace_bytes(nb, nsample, nch, 1)) {
+        set_last_error("stft_frontend(generic path): workspace %zu < required %zu (query with generic=1)", workspace_bytes,
+                       sarssl_stft_workspace_bytes(nb, nsample, nch, 1));
+        return SARSSL_ERR_WORKSPACE;
+    }
+    const int npair = (nch + 1) / 2;
+    stft_spectrum_kernel<<<nb * ipc * npair, kThreads, 0, stream>>>(sig, spec, partials, nb, nsample, nch, nt, ipc, npair);
+    SARSSL_LAUNCH_CHECK();
+    clip_scale_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(partials, scale, nb, ipc, nt, eps);
+    SARSSL_LAUNCH_CHECK();
+    const size_t total = (size_t)nb * (nch - 1) * nt * 256;
+    const int blocks = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
+    pair_normalize_kernel<<<blocks, 256, 0, stream>>>(spec, scale, reinterpret_cast<float4*>(patches), nb, nt, nch);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stft_frontend_error_flag(const void* workspace, int* flag_host, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(workspace && flag_host, "null pointer");
+    unsigned v = 0;
+    SARSSL_CUDA(cudaMemcpyAsync(&v, static_cast<const unsigned*>(workspace) + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    SARSSL_CUDA(cudaStreamSynchronize(stream));
+    *flag_host = (int)v;
+    return SARSSL_OK;
+}
