@@ -396,11 +396,12 @@ def synthetic_waveforms(nb, nsample, nch=2, seed=1234):
     """0.1*randn, channel j>0 = delayed, attenuated copy of channel 0 + noise so that
     `diff` is meaningful."""
     g = torch.Generator().manual_seed(seed)
-    base = 0.1 * torch.randn(nb, nsample + 8, generator=g)
-    chans = [base[:, 8:]]
+    pad = max(8, 3 * nch)
+    base = 0.1 * torch.randn(nb, nsample + pad, generator=g)
+    chans = [base[:, pad:]]
     for j in range(1, nch):
         d = 3 * j
-        chans.append(0.8 * base[:, 8 - d:8 - d + nsample] + 0.02 * torch.randn(nb, nsample, generator=g))
+        chans.append(0.8 * base[:, pad - d:pad - d + nsample] + 0.02 * torch.randn(nb, nsample, generator=g))
     return torch.stack(chans, dim=-1).contiguous()
 
 

@@ -303,8 +303,8 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     const long long resident = (long long)max_ctas_per_sm * sm_count();
     // the bulk-TMA staging needs 16-byte aligned clip starts: nsample * 2 floats * 4 B -> nsample even
     const bool fused_ok = !force_generic && nch == 2 && (nsample % 2 == 0) && resident >= ipc && max_ctas_per_sm > 0;
+    SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
     if (fused_ok) {
-        SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
         const long long items = (long long)nb * ipc;
         const int grid = (int)(items < resident ? items : resident);
         stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb,
