@@ -120,6 +120,134 @@ int sarssl_masked_loss(const void* pred, int pred_dtype, const float* patches, c
 int sarssl_scale_masked_rows(void* dpred, int dtype, const uint8_t* frame_flag, const float* gscale_dev, int nb, int nt, int nf,
                              cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * A7-A11  dense contractions (torch.nn.Linear / Conv1d(k=1) / matmul of the reference, e.g. conformer/feed_forward.py:47-54,
+ * attention.py:72-103, convolution.py:136-146, model.py:297-301) and their gradients
+ * ---------------------------------------------------------------------------------------------------------- */
+
+#define SARSSL_ACT_NONE 0
+#define SARSSL_ACT_RELU 1
+#define SARSSL_ACT_SWISH 2
+
+/* C[z][m][n] = resid[z][m][n] + beta * dropout( act( alpha * sum_k A[z][m][k] * B[z][n][k] + bias[n] ) ),  z = (z1, z2)
+ *   element strides: A(m,k) at A + z1*sAb1 + z2*sAb2 + m*sAm + k*sAk; B(n,k) likewise; C/pre_out/resid row-major with ldc/ldr.
+ *   ab_dtype / c_dtype: SARSSL_F32 or SARSSL_BF16 storage, fp32 accumulation.  bias is fp32 (nullable).
+ *   pre_out (nullable, C's dtype/layout) receives the pre-activation value.  accumulate != 0: C += result.
+ *   drop_p/drop_seed: epilogue dropout keyed by the C element offset.  a_drop_p/a_drop_seed: multiply A by the dropout mask
+ *   (and 1/(1-p)) keyed by the A element offset - how backward re-applies a forward mask without storing it. */
+typedef struct sarssl_gemm_args {
+    const void* A; const void* B; void* C; void* pre_out; const void* resid; const float* bias;
+    long long sAm, sAk, sAb1, sAb2;
+    long long sBn, sBk, sBb1, sBb2;
+    long long ldc, sCb1, sCb2, ldr;
+    int M, N, K, nb1, nb2;
+    int ab_dtype, c_dtype, act, accumulate;
+    float alpha, beta;
+    float drop_p; unsigned long long drop_seed;
+    float a_drop_p; unsigned long long a_drop_seed;
+} sarssl_gemm_args;
+/* CUDA-core kernel (exact fp32 when ab_dtype is F32): any shape / stride. */
+int sarssl_gemm(const sarssl_gemm_args* args, cudaStream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A7-A10  memory-bound Conformer pieces.  `dtype` = storage type of the activation tensors (SARSSL_F32 / SARSSL_BF16);
+ * parameters, statistics and parameter gradients are always fp32; gradients of parameters are ACCUMULATED (+=).
+ * Reduction workspaces: sarssl_reduce_workspace_bytes(cols) bytes.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t sarssl_reduce_workspace_bytes(int cols);
+
+/* nn.LayerNorm (eps 1e-5)        conformer/feed_forward.py:40, attention.py:139, convolution.py:137, Conformer.py:87
+ *   x rows at stride ldx, out rows at stride ldo (lets the final LayerNorm write into the concatenated decoder input);
+ *   mean/rstd (rows) fp32 are saved for the backward (nullable for inference). */
+int sarssl_layernorm_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo, float* mean,
+                         float* rstd, int rows, int cols, float eps, int dtype, cudaStream_t stream);
+/*   dx = add + dLN(dy)   (add nullable: the residual branch's gradient; dx/add contiguous [rows][cols]) */
+int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* mean, const float* rstd,
+                         const float* gamma, const void* add, void* dx, float* dgamma, float* dbeta, int rows, int cols, int dtype,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* out[c] (+)= sum_r x[r][c]      (bias gradients, u/v bias gradients) */
+int sarssl_colsum(const void* x, long long ldx, float* out, int rows, int cols, int dtype, int accumulate, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+
+/* nn.BatchNorm2d / nn.BatchNorm1d over channel-last data [rows][C]      model.py:52-62, conformer/convolution.py:141
+ *   training != 0: batch statistics (biased variance) + running-stat update (momentum, unbiased variance, counter);
+ *   training == 0: running statistics.  stats = 4*C floats: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale. */
+int sarssl_batchnorm_stats(const void* y, long long rows, int C, const float* gamma, const float* beta, float eps, float momentum,
+                           float* running_mean, float* running_var, long long* num_batches_tracked, float* stats, int training, int dtype,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/*   z = act(y*scale + shift), act: SARSSL_ACT_RELU (stem) / SARSSL_ACT_SWISH (conv module) / NONE */
+int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int act, void* z, long long rows, int C, int dtype, cudaStream_t stream);
+/*   dz -> dy through the activation and the batch-statistics normalisation; dgamma/dbeta accumulated */
+int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const float* stats, int act, void* dy, float* dgamma, float* dbeta,
+                             long long rows, int C, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* Swish / ReLU / GLU gradients and GLU forward                              conformer/activation.py:19-42
+ *   swish_bwd: du = ds * dropout_mask(offset)/(1-p) * swish'(u)  (regenerates the FFN dropout mask, feed_forward.py:51) */
+int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, int dtype,
+                     cudaStream_t stream);
+/*   dst = alpha * src * dropout_mask(offset)/(1-p): gradient of `x + alpha*Dropout(v)` w.r.t. v (modules.py:33 + the Dropout sites) */
+int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, int dtype,
+                         cudaStream_t stream);
+int sarssl_relu_bwd(const void* dz, const void* z, void* dy, long long n, int dtype, cudaStream_t stream);
+int sarssl_glu_fwd(const void* g, void* a, long long rows, int D, int dtype, cudaStream_t stream);
+int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long rows, int D, int dtype, cudaStream_t stream);
+
+/* relative-position attention glue                                         conformer/attention.py:87-97,105-113
+ *   add_head_bias: qu = q + u_bias, qv = q + v_bias (q = first D columns of rows with stride ld)
+ *   attn_softmax_fwd: prob[b][h][i][:] = softmax_j((content[b][h][i][j] + shift(pos[h][b])[i][j]) * scale)
+ *   attn_softmax_bwd: dattn (in place) -> dscore; dpos[h][b] = inverse shift of dscore; dropout mask regenerated */
+int sarssl_add_head_bias(const void* q, long long ld, const float* u_bias, const float* v_bias, void* qu, void* qv, long long rows, int D,
+                         int dtype, cudaStream_t stream);
+int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, int B, int H, int T, float scale, int dtype,
+                            cudaStream_t stream);
+int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void* dpos, int B, int H, int T, float scale, float drop_p,
+                            unsigned long long seed, int dtype, cudaStream_t stream);
+int sarssl_add2(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int cols, int dtype,
+                cudaStream_t stream);
+
+/* depthwise Conv1d over time, channel-last [B][T][D], weight (D, K) fp32, K odd <= 31      conformer/convolution.py:140
+ *   flip = 0: forward; flip = 1: input gradient (mirrored taps).  wgrad accumulates into dweight. */
+int sarssl_dwconv(const void* in, const float* weight, void* out, int B, int T, int D, int K, int flip, int dtype, cudaStream_t stream);
+size_t sarssl_dwconv_wgrad_workspace_bytes(int D, int K);
+int sarssl_dwconv_wgrad(const void* a, const void* dc, float* dweight, int B, int T, int D, int K, int dtype, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+
+/* utilities: dtype cast, 4-d permuting copy (weight packing / gradient un-packing), fill */
+int sarssl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t stream);
+int sarssl_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims4_host, const long long* src_strides4_host,
+                    int accumulate, cudaStream_t stream);
+int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A6  CNN patch-embedding stem on channel-last images [B][H = frame][W = bin][C]      model.py:50-64,203-208
+ * ---------------------------------------------------------------------------------------------------------- */
+/* 1x1 conv 4 -> 64.  mode 0: `in` is [P][4] of `dtype`; mode 1 / 2: `in` is the fp32 patch tensor and the spectral /
+ * spatial input masking of model.py:541 / :563 is applied on load (frame_flag (B,H) uint8, ch_idx (B) int32). */
+int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
+                       long long P, int W, int H, int dtype, cudaStream_t stream);
+/* 1x1 conv 64 -> 4 with optional BatchNorm+ReLU of the input applied on load (in_scale/in_shift nullable) */
+int sarssl_stem_reduce(const void* in, const float* in_scale, const float* in_shift, const float* weight4x64, void* out, long long P,
+                       int dtype, cudaStream_t stream);
+size_t sarssl_stem_workspace_bytes(void);
+/* dW[o][c] (64x4) (+)= sum_p f(wide[p][o]) * narrow[p][c];  f = ReLU(BN) when wide_scale given; narrow loaded like stem_expand */
+int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, const float* wide_shift, const void* narrow, int mode,
+                         const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
+                         int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* 3x3 conv 64 -> 64, padding 1, as implicit GEMM; weight_packed [n][tap = (dh+1)*3 + (dw+1)][ci] in `dtype`;
+ * BatchNorm+ReLU of the INPUT applied on load when in_scale given (zero padding stays zero). */
+int sarssl_conv3x3(const void* in, const float* in_scale, const float* in_shift, const void* weight_packed, void* out, int B, int H, int W,
+                   int dtype, cudaStream_t stream);
+int sarssl_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dweight_packed, int accumulate,
+                         int B, int H, int W, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * A14  optimizer: torch.optim.Adam(betas (0.9, 0.999), eps 1e-8, wd 0) over flat fp32 arenas      learner.py:83,111-113
+ * ---------------------------------------------------------------------------------------------------------- */
+/* g is multiplied by grad_scale first; param_bf16 (nullable) receives the refreshed bf16 copy; zero_grad != 0 clears g. */
+int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n, int step, float lr,
+                     float beta1, float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

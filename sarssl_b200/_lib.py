@@ -1,53 +1,83 @@
-"""ctypes loader for libsarssl_b200.so (the C ABI declared in include/sarssl_b200.h).
-
-There is no fallback of any kind: if the shared library is missing the import of any compute op raises, and every
-entry point that launches a kernel raises SarsslError on a non-zero return code."""
+"""ctypes loader for libsarssl_b200.so.  Prototypes are parsed from include/sarssl_b200.h, the single source of truth
+for the C ABI.  There is no fallback of any kind: if the shared library is missing, importing any compute op raises, and
+every entry point that launches a kernel raises SarsslError on a non-zero return code."""
 import ctypes as C
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsarssl_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "sarssl_b200.h")
 
 F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
 
 
 class SarsslError(RuntimeError):
     pass
 
 
+class GemmArgs(C.Structure):
+    """struct sarssl_gemm_args (include/sarssl_b200.h)."""
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("pre_out", C.c_void_p), ("resid", C.c_void_p), ("bias", C.c_void_p),
+                ("sAm", C.c_longlong), ("sAk", C.c_longlong), ("sAb1", C.c_longlong), ("sAb2", C.c_longlong),
+                ("sBn", C.c_longlong), ("sBk", C.c_longlong), ("sBb1", C.c_longlong), ("sBb2", C.c_longlong),
+                ("ldc", C.c_longlong), ("sCb1", C.c_longlong), ("sCb2", C.c_longlong), ("ldr", C.c_longlong),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("nb1", C.c_int), ("nb2", C.c_int),
+                ("ab_dtype", C.c_int), ("c_dtype", C.c_int), ("act", C.c_int), ("accumulate", C.c_int),
+                ("alpha", C.c_float), ("beta", C.c_float),
+                ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
+                ("a_drop_p", C.c_float), ("a_drop_seed", C.c_ulonglong)]
+
+
+_SCALARS = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t,
+            "unsigned long long": C.c_ulonglong, "cudaStream_t": C.c_void_p}
+
+
+def _ctype(decl):
+    decl = decl.strip()
+    if decl in ("void", ""):
+        return None
+    if "*" in decl:
+        return C.c_char_p if decl.replace(" ", "") == "constchar*" else C.c_void_p
+    words = decl.replace("const ", "").split()
+    if len(words) > 1 and " ".join(words) not in _SCALARS:
+        words = words[:-1]                       # drop the parameter name
+    key = " ".join(words)
+    if key not in _SCALARS:
+        raise SarsslError(f"cannot map C type '{decl}'")
+    return _SCALARS[key]
+
+
+def parse_header(path=HEADER):
+    """{name: (restype, [argtypes])} for every `sarssl_*` function declared in the public header."""
+    src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+    src = re.sub(r"typedef struct sarssl_gemm_args \{.*?\} sarssl_gemm_args;", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z_ \*]*?)\b(sarssl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+        restype = _ctype(ret if "*" in ret else ret + " x") if ret != "const char*" else C.c_char_p
+        if ret.replace(" ", "") == "constchar*":
+            restype = C.c_char_p
+        argtypes = [t for t in (_ctype(a) for a in args.split(",")) if t is not None]
+        protos[name] = (restype, argtypes)
+    return protos
+
+
 _lib = None
-
-_vp, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
-
-# name -> (restype, argtypes); mirrors include/sarssl_b200.h one to one (tests/test_abi.py checks the header)
-PROTOTYPES = {
-    "sarssl_version": (_i, []),
-    "sarssl_last_error": (C.c_char_p, []),
-    "sarssl_stft_num_frames": (_i, [_ll, _i, _i]),
-    "sarssl_stft_spectrum": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _vp]),
-    "sarssl_stft_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
-    "sarssl_stft_frontend": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "sarssl_stft_frontend_error_flag": (_i, [_vp, C.POINTER(_i), _vp]),
-    "sarssl_istft": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _vp]),
-    "sarssl_mt19937_seed_host": (_i, [_vp, _vp, _i]),
-    "sarssl_mt19937_draw_masks_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "sarssl_expand_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "sarssl_to_patch_layout": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "sarssl_masked_loss_workspace_bytes": (_sz, [_i, _i]),
-    "sarssl_masked_loss": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
-    "sarssl_scale_masked_rows": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp]),
-}
+PROTOTYPES = None
 
 
 def lib():
-    global _lib
+    global _lib, PROTOTYPES
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise SarsslError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(sarssl_b200 has no CPU or PyTorch fallback)")
         l = C.CDLL(LIB_PATH)
+        PROTOTYPES = parse_header()
         for name, (res, args) in PROTOTYPES.items():
-            fn = getattr(l, name)
+            fn = getattr(l, name)          # AttributeError here = header declares something the library lacks
             fn.restype, fn.argtypes = res, args
         _lib = l
     return _lib
@@ -70,11 +100,12 @@ def ptr(t):
 
 def dtype_code(t):
     import torch
-    if t.dtype == torch.float32:
+    dt = t if isinstance(t, torch.dtype) else t.dtype
+    if dt == torch.float32:
         return F32
-    if t.dtype == torch.bfloat16:
+    if dt == torch.bfloat16:
         return BF16
-    raise SarsslError(f"unsupported dtype {t.dtype}")
+    raise SarsslError(f"unsupported dtype {dt}")
 
 
 def require_cuda(t, name):

@@ -1,0 +1,326 @@
+// Element-wise / row-wise kernels of the Conformer blocks (memory-bound): Swish/ReLU/GLU gradients, relative-position
+// score assembly + softmax (+ its backward and the inverse shift), head-bias adds, strided adds, dtype casts and a
+// small N-d permute used to pack weights for the GEMM-shaped kernels.
+//   Swish / GLU               conformer/activation.py:19-42
+//   relative shift + softmax  conformer/attention.py:87-97,105-113 (scale 1/sqrt(d_model), attention.py:57,91)
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace sarssl {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// du = ds * dropmask(idx)/(1-p) * swish'(u)      (FFN: s = Dropout(Swish(u)), feed_forward.py:49-51)
+template <typename T>
+__global__ void swish_bwd_kernel(const T* __restrict__ ds, const T* __restrict__ u, T* __restrict__ du, long long n, float drop_p,
+                                 unsigned long long seed) {
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float d = to_f32(ds[i]);
+        if (drop_p > 0.f) d = keep_mask(seed, (unsigned long long)i, drop_p) ? d * ks : 0.f;
+        const float x = to_f32(u[i]), sg = sigmoidf_(x);
+        du[i] = from_f32<T>(d * sg * (1.0f + x * (1.0f - sg)));
+    }
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, T* __restrict__ dy, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dy[i] = to_f32(z[i]) > 0.f ? dz[i] : from_f32<T>(0.f);
+}
+
+// a[m][d] = g[m][d] * sigmoid(g[m][D + d])         (GLU over channels, convolution.py:139)
+template <typename T>
+__global__ void glu_fwd_kernel(const T* __restrict__ g, T* __restrict__ a, long long rows, int D) {
+    const long long n = rows * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / D; const int d = (int)(i - m * D);
+        a[i] = from_f32<T>(to_f32(g[m * 2 * D + d]) * sigmoidf_(to_f32(g[m * 2 * D + D + d])));
+    }
+}
+template <typename T>
+__global__ void glu_bwd_kernel(const T* __restrict__ da, const T* __restrict__ g, T* __restrict__ dg, long long rows, int D) {
+    const long long n = rows * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / D; const int d = (int)(i - m * D);
+        const float x = to_f32(g[m * 2 * D + d]), gt = to_f32(g[m * 2 * D + D + d]), sg = sigmoidf_(gt), dd = to_f32(da[i]);
+        dg[m * 2 * D + d] = from_f32<T>(dd * sg);
+        dg[m * 2 * D + D + d] = from_f32<T>(dd * x * sg * (1.0f - sg));
+    }
+}
+
+// qu = q + u_bias, qv = q + v_bias; q = first D columns of qkv rows (ld)        attention.py:87-88
+template <typename T>
+__global__ void add_head_bias_kernel(const T* __restrict__ q, long long ld, const float* __restrict__ u, const float* __restrict__ v,
+                                     T* __restrict__ qu, T* __restrict__ qv, long long rows, int D) {
+    const long long n = rows * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / D; const int d = (int)(i - m * D);
+        const float x = to_f32(q[m * ld + d]);
+        qu[i] = from_f32<T>(x + u[d]);
+        qv[i] = from_f32<T>(x + v[d]);
+    }
+}
+
+// out[m][c] (ldo) = a[m][c] (lda) + b[m][c] (ldb)
+template <typename T>
+__global__ void add2_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out, long long ldo,
+                            long long rows, int cols) {
+    const long long n = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / cols; const int c = (int)(i - m * cols);
+        out[m * ldo + c] = from_f32<T>(to_f32(a[m * lda + c]) + to_f32(b[m * ldb + c]));
+    }
+}
+
+// ---- relative-position scores: prob[b][h][i][:] = softmax_j( (content[b][h][i][j] + shift(pos)[i][j]) * scale )
+// content [B][H][T][T], pos [H][B][T][T];  shift: j <= i -> pos[i][T-1-i+j];  j == i+1 -> 0;  j > i+1 -> pos[i+1][j-i-2]
+// one warp per score row
+template <typename T>
+__global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const T* __restrict__ content, const T* __restrict__ pos, T* __restrict__ prob,
+                                                             int B, int H, int Tn, float scale) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= (long long)B * H * Tn) return;
+    const int i = (int)(row % Tn);
+    const long long bh = row / Tn;
+    const int h = (int)(bh % H), b = (int)(bh / H);
+    const T* crow = content + row * Tn;
+    const T* pbase = pos + ((long long)h * B + b) * Tn * Tn;
+    float mx = -INFINITY;
+    for (int j = lane; j < Tn; j += 32) {
+        float ps = 0.f;
+        if (j <= i) ps = to_f32(pbase[(long long)i * Tn + (Tn - 1 - i + j)]);
+        else if (j > i + 1) ps = to_f32(pbase[(long long)(i + 1) * Tn + (j - i - 2)]);
+        mx = fmaxf(mx, (to_f32(crow[j]) + ps) * scale);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Tn; j += 32) {
+        float ps = 0.f;
+        if (j <= i) ps = to_f32(pbase[(long long)i * Tn + (Tn - 1 - i + j)]);
+        else if (j > i + 1) ps = to_f32(pbase[(long long)(i + 1) * Tn + (j - i - 2)]);
+        sum += __expf((to_f32(crow[j]) + ps) * scale - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    T* orow = prob + row * Tn;
+    for (int j = lane; j < Tn; j += 32) {
+        float ps = 0.f;
+        if (j <= i) ps = to_f32(pbase[(long long)i * Tn + (Tn - 1 - i + j)]);
+        else if (j > i + 1) ps = to_f32(pbase[(long long)(i + 1) * Tn + (j - i - 2)]);
+        orow[j] = from_f32<T>(__expf((to_f32(crow[j]) + ps) * scale - mx) * inv);
+    }
+}
+
+// dscore = scale * P * (dP - sum_j dP*P),  dP = dattn * dropmask/(1-p);  in place over dattn
+template <typename T>
+__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(T* __restrict__ dattn, const T* __restrict__ prob, long long rows, int Tn,
+                                                             float scale, float drop_p, unsigned long long seed) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    T* drow = dattn + row * Tn;
+    const T* prow = prob + row * Tn;
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    float dot = 0.f;
+    for (int j = lane; j < Tn; j += 32) {
+        float d = to_f32(drow[j]);
+        if (drop_p > 0.f) d = keep_mask(seed, (unsigned long long)(row * Tn + j), drop_p) ? d * ks : 0.f;
+        dot += d * to_f32(prow[j]);
+    }
+    dot = warp_sum(dot);
+    for (int j = lane; j < Tn; j += 32) {
+        float d = to_f32(drow[j]);
+        if (drop_p > 0.f) d = keep_mask(seed, (unsigned long long)(row * Tn + j), drop_p) ? d * ks : 0.f;
+        drow[j] = from_f32<T>(scale * to_f32(prow[j]) * (d - dot));
+    }
+}
+
+// inverse of the shift: dpos[h][b][r][k] = k >= T-1-r ? dscore[b][h][r][k-(T-1-r)] : (r >= 1 ? dscore[b][h][r-1][k+r+1] : 0)
+template <typename T>
+__global__ void attn_unshift_kernel(const T* __restrict__ dscore, T* __restrict__ dpos, int B, int H, int Tn) {
+    const long long n = (long long)B * H * Tn * Tn;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % Tn);
+        long long r_ = idx / Tn;
+        const int r = (int)(r_ % Tn); r_ /= Tn;
+        const int b = (int)(r_ % B), h = (int)(r_ / B);
+        const T* base = dscore + ((long long)b * H + h) * Tn * Tn;
+        T v = from_f32<T>(0.f);
+        if (k >= Tn - 1 - r) v = base[(long long)r * Tn + (k - (Tn - 1 - r))];
+        else if (r >= 1) v = base[(long long)(r - 1) * Tn + (k + r + 1)];
+        dpos[idx] = v;
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = from_f32<TD>(to_f32(src[i]));
+}
+
+// dst (contiguous over dims d0..d3) [+]= src[i0*s0 + i1*s1 + i2*s2 + i3*s3]
+template <typename TS, typename TD>
+__global__ void permute4_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int d0, int d1, int d2, int d3, long long s0, long long s1,
+                                long long s2, long long s3, int accumulate) {
+    const long long n = (long long)d0 * d1 * d2 * d3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int i3 = (int)(i % d3); long long r = i / d3;
+        const int i2 = (int)(r % d2); r /= d2;
+        const int i1 = (int)(r % d1); const int i0 = (int)(r / d1);
+        const float v = to_f32(src[i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3]);
+        dst[i] = from_f32<TD>(accumulate ? to_f32(dst[i]) + v : v);
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static int ew_grid(long long n) {
+    long long g = (n + 1023) / 1024;
+    const long long cap = (long long)sm_count() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sarssl
+
+using namespace sarssl;
+
+#define DISPATCH_T(dtype, ...)                                                         \
+    do {                                                                               \
+        if ((dtype) == SARSSL_F32) { using T = float; __VA_ARGS__; }                   \
+        else if ((dtype) == SARSSL_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }     \
+        else { set_last_error("bad dtype %d", (int)(dtype)); return SARSSL_ERR_ARG; }  \
+    } while (0)
+
+extern "C" int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, int dtype,
+                                cudaStream_t stream) {
+    SARSSL_CHECK_ARG(ds && u && du && n > 0, "swish_bwd: bad arguments");
+    DISPATCH_T(dtype, (swish_bwd_kernel<T><<<ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(ds), static_cast<const T*>(u), static_cast<T*>(du), n,
+                                                                          drop_p, seed)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_relu_bwd(const void* dz, const void* z, void* dy, long long n, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dz && z && dy && n > 0, "relu_bwd: bad arguments");
+    DISPATCH_T(dtype, (relu_bwd_kernel<T><<<ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(dz), static_cast<const T*>(z), static_cast<T*>(dy), n)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_glu_fwd(const void* g, void* a, long long rows, int D, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(g && a && rows > 0 && D > 0, "glu_fwd: bad arguments");
+    DISPATCH_T(dtype, (glu_fwd_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(g), static_cast<T*>(a), rows, D)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long rows, int D, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(da && g && dg && rows > 0 && D > 0, "glu_bwd: bad arguments");
+    DISPATCH_T(dtype, (glu_bwd_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(da), static_cast<const T*>(g), static_cast<T*>(dg),
+                                                                               rows, D)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_add_head_bias(const void* q, long long ld, const float* u_bias, const float* v_bias, void* qu, void* qv, long long rows, int D,
+                                    int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(q && u_bias && v_bias && qu && qv && rows > 0 && D > 0, "add_head_bias: bad arguments");
+    DISPATCH_T(dtype, (add_head_bias_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(q), ld, u_bias, v_bias, static_cast<T*>(qu),
+                                                                                     static_cast<T*>(qv), rows, D)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_add2(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int cols, int dtype,
+                           cudaStream_t stream) {
+    SARSSL_CHECK_ARG(a && b && out && rows > 0 && cols > 0, "add2: bad arguments");
+    DISPATCH_T(dtype, (add2_kernel<T><<<ew_grid(rows * cols), 256, 0, stream>>>(static_cast<const T*>(a), lda, static_cast<const T*>(b), ldb,
+                                                                               static_cast<T*>(out), ldo, rows, cols)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, int B, int H, int T_, float scale, int dtype,
+                                       cudaStream_t stream) {
+    SARSSL_CHECK_ARG(content && pos && prob && B > 0 && H > 0 && T_ > 0, "attn_softmax_fwd: bad arguments");
+    const long long rows = (long long)B * H * T_;
+    DISPATCH_T(dtype, (attn_softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(content), static_cast<const T*>(pos),
+                                                                                                static_cast<T*>(prob), B, H, T_, scale)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void* dpos, int B, int H, int T_, float scale, float drop_p,
+                                       unsigned long long seed, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dattn_inout && prob && dpos && B > 0 && H > 0 && T_ > 0, "attn_softmax_bwd: bad arguments");
+    const long long rows = (long long)B * H * T_;
+    DISPATCH_T(dtype, (attn_softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout), static_cast<const T*>(prob),
+                                                                                                rows, T_, scale, drop_p, seed)));
+    SARSSL_LAUNCH_CHECK();
+    DISPATCH_T(dtype, (attn_unshift_kernel<T><<<ew_grid(rows * T_), 256, 0, stream>>>(static_cast<const T*>(dattn_inout), static_cast<T*>(dpos), B, H, T_)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(src && dst && n > 0, "cast: bad arguments");
+    const int g = ew_grid(n);
+    if (src_dtype == SARSSL_F32 && dst_dtype == SARSSL_BF16) cast_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    else if (src_dtype == SARSSL_BF16 && dst_dtype == SARSSL_F32) cast_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    else if (src_dtype == SARSSL_F32 && dst_dtype == SARSSL_F32) cast_kernel<float, float><<<g, 256, 0, stream>>>((const float*)src, (float*)dst, n);
+    else cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims4_host, const long long* src_strides4_host,
+                               int accumulate, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(src && dst && dims4_host && src_strides4_host, "permute4: null pointer");
+    const int* d = dims4_host; const long long* s = src_strides4_host;
+    const long long n = (long long)d[0] * d[1] * d[2] * d[3];
+    SARSSL_CHECK_ARG(n > 0, "permute4: empty");
+    const int g = ew_grid(n);
+    if (src_dtype == SARSSL_F32 && dst_dtype == SARSSL_BF16)
+        permute4_kernel<float, __nv_bfloat16><<<g, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, d[0], d[1], d[2], d[3], s[0], s[1], s[2], s[3], accumulate);
+    else if (src_dtype == SARSSL_BF16 && dst_dtype == SARSSL_F32)
+        permute4_kernel<__nv_bfloat16, float><<<g, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, d[0], d[1], d[2], d[3], s[0], s[1], s[2], s[3], accumulate);
+    else if (src_dtype == SARSSL_F32 && dst_dtype == SARSSL_F32)
+        permute4_kernel<float, float><<<g, 256, 0, stream>>>((const float*)src, (float*)dst, d[0], d[1], d[2], d[3], s[0], s[1], s[2], s[3], accumulate);
+    else
+        permute4_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, d[0], d[1], d[2], d[3], s[0], s[1], s[2], s[3], accumulate);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(p && n > 0, "fill: bad arguments");
+    fill_f32_kernel<<<ew_grid(n), 256, 0, stream>>>(p, value, n);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+namespace sarssl {
+// dst = alpha * src * dropout_mask(offset)/(1-p): re-applies a forward dropout mask to the incoming gradient
+template <typename T>
+__global__ void scale_dropout_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n, float alpha, float drop_p, unsigned long long seed) {
+    const float ks = drop_p > 0.f ? alpha / (1.0f - drop_p) : alpha;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = to_f32(src[i]);
+        v = (drop_p > 0.f && !keep_mask(seed, (unsigned long long)i, drop_p)) ? 0.f : v * ks;
+        dst[i] = from_f32<T>(v);
+    }
+}
+}  // namespace sarssl
+
+extern "C" int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, int dtype,
+                                    cudaStream_t stream) {
+    SARSSL_CHECK_ARG(src && dst && n > 0, "scale_dropout: bad arguments");
+    DISPATCH_T(dtype, (sarssl::scale_dropout_kernel<T><<<sarssl::ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(src), static_cast<T*>(dst), n, alpha,
+                                                                                             drop_p, seed)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}

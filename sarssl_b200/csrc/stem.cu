@@ -1,0 +1,342 @@
+// CNN patch-embedding stem (model.py:50-64) on channel-last images [B][H = frame][W = bin][C] - CUDA-core kernels.
+//   1x1 conv 4 -> 64 with the spectral / spatial input masking of model.py:541,563 fused into the load,
+//   3x3 conv 64 -> 64 as an implicit GEMM (K = 9 taps x 64 channels) with the previous layer's BatchNorm + ReLU applied
+//   while the operand tile is loaded (zero padding stays zero), its data gradient (same kernel, mirrored weights) and
+//   its weight gradient (split-K over pixels, fixed-order reduction), and the 1x1 conv 64 -> 4.
+// These are the exact-fp32 / reference-check versions; the bf16 tensor-core versions live in conv_tc.cu.
+#include "common.cuh"
+
+namespace sarssl {
+
+// ---- input loader shared by the narrow (4-channel) kernels ---------------------------------------------------------
+// mode 0: plain [P][4] tensor of type T.  mode 1 / 2: fp32 patches (re0, re1, im0, im1) with the spectral / spatial mask:
+//   spectral: masked frame -> keep only the un-masked microphone; other frames -> keep only the masked microphone
+//   spatial : masked frame -> zeros; other frames -> both microphones
+template <typename T>
+__device__ __forceinline__ float4 load_narrow(const void* in, long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
+    if (mode == 0) {
+        const T* q = static_cast<const T*>(in) + p * 4;
+        return make_float4(to_f32(q[0]), to_f32(q[1]), to_f32(q[2]), to_f32(q[3]));
+    }
+    float4 x = *reinterpret_cast<const float4*>(static_cast<const float*>(in) + p * 4);
+    const long long row = p / W;
+    const bool pm = flag[row] != 0;
+    const int mc = ch[row / H];
+    if (mode == 1) {
+        const int keep = pm ? 1 - mc : mc;
+        if (keep == 0) { x.y = 0.f; x.w = 0.f; } else { x.x = 0.f; x.z = 0.f; }
+    } else if (pm) x = make_float4(0.f, 0.f, 0.f, 0.f);
+    return x;
+}
+
+// out[p][o] = sum_c W[o][c] * in[p][c],  o < 64.  8 threads per pixel, 8 channels each.
+template <typename T>
+__global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__ in, int mode, const uint8_t* __restrict__ flag,
+                                                      const int32_t* __restrict__ ch, const float* __restrict__ Wt, T* __restrict__ out,
+                                                      long long P, int W, int H) {
+    __shared__ float ws[64][4];
+    if (threadIdx.x < 256) ws[threadIdx.x >> 2][threadIdx.x & 3] = Wt[threadIdx.x];
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (long long)gridDim.x * 32) {
+        const float4 x = load_narrow<T>(in, p, mode, flag, ch, W, H);
+        T* o = out + p * 64 + sub * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* w = ws[sub * 8 + j];
+            o[j] = from_f32<T>(w[0] * x.x + w[1] * x.y + w[2] * x.z + w[3] * x.w);
+        }
+    }
+}
+
+// out[p][c] = sum_o W[c][o] * f(in[p][o]),  f = relu(in*scale+shift) when stats given
+template <typename T>
+__global__ void __launch_bounds__(256) pw_reduce_kernel(const T* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      const float* __restrict__ Wt, T* __restrict__ out, long long P) {
+    __shared__ float ws[4][64];
+    __shared__ float sc[64], sh[64];
+    ws[threadIdx.x >> 6][threadIdx.x & 63] = Wt[threadIdx.x];
+    if (threadIdx.x < 64) { sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f; sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f; }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const bool tr = scale != nullptr;
+    const long long iters = (P + (long long)gridDim.x * 32 - 1) / ((long long)gridDim.x * 32);
+    for (long long it = 0; it < iters; ++it) {
+        const long long p = ((long long)it * gridDim.x + blockIdx.x) * 32 + (threadIdx.x >> 3);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (p < P) {
+            const T* q = in + p * 64 + sub * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int o = sub * 8 + j;
+                float v = to_f32(q[j]);
+                if (tr) v = fmaxf(v * sc[o] + sh[o], 0.f);
+                a0 = fmaf(ws[0][o], v, a0); a1 = fmaf(ws[1][o], v, a1); a2 = fmaf(ws[2][o], v, a2); a3 = fmaf(ws[3][o], v, a3);
+            }
+        }
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, s); a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, s); a3 += __shfl_xor_sync(0xffffffffu, a3, s);
+        }
+        if (p < P && sub == 0) {
+            T* o = out + p * 4;
+            o[0] = from_f32<T>(a0); o[1] = from_f32<T>(a1); o[2] = from_f32<T>(a2); o[3] = from_f32<T>(a3);
+        }
+    }
+}
+
+// partial[cta][o][c] = sum_{p in cta} f(wide[p][o]) * narrow[p][c]
+template <typename T>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wide, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                     const void* __restrict__ narrow, int mode, const uint8_t* __restrict__ flag,
+                                                     const int32_t* __restrict__ ch, float* __restrict__ partials, long long P, int W, int H) {
+    __shared__ float red[32][8][33];
+    const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const bool tr = scale != nullptr;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = tr ? scale[sub * 8 + j] : 1.f; sh[j] = tr ? shift[sub * 8 + j] : 0.f; }
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    for (long long p = (long long)blockIdx.x * 32 + pl; p < P; p += (long long)gridDim.x * 32) {
+        const float4 x = load_narrow<T>(narrow, p, mode, flag, ch, W, H);
+        const T* q = wide + p * 64 + sub * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = to_f32(q[j]);
+            if (tr) v = fmaxf(v * sc[j] + sh[j], 0.f);
+            acc[j][0] = fmaf(v, x.x, acc[j][0]); acc[j][1] = fmaf(v, x.y, acc[j][1]);
+            acc[j][2] = fmaf(v, x.z, acc[j][2]); acc[j][3] = fmaf(v, x.w, acc[j][3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[pl][sub][j * 4 + c] = acc[j][c];
+    __syncthreads();
+    // 256 outputs (o, c): thread t sums over the 32 pixel lanes
+    {
+        const int o = threadIdx.x >> 2, c = threadIdx.x & 3;
+        float s = 0.f;
+        for (int q = 0; q < 32; ++q) s += red[q][o >> 3][(o & 7) * 4 + c];
+        partials[(size_t)blockIdx.x * 256 + threadIdx.x] = s;
+    }
+}
+
+__global__ void stem_reduce_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out, int accumulate) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= width) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * width + w];
+    out[w] = accumulate ? out[w] + (float)s : (float)s;
+}
+
+// ---- 3x3 conv as implicit GEMM: out[p][n] = sum_{tap, ci} f(in[p + tap][ci]) * Wp[n][tap*64 + ci] -------------------------------
+constexpr int CM = 64, CN = 64, CK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv3x3_kernel(const T* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    const T* __restrict__ Wp, T* __restrict__ out, long long P, int H, int W) {
+    __shared__ __align__(16) float As[CK][CM + 4];
+    __shared__ __align__(16) float Bs[CK][CN + 4];
+    __shared__ int ph[CM], pw[CM];
+    __shared__ long long pbase[CM];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long p0 = (long long)blockIdx.x * CM;
+    if (tid < CM) {
+        const long long p = p0 + tid;
+        if (p < P) { pw[tid] = (int)(p % W); ph[tid] = (int)((p / W) % H); pbase[tid] = p; } else { pw[tid] = -100000; ph[tid] = -100000; pbase[tid] = 0; }
+    }
+    __syncthreads();
+    const bool tr = scale != nullptr;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < 576; k0 += CK) {
+        const int tap = k0 >> 6, dh = tap / 3 - 1, dw = tap % 3 - 1, c0 = k0 & 63;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            const int kk = idx & 15, mm = idx >> 4;
+            const int h = ph[mm] + dh, w = pw[mm] + dw;
+            float v = 0.f;
+            if (h >= 0 && h < H && w >= 0 && w < W) {
+                const int ci = c0 + kk;
+                v = to_f32(in[(pbase[mm] + (long long)dh * W + dw) * 64 + ci]);
+                if (tr) v = fmaxf(v * scale[ci] + shift[ci], 0.f);
+            }
+            As[kk][mm] = v;
+            Bs[kk][mm] = to_f32(Wp[(long long)mm * 576 + k0 + kk]);          // here mm plays the role of n
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long p = p0 + ty * 4 + i;
+        if (p >= P) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[p * 64 + tx * 4 + j] = from_f32<T>(acc[i][j]);
+    }
+}
+
+// weight gradient: partial[split][o][tap*64+ci] = sum_{p in split} dy[p][o] * f(z_in[p + tap][ci]);  grid (9 taps, splits)
+template <typename T>
+__global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ in, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float* __restrict__ partials, long long P, int H, int W,
+                                                          long long pix_per_split) {
+    __shared__ __align__(16) float As[CK][CM + 4];     // [pixel kk][o]
+    __shared__ __align__(16) float Bs[CK][CN + 4];     // [pixel kk][ci]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tap = blockIdx.x, dh = tap / 3 - 1, dw = tap % 3 - 1;
+    const long long pbeg = (long long)blockIdx.y * pix_per_split;
+    long long pend = pbeg + pix_per_split;
+    if (pend > P) pend = P;
+    const bool tr = scale != nullptr;
+    const int cc = tid & 63;
+    const float sc = tr ? scale[cc] : 1.f, sh = tr ? shift[cc] : 0.f;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (long long k0 = pbeg; k0 < pend; k0 += CK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            const int c = idx & 63, kk = idx >> 6;            // c == cc for every i
+            const long long p = k0 + kk;
+            float a = 0.f, b = 0.f;
+            if (p < pend) {
+                a = to_f32(dy[p * 64 + c]);
+                const int w = (int)(p % W) + dw, h = (int)((p / W) % H) + dh;
+                if (h >= 0 && h < H && w >= 0 && w < W) {
+                    b = to_f32(in[(p + (long long)dh * W + dw) * 64 + c]);
+                    if (tr) b = fmaxf(b * sc + sh, 0.f);
+                }
+            }
+            As[kk][c] = a;
+            Bs[kk][c] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* dst = partials + (size_t)blockIdx.y * 64 * 576;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[(size_t)(ty * 4 + i) * 576 + tap * 64 + tx * 4 + j] = acc[i][j];
+}
+
+static int pix_grid(long long P) {
+    long long g = (P + 31) / 32;
+    const long long cap = (long long)sm_count() * 8;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace sarssl
+
+using namespace sarssl;
+
+extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
+                                  long long P, int W, int H, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0, "stem_expand: bad arguments");
+    SARSSL_CHECK_ARG(mode == 0 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
+    if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
+    else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
+    else { set_last_error("stem_expand: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stem_reduce(const void* in, const float* in_scale, const float* in_shift, const float* weight4x64, void* out, long long P,
+                                  int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(in && weight4x64 && out && P > 0, "stem_reduce: bad arguments");
+    if (dtype == SARSSL_F32) pw_reduce_kernel<float><<<pix_grid(P), 256, 0, stream>>>((const float*)in, in_scale, in_shift, weight4x64, (float*)out, P);
+    else if (dtype == SARSSL_BF16) pw_reduce_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>((const __nv_bfloat16*)in, in_scale, in_shift, weight4x64, (__nv_bfloat16*)out, P);
+    else { set_last_error("stem_reduce: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" size_t sarssl_stem_workspace_bytes(void) {
+    const size_t a = (size_t)sm_count() * 8 * 256 * sizeof(float);           // pw_wgrad partials
+    const size_t b = (size_t)sm_count() * 2 * 64 * 576 * sizeof(float);      // conv3x3 wgrad partials
+    return a > b ? a : b;
+}
+
+// dW[o][c] (64 x 4, row-major) (+)= sum_p f(wide[p][o]) * narrow[p][c]
+extern "C" int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, const float* wide_shift, const void* narrow, int mode,
+                                    const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
+                                    int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0, "stem_pw_wgrad: bad arguments");
+    const int grid = pix_grid(P);
+    if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    float* partials = static_cast<float*>(workspace);
+    if (dtype == SARSSL_F32) pw_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
+    else if (dtype == SARSSL_BF16) pw_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
+    else { set_last_error("stem_pw_wgrad: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    stem_reduce_kernel<<<1, 256, 0, stream>>>(partials, grid, 256, dweight64x4, accumulate);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// in/out: [B][H][W][64]; weight_packed [64 n][9 taps][64 ci] of the activation dtype; optional BN+ReLU on the input
+extern "C" int sarssl_conv3x3(const void* in, const float* in_scale, const float* in_shift, const void* weight_packed, void* out, int B, int H, int W,
+                              int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(in && weight_packed && out && B > 0 && H > 0 && W > 0, "conv3x3: bad arguments");
+    const long long P = (long long)B * H * W;
+    const unsigned grid = (unsigned)((P + CM - 1) / CM);
+    if (dtype == SARSSL_F32) conv3x3_kernel<float><<<grid, 256, 0, stream>>>((const float*)in, in_scale, in_shift, (const float*)weight_packed, (float*)out, P, H, W);
+    else if (dtype == SARSSL_BF16) conv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)in, in_scale, in_shift, (const __nv_bfloat16*)weight_packed, (__nv_bfloat16*)out, P, H, W);
+    else { set_last_error("conv3x3: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// dweight_packed [64 o][9][64 ci] fp32 (+)= sum_p dy[p][o] * f(in[p + tap][ci])
+extern "C" int sarssl_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dweight_packed, int accumulate,
+                                    int B, int H, int W, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dy && in && dweight_packed && workspace && B > 0 && H > 0 && W > 0, "conv3x3_wgrad: bad arguments");
+    const long long P = (long long)B * H * W;
+    long long splits = (long long)sm_count() * 2 / 9;
+    if (splits < 1) splits = 1;
+    long long pps = (P + splits - 1) / splits;
+    pps = (pps + CK - 1) / CK * CK;
+    splits = (P + pps - 1) / pps;
+    if (workspace_bytes < (size_t)splits * 64 * 576 * sizeof(float)) { set_last_error("conv3x3_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    float* partials = static_cast<float*>(workspace);
+    dim3 grid(9, (unsigned)splits);
+    if (dtype == SARSSL_F32) conv3x3_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)dy, (const float*)in, in_scale, in_shift, partials, P, H, W, pps);
+    else if (dtype == SARSSL_BF16) conv3x3_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)in, in_scale, in_shift, partials, P, H, W, pps);
+    else { set_last_error("conv3x3_wgrad: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    stem_reduce_kernel<<<(64 * 576 + 255) / 256, 256, 0, stream>>>(partials, (int)splits, 64 * 576, dweight_packed, accumulate);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}

@@ -40,6 +40,53 @@ class Learner(ABC):
             self.model.set_compute_dtype(torch.bfloat16)
 
 
+    def mul_gpu(self):
+        """learner.py:25-31 wraps the model in nn.DataParallel (one process, per-step weight broadcast).  Here: one process per
+        GPU (torchrun); gradients are all-reduced in contiguous buckets of the flat gradient arena over NCCL, overlapped with
+        the rest of backward (see sarssl_b200/parallel.py).  Without an initialised process group this is a no-op."""
+        from .parallel import GradientSync
+        self.grad_sync = GradientSync.create(self.model)
+
+    def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True):
+        """learner.py:76-131: one epoch of pre-training.  A fresh Adam (moments reset) per epoch like the reference; loss / diff
+        of every step are kept on the device and read back once at the end of the epoch (the reference syncs 3x per step)."""
+        from .optim import FusedAdam
+        self.model.train()
+        optimizer = FusedAdam(self.model, lr=lr)
+        optimizer.zero_grad()
+        sync = getattr(self, "grad_sync", None)
+        log, vis_batch = [], None
+        for batch_idx, (mic_sig_batch,) in enumerate(dataset):
+            in_batch, = self.data_preprocess(mic_sig_batch, None)
+            loss_batch, diff_batch, vis_batch = self.model(in_batch)
+            loss_batch.backward()
+            scale = 1.0
+            if sync is not None:
+                scale = sync.all_reduce()
+            optimizer.step(lr, grad_scale=scale, zero_grad=True)
+            log.append(torch.stack([loss_batch.detach(), diff_batch.detach()]))
+        vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]
+        if return_diff:
+            return vals[0], vals[1], vis_batch
+        return vals[0]
+
+    def pretest_epoch(self, dataset, return_diff=True, return_eval=False):
+        """learner.py:133-167: eval-mode pass (BatchNorm running statistics, no dropout, masks still random)."""
+        if return_eval:
+            raise SarsslError("pretest_epoch(return_eval=True) needs pretrain_evaluate (iSTFT + PESQ, SURVEY.md 8(f) row 3): not built yet")
+        self.model.eval()
+        log, vis_batch = [], None
+        with torch.no_grad():
+            for data in dataset:
+                in_batch, = self.data_preprocess(data[0], None)
+                loss_batch, diff_batch, vis_batch = self.model(in_batch)
+                log.append(torch.stack([loss_batch, diff_batch]))
+        vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]
+        if return_diff:
+            return vals[0], vals[1], vis_batch
+        return vals[0]
+
+
 class STFTLearner(Learner):
     """learner.py:488-572."""
 

@@ -1,9 +1,12 @@
-"""Mirror of the reference's model surface (code/model.py) - pre-training path."""
+"""Mirror of the reference's model surface (code/model.py) for the pre-training path: `SARSSL` with the same constructor
+signature, `forward(x) -> (loss, diff, data_vis)` contract and `state_dict` keys, running on the fused engine."""
 import torch
 import torch.nn as nn
 
-from . import ops
-from .modules import PatchMask, as_patch_layout
+from . import _lib, ops
+from .engine import Engine
+from .modules import PatchMask, PatchRecover, PatchSplit, as_patch_layout
+from .params import ParamStore
 
 
 class _MaskedLossFn(torch.autograd.Function):
@@ -14,19 +17,15 @@ class _MaskedLossFn(torch.autograd.Function):
         want = pred.requires_grad
         out2, dpred = ops.masked_loss(pred.detach(), patches, frame_flag, ch_idx, nmasked, want_grad=want)
         ctx.dpred, ctx.flag = dpred, frame_flag
-        ctx.mark_non_differentiable(out2)
-        loss = out2[0].clone()
-        ctx.save_for_backward()
-        return loss, out2[1]
+        return out2[0].clone(), out2[1].clone()
 
     @staticmethod
     def backward(ctx, g_loss, g_diff):
-        from ._lib import check, lib, ptr, stream_ptr, dtype_code
         d = ctx.dpred
         nb, nt, w = d.shape
         g = g_loss.reshape(1).float().contiguous()
-        check(lib().sarssl_scale_masked_rows(ptr(d), dtype_code(d), ptr(ctx.flag), ptr(g), nb, nt, w // 4, stream_ptr(d.device)),
-              "sarssl_scale_masked_rows")
+        _lib.check(_lib.lib().sarssl_scale_masked_rows(_lib.ptr(d), _lib.dtype_code(d), _lib.ptr(ctx.flag), _lib.ptr(g), nb, nt, w // 4,
+                                                       _lib.stream_ptr(d.device)), "sarssl_scale_masked_rows")
         return d, None, None, None, None
 
 
@@ -46,3 +45,117 @@ class MaskedReconLoss(nn.Module):
         pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state)
         loss, diff = _MaskedLossFn.apply(pred.reshape(nb, nt, nf * 4), patches, flag, cidx, self.patch_mask.nmasked_patch)
         return loss, diff, {"mask_patch_idx": pidx, "mask_ch_idx": cidx}
+
+
+class _PretrainFn(torch.autograd.Function):
+    """One autograd node for the whole model.  `anchor` is a dummy leaf that makes autograd call backward(); parameter
+    gradients are accumulated directly into the flat gradient arena (p.grad are views of it), not returned."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, patches, flag, ch, want):
+        out2, pred, saved = model.engine.forward(patches, flag, ch, model.nmasked_patch, training=model.training, want_grad=want)
+        ctx.model, ctx.saved = model, saved
+        model._last = {"pred": pred, "saved": saved}
+        return out2[0].clone(), out2[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_diff):
+        if ctx.saved is None:
+            raise _lib.SarsslError("backward() through a forward that ran without gradient tracking (eval() or no_grad())")
+        ctx.model.store.reattach_grads()
+        ctx.model.engine.backward(ctx.saved, gscale=g_loss.reshape(1).float().contiguous())
+        ctx.saved = None
+        return None, None, None, None, None, None
+
+
+class VisDict(dict):
+    """data_vis of model.py:595-599 ('mask', 'pred', 'tar').  'pred' / 'tar' are zero-copy views; the dense 'mask' is only
+    materialised when somebody reads it (the reference folds all three every step and uses them once per epoch)."""
+
+    def __init__(self, pred, patches, flag, ch):
+        nb, nt, nf = patches.shape[:3]
+        super().__init__(pred=pred.view(nb, nt, nf, 2, 2).permute(0, 2, 1, 3, 4), tar=patches.permute(0, 2, 1, 3, 4), mask=None)
+        self._flag, self._ch, self._shape = flag, ch, (nb, nt, nf, 2)
+
+    def __getitem__(self, key):
+        if key == "mask" and dict.__getitem__(self, "mask") is None:
+            nb, nt, nf, nmic = self._shape
+            m = [torch.empty(self._shape, device=self._flag.device) for _ in range(3)]
+            _lib.check(_lib.lib().sarssl_expand_masks(_lib.ptr(self._flag), _lib.ptr(self._ch), _lib.ptr(m[0]), _lib.ptr(m[1]), _lib.ptr(m[2]), nb, nt,
+                                                      nf, nmic, _lib.stream_ptr(self._flag.device)), "sarssl_expand_masks")
+            dict.__setitem__(self, "mask", m[0].permute(0, 2, 1, 3))
+        return dict.__getitem__(self, key)
+
+
+class SARSSL(nn.Module):
+    """model.py:350-601 (pre-training branch, spec/spat = ['cnn', 'conformer'], in_ver 'separate', decoder ['', 'fc'])."""
+
+    def __init__(self, sig_shape=[256, 256, 2, 2], patch_shape=(256, 1), patch_mode="T", nmasked_patch=128 * 1, pretrain=True, use_cls=False,
+                 downstream_token="all", downstream_head="mlp", downstream_embed="spec_spat", downstream_dlabel=1, device="cpu",
+                 pretrain_frozen_encoder=False):
+        super().__init__()
+        nf, nt, nreim, nmic = sig_shape
+        if not pretrain or pretrain_frozen_encoder or use_cls:
+            raise _lib.SarsslError("sarssl_b200.SARSSL implements the pre-training path (pretrain=True, use_cls=False); the downstream branch "
+                                   "(model.py:667-719) is a 'next' row of SURVEY.md 8(f)")
+        if tuple(patch_shape) != (nf, 1) or patch_mode != "T" or nreim != 2 or nmic != 2:
+            raise _lib.SarsslError("only frame patches (patch_shape == (nf, 1), patch_mode 'T') of 2-microphone re/im spectrograms are on the hot path")
+        npatch = nt
+        if nmasked_patch != npatch // 2:                   # model.py:361-364
+            nmasked_patch = npatch // 2
+        self.pretrain, self.pretrain_frozen_encoder, self.use_cls = pretrain, pretrain_frozen_encoder, use_cls
+        self.sig_shape, self.nmasked_patch, self.in_ver = tuple(sig_shape), nmasked_patch, "separate"
+        self.device = torch.device(device if str(device) != "cpu" else ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.store = ParamStore(self, nf=nf, device=self.device)
+        # the rest are plain attributes (not sub-modules) so that state_dict() holds exactly the reference's 214 entries
+        object.__setattr__(self, "patch_split", PatchSplit(patch_shape=patch_shape, f_first=False))
+        object.__setattr__(self, "patch_recover", PatchRecover(output_shape=(nf, nt), patch_shape=patch_shape, f_first=False))
+        object.__setattr__(self, "patch_mask", PatchMask(patch_mode=patch_mode, nmasked_patch=nmasked_patch, npatch_shape=[1, npatch], device=self.device))
+        self.engine = None
+        self.compute_dtype = torch.float32
+        self.dropout_p = 0.1
+        self.rng_state = None            # None: consume python's global `random` stream like the reference; else np.uint32[625]
+        self._anchor = torch.zeros((), requires_grad=True)
+        self._last = None
+
+    # ---- device / dtype plumbing
+    def _apply(self, fn, recurse=True):
+        probe = fn(torch.zeros(1, device=self.store.device))
+        if probe.dtype != torch.float32:
+            raise _lib.SarsslError("master parameters stay fp32; use set_compute_dtype(torch.bfloat16) for mixed precision")
+        self.store.to(probe.device)
+        self.device = self.store.device
+        self.patch_mask.device = self.device
+        self.engine = None
+        return self
+
+    def set_compute_dtype(self, dtype):
+        self.compute_dtype = dtype
+        self.engine = None
+
+    def set_dropout(self, p):
+        self.dropout_p = float(p)
+        if self.engine is not None:
+            self.engine.dropout_p = float(p)
+
+    def _engine(self):
+        if self.engine is None:
+            if self.device.type != "cuda":
+                raise _lib.SarsslError("SARSSL.forward needs the model on a CUDA device (no CPU path)")
+            self.engine = Engine(self.store, self.device, self.compute_dtype, self.dropout_p)
+        return self.engine
+
+    # ---- forward
+    def forward(self, x):
+        """x (nb, 2, nf, nt, 2) -> (loss, diff, {'mask': (nb,nf,nt,2), 'pred': (nb,nf,nt,2,2), 'tar': (nb,nf,nt,2,2)})   model.py:519-601"""
+        self._engine()
+        patches = as_patch_layout(x)
+        nb, nt, nf = patches.shape[:3]
+        if (nf, nt) != tuple(self.sig_shape[:2]):
+            raise _lib.SarsslError(f"input is {nf} bins x {nt} frames but the model was built for {self.sig_shape[:2]}")
+        pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state)
+        want = torch.is_grad_enabled() and self.training
+        loss, diff = _PretrainFn.apply(self._anchor, self, patches, flag, cidx, want)
+        vis = VisDict(self._last["pred"], patches, flag, cidx)
+        vis.mask_patch_idx, vis.mask_ch_idx = pidx, cidx
+        return loss, diff, vis

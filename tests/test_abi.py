@@ -26,6 +26,9 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(l, s), f"{s} declared in include/sarssl_b200.h but not exported"
     assert set(_lib.PROTOTYPES) == set(syms), set(_lib.PROTOTYPES) ^ set(syms)
+    import subprocess
+    exported = {ln.split()[-1] for ln in subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout.splitlines() if " T sarssl_" in ln}
+    assert exported == set(syms), exported ^ set(syms)
     assert l.sarssl_version() >= 100
 
 

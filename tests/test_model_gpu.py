@@ -1,0 +1,150 @@
+"""GPU parity of the fused model (SARSSL.forward / backward through the C ABI) against the CPU oracle and the fixtures the
+real reference produced.  fp32 mode: forward within 1e-4 relative; gradients norm-wise per tensor."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sarssl_oracle as O
+from sarssl_b200 import ops
+from sarssl_b200.learner import STFTLearner
+from sarssl_b200.model import SARSSL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def build(nt, sd_seed=7, dtype=torch.float32):
+    m = SARSSL(sig_shape=(256, nt, 2, 2), device=DEV)
+    m.load_state_dict(O.synthetic_state_dict(sd_seed))
+    m.to(DEV)
+    m.set_dropout(0.0)
+    m.set_compute_dtype(dtype)
+    m.train()
+    return m
+
+
+def run_ours(m, sig, mask_seed):
+    L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    x, = L.data_preprocess(sig.to(DEV))
+    random.seed(mask_seed)
+    loss, diff, vis = m(x)
+    loss.backward()
+    return loss, diff, vis
+
+
+def run_oracle(sig, nt, sd_seed, mask_seed):
+    x = O.preprocess(sig)
+    sd = O.synthetic_state_dict(sd_seed)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k and not k.endswith(".pe"):
+            v.requires_grad_(True)
+    random.seed(mask_seed)
+    pidx, cidx = O.draw_masks(sig.shape[0], nt, nt // 2, 2)
+    taps = {}
+    loss, diff, vis = O.pretrain_forward(x, sd, pidx, cidx, training=True, taps=taps)
+    loss.backward()
+    return loss, diff, vis, sd, taps
+
+
+def check_grads(m, ref_grad, tol):
+    gmax = max(float(g.norm()) for g in ref_grad.values())
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        g, r = p.grad.detach().cpu().double(), ref_grad[k].double()
+        err = float((g - r).norm()) / (float(r.norm()) + 1e-6 * gmax)
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < tol, f"worst gradient mismatch {worst}"
+
+
+@pytest.mark.parametrize("nb,nt", [(3, 16), (2, 7)])
+def test_forward_backward_fp32_vs_oracle(nb, nt):
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=5)
+    m = build(nt)
+    loss, diff, vis = run_ours(m, sig, 11)
+    rl, rd, rvis, sd, taps = run_oracle(sig, nt, 7, 11)
+    assert rel(vis["pred"].cpu(), rvis["pred"]) < 1e-4
+    assert torch.equal(vis["mask"].cpu(), rvis["mask"])
+    assert rel(vis["tar"].cpu(), rvis["tar"]) < 1e-5
+    assert abs(float(loss) - float(rl)) < 1e-4 * float(rl) and abs(float(diff) - float(rd)) < 1e-4 * float(rd)
+    check_grads(m, {k: sd[k].grad for k, _ in m.named_parameters()}, 2e-3)
+    for k, v in m.state_dict().items():                       # BatchNorm running statistics after one step
+        if "running_" in k:
+            assert torch.allclose(v.cpu(), sd[k].detach(), rtol=1e-4, atol=1e-6), k
+        if "num_batches" in k:
+            assert int(v) == 1
+
+
+def test_matches_reference_fixture_tiny():
+    g = np.load(os.path.join(GOLDEN, "tiny_nt16_b3.npz"))
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"]))
+    m = build(nt, int(g["sd_seed"]))
+    loss, diff, vis = run_ours(m, sig, int(g["mask_seed"]))
+    assert np.array_equal(vis.mask_patch_idx.cpu().numpy(), g["mask_patch_idx"])
+    assert np.array_equal(vis.mask_ch_idx.cpu().numpy(), g["mask_ch_idx"][:, 0])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+    assert abs(float(diff) - float(g["diff"])) < 1e-4 * float(g["diff"])
+    assert rel(vis["pred"].cpu(), torch.from_numpy(g["pred"])) < 1e-4
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    for k, p in m.named_parameters():
+        mine = p.grad.detach().cpu().reshape(-1)
+        assert abs(float(mine.norm()) - float(g["grad_norm/" + k])) <= 2e-3 * float(g["grad_norm/" + k]) + 1e-6 * gmax, k
+        samp = mine[torch.from_numpy(g["grad_idx/" + k])].numpy()
+        assert np.abs(samp - g["grad_val/" + k]).max() <= 5e-3 * np.abs(g["grad_val/" + k]).max() + 1e-5 * gmax, k
+    # eval-mode forward with the updated running statistics (pretest_epoch path)
+    m.eval()
+    L = STFTLearner(m, 512, 0.5, 512, 1, 16000)
+    x, = L.data_preprocess(sig.to(DEV))
+    random.seed(int(g["mask_seed"]) + 1)
+    with torch.no_grad():
+        le, de, _ = m(x)
+    assert abs(float(le) - float(g["eval_loss"])) < 1e-4 * float(g["eval_loss"])
+
+
+def test_matches_reference_fixture_full_size():
+    g = np.load(os.path.join(GOLDEN, "full_nt256_b2.npz"))
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"]))
+    m = build(nt, int(g["sd_seed"]))
+    loss, diff, vis = run_ours(m, sig, int(g["mask_seed"]))
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+    got = vis["pred"].contiguous().reshape(-1)[torch.from_numpy(g["pred_sample_idx"]).to(DEV)].cpu().numpy()
+    assert np.abs(got - g["pred_sample"]).max() <= 1e-3 * np.abs(g["pred_sample"]).max()
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    for k, p in m.named_parameters():
+        assert abs(float(p.grad.norm()) - float(g["grad_norm/" + k])) <= 5e-3 * float(g["grad_norm/" + k]) + 1e-6 * gmax, k
+
+
+def test_bf16_mode_loss_and_gradients():
+    nb, nt = 3, 16
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=5)
+    m = build(nt, dtype=torch.bfloat16)
+    loss, diff, vis = run_ours(m, sig, 11)
+    rl, rd, rvis, sd, taps = run_oracle(sig, nt, 7, 11)
+    assert abs(float(loss) - float(rl)) < 2e-2 * float(rl)
+    check_grads(m, {k: sd[k].grad for k, _ in m.named_parameters()}, 6e-2)
+
+
+def test_dropout_statistics_and_train_step():
+    """Dropout on: the loss stays finite, differs between steps (new masks), and a few fused-Adam steps reduce it."""
+    nb, nt = 4, 16
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=8)
+    m = build(nt)
+    m.set_dropout(0.1)
+    L = STFTLearner(m, 512, 0.5, 512, 1, 16000)
+    L.device = DEV
+    random.seed(3)
+    first, _, _ = L.pretrain_epoch([[sig]] * 2, lr=1e-3, epoch=1)
+    last, _, _ = L.pretrain_epoch([[sig]] * 6, lr=1e-3, epoch=2)
+    assert np.isfinite(first) and np.isfinite(last) and last < first
+    le, de, _ = L.pretest_epoch([[sig]])
+    assert np.isfinite(le) and de > 0
