@@ -118,9 +118,9 @@ def draw_masks(nbatch, npatch, nmasked, nmic=2, rng=None):
 def dense_masks(pidx, cidx, npatch, dpatch, nmic=2):
     """(mask_dense, mask_patch_dense, mask_ch_dense), each (nb, npatch, dpatch, nmic) f32; 0 = masked."""
     nb = pidx.shape[0]
-    mp = torch.ones(nb, npatch)
+    mp = torch.ones(nb, npatch, device=pidx.device)
     mp.scatter_(1, pidx, 0.0)
-    mc = torch.ones(nb, nmic)
+    mc = torch.ones(nb, nmic, device=pidx.device)
     mc.scatter_(1, cidx, 0.0)
     mask_patch = mp[:, :, None, None].expand(nb, npatch, dpatch, nmic)
     mask_ch = mc[:, None, None, :].expand(nb, npatch, dpatch, nmic)
@@ -183,8 +183,8 @@ def relative_shift(pos):
                   = pos[i+1, j-i-2]   for j >  i+1
     pos (..., T, T).  (The pad/view trick of the reference produces exactly this.)"""
     T = pos.shape[-1]
-    i = torch.arange(T).view(T, 1)
-    j = torch.arange(T).view(1, T)
+    i = torch.arange(T, device=pos.device).view(T, 1)
+    j = torch.arange(T, device=pos.device).view(1, T)
     low = j <= i
     up = j > i + 1
     row = torch.where(up, i + 1, i).clamp(max=T - 1).expand(T, T)

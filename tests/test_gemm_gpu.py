@@ -1,0 +1,126 @@
+"""GPU: the two GEMM kernels through the C ABI.  CUDA-core kernel vs torch (CPU fp32 matmul); tensor-core (tcgen05) kernel vs
+the CUDA-core kernel on identical bf16 operands (both accumulate in fp32, so they agree to accumulation-order noise)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from sarssl_b200 import _lib
+from sarssl_b200.kernels import KernelSet, ACT_NONE, ACT_RELU, ACT_SWISH
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (100, 70, 33), (257, 129, 200), (1, 5, 7)])
+def test_simt_gemm_fp32_plain_and_transposed(M, N, K):
+    k = KernelSet(DEV, torch.float32)
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    Cd = k.empty(M, N)
+    k.linear(A.to(DEV), B.to(DEV), Cd, M, N, K)
+    assert rel(Cd.cpu(), A @ B.T) < 1e-5
+    At, Bt = A.T.contiguous().to(DEV), B.T.contiguous().to(DEV)        # both operands with the contraction on the slow axis
+    k.gemm(At, Bt, Cd, M, N, K, (1, M), (1, N), N)
+    assert rel(Cd.cpu(), A @ B.T) < 1e-5
+
+
+def test_simt_gemm_epilogue_and_batch():
+    k = KernelSet(DEV, torch.float32)
+    g = torch.Generator().manual_seed(1)
+    nb1, nb2, M, N, K = 3, 2, 40, 50, 24
+    A, B = torch.randn(nb1, nb2, M, K, generator=g), torch.randn(nb1, nb2, N, K, generator=g)
+    bias, R = torch.randn(N, generator=g), torch.randn(nb1, nb2, M, N, generator=g)
+    Cd, pre = k.empty(nb1, nb2, M, N), k.empty(nb1, nb2, M, N)
+    k.gemm(A.to(DEV), B.to(DEV), Cd, M, N, K, (K, 1), (K, 1), N, batch=(nb1, nb2), sAb=(nb2 * M * K, M * K), sBb=(nb2 * N * K, N * K),
+           sCb=(nb2 * M * N, M * N), bias=bias.to(DEV), act=ACT_SWISH, pre=pre, resid=R.to(DEV), ldr=N, alpha=0.7, beta=0.5)
+    u = 0.7 * (A @ B.transpose(-1, -2)) + bias
+    assert rel(pre.cpu(), u) < 1e-5
+    assert rel(Cd.cpu(), R + 0.5 * u * torch.sigmoid(u)) < 1e-5
+
+
+def test_simt_gemm_dropout_is_consistent_between_epilogue_and_a_operand():
+    """Forward: Y = drop(X W^T) with mask keyed by Y's element offset.  Backward re-creates the mask on the A operand."""
+    k = KernelSet(DEV, torch.float32)
+    M, N, K = 96, 80, 32
+    X, W = torch.randn(M, K).to(DEV), torch.randn(N, K).to(DEV)
+    Y0, Y = k.empty(M, N), k.empty(M, N)
+    k.linear(X, W, Y0, M, N, K)
+    k.linear(X, W, Y, M, N, K, drop=(0.25, 1234))
+    kept = (Y != 0)
+    frac = float(kept.float().mean())
+    assert 0.70 < frac < 0.80
+    assert rel(Y[kept].cpu(), (Y0[kept] / 0.75).cpu()) < 1e-5
+    # A-side mask: Z = (mask(Y0)/0.75) @ I  must equal Y
+    eye = torch.eye(N, device=DEV)
+    Z = k.empty(M, N)
+    k.gemm(Y0, eye, Z, M, N, N, (N, 1), (N, 1), N, a_drop=(0.25, 1234))
+    assert rel(Z.cpu(), Y.cpu()) < 1e-6
+    S = k.empty(M, N)
+    k.scale_dropout(Y0, S, M * N, 1.0, (0.25, 1234))
+    assert torch.equal(S != 0, kept)
+
+
+def _tc(k, A, B, Cmat, M, N, K, sA, sB, ldc, **kw):
+    g = _lib.GemmArgs()
+    from sarssl_b200.kernels import _addr
+    g.A, g.B, g.C = _addr(A), _addr(B), _addr(Cmat)
+    g.pre_out = _addr(kw["pre"]) if kw.get("pre") is not None else None
+    g.resid = _addr(kw["resid"]) if kw.get("resid") is not None else None
+    g.bias = kw["bias"].data_ptr() if kw.get("bias") is not None else None
+    g.sAm, g.sAk, g.sBn, g.sBk, g.ldc, g.ldr = sA[0], sA[1], sB[0], sB[1], ldc, kw.get("ldr", 0)
+    g.M, g.N, g.K, g.nb1, g.nb2 = M, N, K, 1, 1
+    g.ab_dtype, g.c_dtype, g.act, g.accumulate = _lib.BF16, _lib.dtype_code(Cmat), kw.get("act", 0), int(kw.get("accumulate", False))
+    g.alpha, g.beta = kw.get("alpha", 1.0), kw.get("beta", 1.0)
+    g.drop_p, g.drop_seed = kw.get("drop", (0.0, 0))
+    _lib.check(k.L.sarssl_gemm_tc(C.byref(g), k.stream), "sarssl_gemm_tc")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 200, 136), (4096, 512, 2048), (128, 64, 64), (1000, 48, 1024),
+                                   (65536 // 8, 1024, 3072)])
+def test_tc_gemm_k_major_matches_simt(M, N, K):
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    ref, out = k.empty(M, N, dtype=torch.float32), k.empty(M, N, dtype=torch.float32)
+    k.linear(A, B, ref, M, N, K)
+    _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+
+
+def test_tc_gemm_epilogue_matches_simt():
+    k = KernelSet(DEV, torch.bfloat16)
+    M, N, K = 384, 256, 192
+    g = torch.Generator(device=DEV).manual_seed(3)
+    A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    R = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    ref, pre_ref, out, pre = k.empty(M, N), k.empty(M, N), k.empty(M, N), k.empty(M, N)
+    kw = dict(bias=bias, act=ACT_SWISH, resid=R, ldr=N, alpha=1.0, beta=0.5, drop=(0.1, 77))
+    k.linear(A, B, ref, M, N, K, pre=pre_ref, **kw)
+    _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N, pre=pre, **kw)
+    torch.cuda.synchronize()
+    assert rel(pre.float(), pre_ref.float()) < 1e-3 and rel(out.float(), ref.float()) < 5e-3
+    assert torch.equal(out == R, ref == R)                     # identical dropout pattern
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 256, 4096), (200, 72, 1000), (1024, 64, 8192), (2048, 512, 65536 // 4)])
+def test_tc_gemm_mn_major_weight_gradient(M, N, K):
+    """dW[M][N] (+)= sum_k dY[k][M] * X[k][N]: both operands stored with the contraction on the slow axis."""
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M * 3 + N + K)
+    dY = torch.randn(K, M, device=DEV, generator=g).bfloat16()
+    X = (torch.randn(K, N, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    ref, out = k.zeros_f32(M, N), k.zeros_f32(M, N)
+    k.gemm(dY, X, ref, M, N, K, (1, M), (1, N), N, accumulate=True)
+    _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)
+    _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)          # accumulates: 2x
+    torch.cuda.synchronize()
+    assert rel(out, 2 * ref) < 1e-5, rel(out, 2 * ref)
