@@ -1,17 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the SAR-SSL pre-training hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+"""Benchmark of the SAR-SSL pre-training hot path on B200 (contract: task statement / DESIGN.md section 6).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5                      # our arm (CUDA kernels through the C ABI)
-    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # reference arm: CPU restatement on host cores
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # our arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # reference arm: CPU restatement on the host cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, weak scaling over clips
 
-One JSON line on stdout (rank 0).  metric = clips/s (BASELINE.json); a "step" is one pass of the hot path over one
-batch of synthetic clips.  `value` is measured with inputs resident in HBM; `e2e` goes through the reference-facing
-Python API from pinned host memory (H2D of the waveforms and D2H of the loss inside the timed region).
+One JSON line on stdout (rank 0).  metric = pre-training clips/s (BASELINE.json); a "step" is one full training step
+(STFT front-end -> masks -> MC-Conformer forward -> masked reconstruction loss -> backward -> Adam) over one micro-batch of
+synthetic 2-microphone clips per GPU.  `value` has the waveforms resident in HBM; `e2e` goes through the reference-facing
+`STFTLearner.pretrain_epoch` from pinned host memory (H2D of the waveforms + D2H of the loss inside the timed region).
+The front-end + loss sub-path (BASELINE.json configs[1]) is reported in the same line under "frontend".
 """
 import argparse
 import json
 import os
+import random
 import subprocess
 import sys
 import threading
@@ -21,9 +24,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NSAMPLE = 65792            # 4.112 s @ 16 kHz -> 256 frames (opt.py:19, run_pretrain.py:67-72)
-STFT_BYTES_PER_CLIP = NSAMPLE * 2 * 4 + 2 * 256 * 256 * 2 * 4           # 1,574,912 B
+NT, NF = 256, 256
+STFT_BYTES_PER_CLIP = NSAMPLE * 2 * 4 + 2 * 256 * 256 * 2 * 4                  # 1,574,912 B
 LOSS_BYTES_PER_CLIP = 128 * 256 * 2 * 4 + 128 * 256 * 4 * 4 + 256 * 1024 * 4   # 1,835,008 B fp32 pred
-FLOP_PER_CLIP = 86.53e9    # fwd+bwd, 3 x forward convention
+FLOP_PER_CLIP = 86.53e9                                                          # fwd+bwd, 3 x forward convention
+CONV3_FLOP_PER_CLIP = 2.0 * 256 * 256 * 64 * 576                                # one 3x3 64->64 conv over a 256x256 map
 
 
 def peaks():
@@ -68,55 +73,62 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
+def workload_config(world, per_gpu_batch, dtype):
+    return {"workload": "MC-Conformer pre-training step (STFT front-end + masks + fwd + masked recon loss + bwd + Adam), 2-mic, 65792 samples "
+                        f"(4.112 s @16 kHz), micro-batch {per_gpu_batch}/GPU, {dtype} (BASELINE.json configs[2])",
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world, "nsample": NSAMPLE, "nmic": 2, "nt": NT, "nf": NF,
+            "dropout": 0.1, "optimizer": "Adam", "l2": "activations per step (tens of GB) far exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"dp{world}"}
+
+
 # --------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU restatement of the reference (oracle/) on the host cores
 # --------------------------------------------------------------------------------------------------------------
 
-def cpu_frontend_loss(nb, steps, warmup, threads):
+def cpu_pretrain_clips_per_s(nb, steps, warmup, threads):
+    """Full training step of the oracle (= the reference's algorithm: STFT, masks, fwd, loss, autograd bwd, Adam) on CPU, dropout on."""
     import torch
     from oracle import sarssl_oracle as O
     torch.set_num_threads(threads)
     sig = O.synthetic_waveforms(nb, NSAMPLE, 2, seed=1234)
-    pred = torch.randn(nb, 256, 1024, generator=torch.Generator().manual_seed(1)).requires_grad_(True)
-    import random
+    sd = O.synthetic_state_dict(7)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    m = [torch.zeros_like(sd[k]) for k in names]
+    v = [torch.zeros_like(sd[k]) for k in names]
     random.seed(400000001)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         x = O.preprocess(sig)
-        vec = x.permute(0, 3, 2, 4, 1)
-        pidx, cidx = O.draw_masks(nb, 256, 128, 2)
-        loss, diff = O.masked_loss(pred.view(nb, 256, 256, 2, 2), vec, pidx, cidx)
+        pidx, cidx = O.draw_masks(nb, NT, NT // 2, 2)
+        loss, diff, _ = O.pretrain_forward(x, sd, pidx, cidx, training=True, dropout_p=0.1)
         loss.backward()
-        pred.grad = None
+        with torch.no_grad():
+            O.adam_step([sd[k] for k in names], [sd[k].grad for k in names], m, v, i + 1, 1e-3)
+        for k in names:
+            sd[k].grad = None
+        float(loss)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return nb * len(times) / sum(times)
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
     cores = os.cpu_count() or 1
-    nb = 64
-    v = cpu_frontend_loss(nb, args.steps, args.warmup, cores)
-    sample = f"{nb} clips/step x {args.steps} steps of the frontend+loss workload (oracle port of the reference, torch CPU fp32)"
-    line = {"impl": "reference", "metric": "pretrain_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nb / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, per_gpu_batch=nb),
+    nb = 8                                                   # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    v = cpu_pretrain_clips_per_s(nb, steps, warmup, cores)
+    sample = f"{nb} clips/step x {steps} steps (+{warmup} warm-up) of the same training step, oracle port of the reference (torch CPU fp32, dropout on)"
+    line = {"impl": "reference", "metric": "pretrain_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * nb / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus, nb, "f32"),
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, per_gpu_batch):
-    return {"workload": "stft_frontend+masked_recon_loss fwd+bwd, 2-mic, 65792 samples (4.112 s @16 kHz), "
-                        f"batch {per_gpu_batch}/GPU (BASELINE.json configs[1])",
-            "per_gpu_batch": per_gpu_batch, "nsample": NSAMPLE, "nmic": 2, "nt": 256, "nf": 256,
-            "l2": "inputs (539 MB/step) larger than the 126 MB L2; no explicit flush", "parallelism": f"dp{args.gpus}"}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -127,8 +139,10 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from sarssl_b200 import ops
+    from sarssl_b200.kernels import KernelSet
     from sarssl_b200.learner import STFTLearner
-    from sarssl_b200.model import MaskedReconLoss
+    from sarssl_b200.model import SARSSL, MaskedReconLoss
+    from sarssl_b200.optim import FusedAdam
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -138,36 +152,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     nb = args.batch
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    sig = 0.1 * torch.randn(nb, NSAMPLE, 2, device=dev, generator=g)
-    pred = torch.randn(nb, 256, 1024, device=dev, generator=g)
-    state = ops.mt_seed(400000001 + rank)
-    host_sig = torch.empty(nb, NSAMPLE, 2, dtype=torch.float32).pin_memory()
-    host_sig.copy_(sig)
-
-    def draw():
-        pidx, cidx, flag = ops.draw_masks(state, nb, 256, 128, 2)
-        return torch.from_numpy(flag).pin_memory().to(dev, non_blocking=True), \
-            torch.from_numpy(cidx.astype("int32")).pin_memory().to(dev, non_blocking=True)
-
-    patches = torch.empty(nb, 256, 256, 2, 2, device=dev)
-    dpred = torch.empty_like(pred)
-    out2 = torch.empty(2, device=dev)
-
-    def step_resident():
-        flag, cidx = draw()
-        ops.stft_frontend(sig, out=patches)
-        ops.masked_loss(pred, patches, flag, cidx, 128, out2=out2, dpred=dpred)
-
-    learner = STFTLearner(None, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
-    learner.device = dev
-    loss_mod = MaskedReconLoss(nmasked_patch=128, npatch=256, device=dev, rng_state=state)
-
-    def step_e2e():
-        x, = learner.data_preprocess(host_sig)                  # H2D of the waveforms happens inside (learner.py:533)
-        loss, diff, _ = loss_mod(pred, x)
-        return float(loss)                                       # D2H of the step's result
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -189,51 +176,111 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    # ---------------- model + learner (identical weights on every rank)
+    torch.manual_seed(1)
+    model = SARSSL(sig_shape=(NF, NT, 2, 2), device=dev)
+    model.to(dev)
+    model.set_compute_dtype(dtype)
+    model.set_dropout(0.1)
+    model.rng_state = ops.mt_seed(400000001 + rank)
+    model.train()
+    learner = STFTLearner(model, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    learner.device = dev
+    if world > 1:
+        learner.mul_gpu()
+    sync = getattr(learner, "grad_sync", None)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    sig = 0.1 * torch.randn(nb, NSAMPLE, 2, device=dev, generator=g)
+    host_sig = torch.empty(nb, NSAMPLE, 2, dtype=torch.float32).pin_memory()
+    host_sig.copy_(sig)
+    opt = FusedAdam(model, lr=1e-3)
+    losses = []
+
+    def step_resident():
+        x, = learner.data_preprocess(sig)
+        loss, diff, _ = model(x)
+        loss.backward()
+        scale = sync.all_reduce() if sync is not None else 1.0
+        opt.step(1e-3, grad_scale=scale, zero_grad=True)
+        losses.append(loss.detach())
+
+    for _ in range(warmup):
         step_resident()
+    eng = model.engine
+    l0 = eng.k.launches + opt.k.launches
     sampler = ClockSampler(local)
     sampler.start()
     ms = timed(step_resident, args.steps)
     sampler.stop_flag = True
+    launches = eng.k.launches + opt.k.launches - l0 + args.steps       # + the front-end kernel
     ops.stft_frontend_check(dev)
-    clips = nb * world * args.steps
-    value = clips / (ms * 1e-3)
+    value = nb * world * args.steps / (ms * 1e-3)
+    loss_first, loss_last = float(losses[0]), float(losses[-1])
 
-    # dominant kernel alone (the fused STFT front-end), CUDA events on the launching stream
-    flag, cidx = draw()
-    for _ in range(3):
-        ops.stft_frontend(sig, out=patches)
-    k_ms = timed(lambda: ops.stft_frontend(sig, out=patches), args.steps) / args.steps
-    l_ms = timed(lambda: ops.masked_loss(pred, patches, flag, cidx, 128, out2=out2, dpred=dpred), args.steps) / args.steps
-    pk = peaks()
-    achieved = nb * STFT_BYTES_PER_CLIP / (k_ms * 1e-3) / 1e9
-    loss_gbs = nb * LOSS_BYTES_PER_CLIP / (l_ms * 1e-3) / 1e9
-
-    for _ in range(2):
-        step_e2e()
-    e2e_steps = max(2, min(args.steps, 10))
-    e2e_ms = timed(step_e2e, e2e_steps)
+    # ---------------- end to end through the reference-facing API, host buffers
+    e2e_steps = max(2, min(args.steps, 5))
+    learner.pretrain_epoch([[host_sig]] * 2, lr=1e-3, epoch=1)
+    e2e_ms = timed(lambda: learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1), 1)
     e2e_value = nb * world * e2e_steps / (e2e_ms * 1e-3)
 
+    # ---------------- dominant kernel of the step alone: 3x3 conv 64->64 (69 % of the FLOPs), CUDA events on the launching stream
+    k = KernelSet(dev, dtype)
+    cb = min(nb, 64)
+    xin = torch.randn(cb * NT * NF, 64, device=dev, generator=g).to(dtype)
+    wpk = (torch.randn(64, 9, 64, device=dev, generator=g) / 24.0).to(dtype)
+    yout = torch.empty_like(xin)
+    conv = lambda: k.conv3x3(xin, None, wpk, yout, cb, NT, NF)
+    for _ in range(3):
+        conv()
+    conv_ms = timed(conv, 5) / 5
+    pk = peaks()
+    conv_tflops = cb * CONV3_FLOP_PER_CLIP / (conv_ms * 1e-3) / 1e12
+    del xin, yout
+
+    # ---------------- front-end + loss sub-path (BASELINE.json configs[1], batch 1024)
+    fb = args.frontend_batch
+    fsig = 0.1 * torch.randn(fb, NSAMPLE, 2, device=dev, generator=g)
+    fpred = torch.randn(fb, NT, 4 * NF, device=dev, generator=g)
+    patches = torch.empty(fb, NT, NF, 2, 2, device=dev)
+    dpred, out2 = torch.empty_like(fpred), torch.empty(2, device=dev)
+    st = ops.mt_seed(7)
+    pidx, cidx, flag = ops.draw_masks(st, fb, NT, NT // 2, 2)
+    flag_d, cidx_d = torch.from_numpy(flag).to(dev), torch.from_numpy(cidx.astype("int32")).to(dev)
+    fe = lambda: ops.stft_frontend(fsig, out=patches)
+    ls = lambda: ops.masked_loss(fpred, patches, flag_d, cidx_d, NT // 2, out2=out2, dpred=dpred)
+    for _ in range(3):
+        fe(); ls()
+    fe_ms = timed(fe, 10) / 10
+    ls_ms = timed(ls, 10) / 10
+    both_ms = timed(lambda: (fe(), ls()), 10) / 10
+    fe_gbs = fb * STFT_BYTES_PER_CLIP / (fe_ms * 1e-3) / 1e9
+    ls_gbs = fb * LOSS_BYTES_PER_CLIP / (ls_ms * 1e-3) / 1e9
+
     if rank == 0:
-        cores = os.cpu_count() or 1
-        cpu_nb = 64
-        cpu_v = cpu_frontend_loss(cpu_nb, 3, 1, cores) if world == 1 else None
-        line = {"metric": "pretrain_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, nb),
-                "clocks": sampler.summary(),
-                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 256 + nb * 4),
-                        "d2h_bytes_per_step": 4},
-                "gpu_launches": 2 * args.steps,
-                "roofline": {"bound": "hbm", "kernel": "stft_frontend_fused_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                             "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nb * STFT_BYTES_PER_CLIP,
-                             "secondary": {"kernel": "masked_loss_kernel", "achieved": loss_gbs, "frac": loss_gbs / pk["hbm_gbs"],
-                                           "kernel_ms": l_ms, "algorithmic_bytes_per_launch": nb * LOSS_BYTES_PER_CLIP}}}
-        if cpu_v is not None:
+        step_tflops = value * FLOP_PER_CLIP / 1e12 / world
+        line = {"metric": "pretrain_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic", "config": workload_config(world, nb, args.dtype), "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * NT + nb * 4),
+                        "d2h_bytes_per_step": 8},
+                "gpu_launches": int(launches), "tensor_core_gemm_launches": int(eng.k.tc_launches),
+                "loss_first_step": loss_first, "loss_last_step": loss_last,
+                "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / pk["bf16_tflops_sustained"],
+                "roofline": {"bound": "tensor", "kernel": "conv3x3 64->64 implicit GEMM (forward)", "achieved": conv_tflops,
+                             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": None,
+                             "peak_source": pk["source"], "kernel_ms": conv_ms, "algorithmic_flops_per_launch": cb * CONV3_FLOP_PER_CLIP,
+                             "clips_per_launch": cb},
+                "frontend": {"workload": f"stft_frontend + masked_recon_loss fwd+bwd, batch {fb} (BASELINE.json configs[1])",
+                             "clips_per_s": fb / (both_ms * 1e-3),
+                             "stft": {"bound": "hbm", "kernel": "stft_frontend_fused_kernel", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                      "frac": fe_gbs / pk["hbm_gbs"], "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": fb * STFT_BYTES_PER_CLIP},
+                             "loss": {"bound": "hbm", "kernel": "masked_loss_kernel", "achieved": ls_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                      "frac": ls_gbs / pk["hbm_gbs"], "kernel_ms": ls_ms, "algorithmic_bytes_per_launch": fb * LOSS_BYTES_PER_CLIP}}}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cpu_v = cpu_pretrain_clips_per_s(8, 2, 1, cores)
             line["cpu_baseline"] = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cpu_nb} clips/step x 3 steps of the same workload, oracle port (torch CPU fp32)"}
+                                    "sample": "8 clips/step x 2 steps (+1 warm-up) of the same training step, oracle port (torch CPU fp32, dropout on)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -242,10 +289,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step (micro-batch)")
+    ap.add_argument("--frontend-batch", type=int, default=1024)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -149,9 +149,9 @@ typedef struct sarssl_gemm_args {
 /* CUDA-core kernel (exact fp32 when ab_dtype is F32): any shape / stride. */
 int sarssl_gemm(const sarssl_gemm_args* args, cudaStream_t stream);
 /* Tensor-core kernel: tcgen05.mma with TMEM accumulators, TMA-staged 128B-swizzled operand tiles, warp-specialised
- * (TMA / MMA / epilogue).  Same argument block; requires bf16 operands, no batching, no A-side dropout, both operands K-major
- * (sAk == sBk == 1: forward and data-gradient GEMMs) or both MN-major (sAm == sBn == 1: weight-gradient GEMMs), leading
- * dimensions multiple of 8 elements, 16-byte aligned bases.  Returns SARSSL_ERR_UNSUPPORTED otherwise (call sarssl_gemm). */
+ * (TMA / MMA / epilogue).  Same argument block; requires bf16 operands, no batching, no A-side dropout, each operand K-major
+ * (unit stride along K) or MN-major (unit stride along M / N) - forward = K x K, data gradient = K x MN, weight gradient =
+ * MN x MN -, leading dimensions multiple of 8 elements, 16-byte aligned bases.  Returns SARSSL_ERR_UNSUPPORTED otherwise (call sarssl_gemm). */
 int sarssl_gemm_tc(const sarssl_gemm_args* args, cudaStream_t stream);
 
 

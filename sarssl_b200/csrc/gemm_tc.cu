@@ -246,12 +246,12 @@ using namespace sarssl;
 
 // Same argument block as sarssl_gemm; requirements of the tensor-core path (otherwise SARSSL_ERR_UNSUPPORTED, and the caller
 // uses sarssl_gemm): bf16 operands, no batching, no A-side dropout, each operand either K-major (sXk == 1) or MN-major
-// (sAm == 1 / sBn == 1), leading dimensions multiples of 8 elements, 16-byte aligned bases.
+// (sAm == 1 / sBn == 1) - any mix -, leading dimensions multiples of 8 elements, 16-byte aligned bases.
 extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     SARSSL_CHECK_ARG(a && a->A && a->B && a->C, "gemm_tc: null pointer");
     const bool a_k = a->sAk == 1, a_mn = a->sAm == 1 && !a_k, b_k = a->sBk == 1, b_mn = a->sBn == 1 && !b_k;
-    if (a->ab_dtype != SARSSL_BF16 || a->nb1 != 1 || a->nb2 != 1 || a->a_drop_p > 0.f || !(a_k || a_mn) || !(b_k || b_mn) || (a_mn != b_mn)) {
-        set_last_error("gemm_tc: unsupported configuration (needs bf16, unbatched, both operands K-major or both MN-major)");
+    if (a->ab_dtype != SARSSL_BF16 || a->nb1 != 1 || a->nb2 != 1 || a->a_drop_p > 0.f || !(a_k || a_mn) || !(b_k || b_mn)) {
+        set_last_error("gemm_tc: unsupported configuration (needs bf16, unbatched, unit stride along K or along M/N for each operand)");
         return SARSSL_ERR_UNSUPPORTED;
     }
     const long long lda = a_k ? a->sAm : a->sAk, ldb = b_k ? a->sBn : a->sBk;
@@ -268,13 +268,11 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     const int BN = bn64 ? 64 : 128;
     CUtensorMap ma, mb;
     int rc;
-    if (a_k) {
-        if ((rc = make_map_2d(&ma, a->A, a->M, a->K, lda, TBK, TBM))) return rc;
-        if ((rc = make_map_2d(&mb, a->B, a->N, a->K, ldb, TBK, BN))) return rc;
-        return bn64 ? launch_tc<64, false, false>(ma, mb, e, stream) : launch_tc<128, false, false>(ma, mb, e, stream);
-    }
-    // MN-major: global matrices are [K rows][M or N cols]; 64 x 64 boxes
-    if ((rc = make_map_2d(&ma, a->A, a->K, a->M, lda, 64, TBK))) return rc;
-    if ((rc = make_map_2d(&mb, a->B, a->K, a->N, ldb, 64, TBK))) return rc;
+    // K-major operand: global [M or N rows][K cols], one box of 64 k x (128 | BN) rows.  MN-major: global [K rows][M or N cols], 64 x 64 boxes.
+    if ((rc = a_k ? make_map_2d(&ma, a->A, a->M, a->K, lda, TBK, TBM) : make_map_2d(&ma, a->A, a->K, a->M, lda, 64, TBK))) return rc;
+    if ((rc = b_k ? make_map_2d(&mb, a->B, a->N, a->K, ldb, TBK, BN) : make_map_2d(&mb, a->B, a->K, a->N, ldb, 64, TBK))) return rc;
+    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, e, stream) : launch_tc<128, false, false>(ma, mb, e, stream);
+    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, e, stream) : launch_tc<128, false, true>(ma, mb, e, stream);
+    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, e, stream) : launch_tc<128, true, false>(ma, mb, e, stream);
     return bn64 ? launch_tc<64, true, true>(ma, mb, e, stream) : launch_tc<128, true, true>(ma, mb, e, stream);
 }

@@ -88,10 +88,11 @@ def test_tc_gemm_k_major_matches_simt(M, N, K):
     A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
     B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
     ref, out = k.empty(M, N, dtype=torch.float32), k.empty(M, N, dtype=torch.float32)
+    k.use_tc = False
     k.linear(A, B, ref, M, N, K)
     _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N)
     torch.cuda.synchronize()
-    assert rel(out, ref) < 1e-5, rel(out, ref)
+    assert rel(out, ref) < 1e-4, rel(out, ref)
 
 
 def test_tc_gemm_epilogue_matches_simt():
@@ -104,6 +105,7 @@ def test_tc_gemm_epilogue_matches_simt():
     R = torch.randn(M, N, device=DEV, generator=g).bfloat16()
     ref, pre_ref, out, pre = k.empty(M, N), k.empty(M, N), k.empty(M, N), k.empty(M, N)
     kw = dict(bias=bias, act=ACT_SWISH, resid=R, ldr=N, alpha=1.0, beta=0.5, drop=(0.1, 77))
+    k.use_tc = False
     k.linear(A, B, ref, M, N, K, pre=pre_ref, **kw)
     _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N, pre=pre, **kw)
     torch.cuda.synchronize()
@@ -119,8 +121,27 @@ def test_tc_gemm_mn_major_weight_gradient(M, N, K):
     dY = torch.randn(K, M, device=DEV, generator=g).bfloat16()
     X = (torch.randn(K, N, device=DEV, generator=g) / K ** 0.5).bfloat16()
     ref, out = k.zeros_f32(M, N), k.zeros_f32(M, N)
+    k.use_tc = False
     k.gemm(dY, X, ref, M, N, K, (1, M), (1, N), N, accumulate=True)
     _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)
     _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)          # accumulates: 2x
     torch.cuda.synchronize()
-    assert rel(out, 2 * ref) < 1e-5, rel(out, 2 * ref)
+    assert rel(out, 2 * ref) < 1e-4, rel(out, 2 * ref)      # fp32 accumulation-order noise only
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 520, 2048), (512, 64, 256)])
+def test_tc_gemm_data_gradient_mixed_majors(M, N, K):
+    """dX[M][N] = dY[M][K] @ W[K][N]: A K-major, B with the contraction on the slow axis."""
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(M + 7 * N + K)
+    dY = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    W = (torch.randn(K, N, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    ref, out = k.empty(M, N, dtype=torch.float32), k.empty(M, N, dtype=torch.float32)
+    k.use_tc = False
+    k.gemm(dY, W, ref, M, N, K, (K, 1), (1, N), N)
+    _tc(k, dY, W, out, M, N, K, (K, 1), (1, N), N)
+    Wt, dYt = W.T.contiguous(), dY.T.contiguous()
+    out2 = k.empty(M, N, dtype=torch.float32)
+    _tc(k, dYt, Wt, out2, M, N, K, (1, M), (K, 1), N)              # A MN-major, B K-major
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-4 and rel(out2, ref) < 1e-4

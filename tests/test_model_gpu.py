@@ -126,14 +126,46 @@ def test_matches_reference_fixture_full_size():
         assert abs(float(p.grad.norm()) - float(g["grad_norm/" + k])) <= 5e-3 * float(g["grad_norm/" + k]) + 1e-6 * gmax, k
 
 
+def _autocast_reference_grads(sig, nt, sd_seed, mask_seed):
+    """Calibration: the reference's own mixed-precision route - the oracle's functional model on CUDA under
+    torch.autocast(bfloat16) (what learner.py:100 does with --use-amp, in bf16)."""
+    x = O.preprocess(sig).to(DEV)
+    sd = {k: v.to(DEV) for k, v in O.synthetic_state_dict(sd_seed).items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k and not k.endswith(".pe"):
+            v.requires_grad_(True)
+    random.seed(mask_seed)
+    pidx, cidx = O.draw_masks(sig.shape[0], nt, nt // 2, 2)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss, _, _ = O.pretrain_forward(x, sd, pidx.to(DEV), cidx.to(DEV), training=True)
+    loss.backward()
+    return {k: v.grad.float().cpu() for k, v in sd.items() if v.requires_grad}
+
+
 def test_bf16_mode_loss_and_gradients():
+    """bf16 activation storage (fp32 accumulation / statistics / master weights), tcgen05 GEMMs.  Gates: loss within 2e-2 of the
+    fp32 oracle (north star); every gradient tensor no further from fp32 than 1.5 x what torch autocast(bf16) itself is, plus
+    2e-2 (profiles/r01_bf16_calibration.txt: any bf16-activation run of this net has 4 % median / 13 % worst gradient error)."""
     nb, nt = 3, 16
     sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=5)
     m = build(nt, dtype=torch.bfloat16)
     loss, diff, vis = run_ours(m, sig, 11)
+    assert m.engine.k.tc_launches > 50                                   # the tensor-core GEMM path really ran
     rl, rd, rvis, sd, taps = run_oracle(sig, nt, 7, 11)
     assert abs(float(loss) - float(rl)) < 2e-2 * float(rl)
-    check_grads(m, {k: sd[k].grad for k, _ in m.named_parameters()}, 6e-2, floor=1e-3)
+    assert rel(vis["pred"].float().cpu(), rvis["pred"]) < 2e-2
+    ac = _autocast_reference_grads(sig, nt, 7, 11)
+    gmax = max(float(sd[k].grad.norm()) for k, _ in m.named_parameters())
+    errs = []
+    for k, p in m.named_parameters():
+        r = sd[k].grad.double()
+        den = float(r.norm()) + 1e-3 * gmax
+        mine = float((p.grad.detach().cpu().double() - r).norm()) / den
+        auto = float((ac[k].double() - r).norm()) / den
+        assert mine <= 1.5 * auto + 2e-2, (k, mine, auto)
+        errs.append(mine)
+    errs.sort()
+    assert errs[len(errs) // 2] < 6e-2
 
 
 def test_dropout_statistics_and_train_step():
