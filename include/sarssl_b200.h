@@ -246,12 +246,27 @@ int sarssl_conv3x3(const void* in, const float* in_scale, const float* in_shift,
 int sarssl_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dweight_packed, int accumulate,
                          int B, int H, int W, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Tensor-core versions (bf16 only): tcgen05 implicit GEMM, TMA row boxes shared by the three horizontal taps, weights
+ * resident in shared memory, persistent CTAs.  `in` must already be the post-BatchNorm/ReLU activation (or dy for the data
+ * gradient, with the mirrored weight pack).  wgrad workspace: sarssl_conv3x3_wgrad_tc_workspace_bytes(). */
+int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, int B, int H, int W, cudaStream_t stream);
+size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void);
+int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * A14  optimizer: torch.optim.Adam(betas (0.9, 0.999), eps 1e-8, wd 0) over flat fp32 arenas      learner.py:83,111-113
  * ---------------------------------------------------------------------------------------------------------- */
 /* g is multiplied by grad_scale first; param_bf16 (nullable) receives the refreshed bf16 copy; zero_grad != 0 clears g. */
 int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n, int step, float lr,
                      float beta1, float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * diagnostics
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Hardware probe used by tests/test_tc_probe_gpu.py: one UMMA tile whose A descriptor starts row_off (0..7) 128-byte rows into
+ * a TMA-written 128B-swizzled tile (mode 0: K-major A [136][64]; mode 1: MN-major A [72][128], B [64][64]); D f32 [128][64]. */
+int sarssl_probe_umma_row_offset(const void* A, const void* B, float* D, int mode, int row_off, int use_base_offset, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

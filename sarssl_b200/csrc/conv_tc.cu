@@ -1,0 +1,446 @@
+// 3x3 convolution 64 -> 64 (padding 1) on the tcgen05 tensor cores as an implicit GEMM - the CNN patch-embedding stem's
+// dominant cost (69 % of the model FLOPs; reference: nn.Conv2d(64, 64, 3, padding=1) at model.py:54,57 through cuDNN).
+//
+// Images are channel-last bf16 [B][H][W][64]; one pixel is one 128-byte row, exactly one row of a 128B-swizzled UMMA operand.
+//
+// Forward / data gradient  (conv3x3_tc_kernel, persistent, 1 CTA per SM):
+//   out[b,h,w,:] = sum_{dh,dw} in[b,h+dh,w+dw,:] . Wp[:, tap(dh,dw), :]        (data gradient = same kernel, mirrored weights)
+//   * output tile = 128 consecutive pixels of one image row, accumulator 128 x 64 fp32 in TMEM (double buffered);
+//   * A operand: ONE TMA box per image row ([w0-1, w0+135) x 64 ch, out-of-bounds pixels zero-filled = the padding) serves the
+//     three horizontal taps by sliding the UMMA descriptor start by one pixel row (128 B) - swizzling is address based, see
+//     tests/test_tc_probe_gpu.py; a rolling ring of row boxes lets vertically consecutive tiles re-use two of their three rows,
+//     so shared memory is filled with ~1.06 x the input instead of 9 x (which would saturate the L2 -> SM path);
+//   * B operand: all 9 taps of the packed weights (72 KB) stay resident in shared memory for the life of the CTA;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bf16 -> 128-byte row stores).
+//
+// Weight gradient  (conv3x3_wgrad_tc_kernel, persistent, split over pixels):
+//   dWp[o, tap, ci] = sum_pixels dy[p, o] * in[p + tap, ci]; the contraction runs over pixels, so both operands are MN-major;
+//   the whole 576 x 64 result lives in TMEM (6 accumulators of 128 x 64: two taps of the same image row per UMMA), each k-block
+//   (64 pixels) loads one dy box and re-uses the rolling ring of input row boxes; per-CTA partial sums are reduced in a fixed
+//   order by a second kernel.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace sarssl {
+
+// ---- shared PTX helpers (same encodings as gemm_tc.cu) ----------------------------------------------------------------------
+__device__ __forceinline__ void ctma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)), "l"(map),
+                 "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ctma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t cdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void cumma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db),
+                 "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void ccommit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cfence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cfence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ctmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ============================================================================================================================
+// forward / data gradient
+// ============================================================================================================================
+constexpr int CW = 128;                  // output pixels per tile
+constexpr int CBOXR = 136;               // rows per input box: CW + 2 halo pixels, rounded up to 8
+constexpr int CBOXB = CBOXR * 128;       // 17408 B (multiple of 1024)
+constexpr int CSLOTS = 6;                // ring of row boxes
+constexpr int CSEG = 32;                 // image rows per work unit (2 halo row loads amortised over 32 tiles)
+constexpr int CWB = 9 * 8192;            // resident weights
+constexpr int kConvSmem = CSLOTS * CBOXB + CWB + 1024 + 256;
+constexpr int kConvThreads = 192;
+
+struct ConvP {
+    __nv_bfloat16* out;
+    int B, H, W, tiles_w, nseg_h;
+    long long nunits;
+};
+
+__global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, ConvP p) {
+    extern __shared__ unsigned char raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* ring = smem;
+    unsigned char* wsm = smem + CSLOTS * CBOXB;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + CSLOTS * CBOXB + CWB);
+    uint64_t* empty = full + CSLOTS;
+    uint64_t* wbar = empty + CSLOTS;
+    uint64_t* tfull = wbar + 1;          // [2]
+    uint64_t* tempty = tfull + 2;        // [2]
+    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < CSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(wbar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_tmem)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    cfence_before();
+    __syncthreads();
+    cfence_after();
+    const uint32_t tmem = *slot_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, CWB);
+            for (int t = 0; t < 9; ++t) ctma_load_2d(wsm + t * 8192, &tmW, t * 64, 0, wbar);
+            long long ib = 0;                                   // global box counter
+            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+                const int hs = (int)(u % p.nseg_h);
+                const long long r = u / p.nseg_h;
+                const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
+                const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
+                for (int row = h0 - 1; row <= h1; ++row, ++ib) {
+                    const int s = (int)(ib % CSLOTS);
+                    const uint32_t ph = (uint32_t)((ib / CSLOTS) & 1);
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], CBOXB);
+                    ctma_load_4d(ring + s * CBOXB, &tmIn, 0, w0 - 1, row, b, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            mbar_wait(wbar, 0);
+            long long ib = 0, it = 0;                           // box / tile counters
+            const uint32_t w_addr = smem_u32(wsm);
+            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+                const int hs = (int)(u % p.nseg_h);
+                const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG);
+                const int ntile = h1 - h0;
+                for (int t = 0; t < ntile; ++t, ++it) {
+                    // rows needed: boxes ib+t, ib+t+1, ib+t+2; each box's full barrier is waited exactly once, in order
+                    for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
+                        const long long bi = ib + t + j;
+                        mbar_wait(&full[bi % CSLOTS], (uint32_t)((bi / CSLOTS) & 1));
+                    }
+                    const int acc = (int)(it & 1);
+                    mbar_wait(&tempty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                    cfence_after();
+                    const uint32_t d = tmem + acc * 64;
+#pragma unroll
+                    for (int dh = 0; dh < 3; ++dh) {
+                        const uint32_t a_addr = smem_u32(ring + ((ib + t + dh) % CSLOTS) * CBOXB);
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                cumma(d, cdesc(a_addr + dw * 128 + k * 32, 16, 1024), cdesc(w_addr + (dh * 3 + dw) * 8192 + k * 32, 16, 1024), idesc,
+                                      (uint32_t)((dh | dw | k) != 0));
+                        }
+                    }
+                    ccommit(&empty[(ib + t) % CSLOTS]);         // the oldest row is dead after this tile
+                    if (t == ntile - 1) { ccommit(&empty[(ib + t + 1) % CSLOTS]); ccommit(&empty[(ib + t + 2) % CSLOTS]); }
+                    ccommit(&tfull[acc]);
+                }
+                ib += ntile + 2;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        long long it = 0;
+        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const int hs = (int)(u % p.nseg_h);
+            const long long r = u / p.nseg_h;
+            const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
+            const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
+            for (int h = h0; h < h1; ++h, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
+                cfence_after();
+                const int w = w0 + q * 32 + lane;
+                __nv_bfloat16* orow = p.out + (((long long)b * p.H + h) * p.W + w) * 64;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
+                    if (w < p.W) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            *reinterpret_cast<uint4*>(orow + c0 + j) = pk;
+                        }
+                    }
+                }
+                cfence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+        }
+    }
+    cfence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+}
+
+// ============================================================================================================================
+// weight gradient
+// ============================================================================================================================
+constexpr int GK = 64;                   // pixels per k-block
+constexpr int GBOXR = 72;                // input rows per box: GK + 2 halo, rounded up to 8
+constexpr int GBOXB = 10240;             // 72 * 128 = 9216, padded to a multiple of 1024
+constexpr int GSLOTS = 8;                // ring of input row boxes
+constexpr int GDY = 4;                   // ring of dy boxes (8 KB each)
+constexpr int kWgradSmem = GSLOTS * GBOXB + GDY * 8192 + 1024 + 256;
+constexpr int GSEG = 32;
+
+struct WgradP {
+    float* partials;                     // [gridDim.x][576][64]
+    int B, H, W, tiles_w, nseg_h;
+    long long nunits;
+};
+
+// accumulator g (0..5) holds taps (3*(g/2) + 2*(g%2)) and, in its upper 64 lanes, the next tap of the same image row (g even)
+__global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy,
+                                                                      WgradP p) {
+    extern __shared__ unsigned char raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* ring = smem;
+    unsigned char* dyr = smem + GSLOTS * GBOXB;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GSLOTS * GBOXB + GDY * 8192);
+    uint64_t* empty = full + GSLOTS;
+    uint64_t* dfull = empty + GSLOTS;
+    uint64_t* dempty = dfull + GDY;
+    uint64_t* done = dempty + GDY;
+    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDy) : "memory");
+        for (int s = 0; s < GSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < GDY; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    cfence_before();
+    __syncthreads();
+    cfence_after();
+    const uint32_t tmem = *slot_tmem;
+    bool any = false;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long long ib = 0, id = 0;
+            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+                const int hs = (int)(u % p.nseg_h);
+                const long long r = u / p.nseg_h;
+                const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
+                const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG), w0 = wt * GK;
+                // interleave: input rows h0-1, h0 first, then for each output row h: input row h+1 and dy row h
+                for (int row = h0 - 1; row <= h1; ++row, ++ib) {
+                    const int s = (int)(ib % GSLOTS);
+                    mbar_wait(&empty[s], (uint32_t)(((ib / GSLOTS) & 1) ^ 1));
+                    mbar_expect_tx(&full[s], GBOXR * 128);
+                    ctma_load_4d(ring + s * GBOXB, &tmIn, 0, w0 - 1, row, b, &full[s]);
+                    if (row >= h0 + 1) {                        // dy row (row - 1) is needed together with input row `row`
+                        const int sd = (int)(id % GDY);
+                        mbar_wait(&dempty[sd], (uint32_t)(((id / GDY) & 1) ^ 1));
+                        mbar_expect_tx(&dfull[sd], 8192);
+                        ctma_load_4d(dyr + sd * 8192, &tmDy, 0, w0, row - 1, b, &dfull[sd]);
+                        ++id;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // A (input taps) MN-major M = 128: two 64-channel groups LBO apart; B (dy) MN-major N = 64
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            long long ib = 0, id = 0;
+            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+                const int hs = (int)(u % p.nseg_h);
+                const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG);
+                const int ntile = h1 - h0;
+                for (int t = 0; t < ntile; ++t, ++id) {
+                    for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
+                        const long long bi = ib + t + j;
+                        mbar_wait(&full[bi % GSLOTS], (uint32_t)((bi / GSLOTS) & 1));
+                    }
+                    const int sd = (int)(id % GDY);
+                    mbar_wait(&dfull[sd], (uint32_t)((id / GDY) & 1));
+                    cfence_after();
+                    const uint32_t dy_addr = smem_u32(dyr + sd * 8192);
+#pragma unroll
+                    for (int dh = 0; dh < 3; ++dh) {
+                        const uint32_t a_addr = smem_u32(ring + ((ib + t + dh) % GSLOTS) * GBOXB);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {                  // taps (dw = -1, 0) together, then (dw = +1, -)
+                            const uint32_t d = tmem + (dh * 2 + half) * 64;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                cumma(d, cdesc(a_addr + half * 256 + k * 2048, 128, 1024), cdesc(dy_addr + k * 2048, 8192, 1024), idesc,
+                                      (uint32_t)(any || k != 0));
+                        }
+                    }
+                    any = true;
+                    ccommit(&empty[(ib + t) % GSLOTS]);
+                    if (t == ntile - 1) { ccommit(&empty[(ib + t + 1) % GSLOTS]); ccommit(&empty[(ib + t + 2) % GSLOTS]); }
+                    ccommit(&dempty[sd]);
+                }
+                ib += ntile + 2;
+            }
+            ccommit(done);
+        }
+    }
+    // every CTA writes its partial (zeros if it had no work) so the reduction can read a fixed number of partials
+    const bool has_work = (long long)blockIdx.x < p.nunits;
+    if (warp >= 2) {
+        const int q = warp & 3;
+        float* dst = p.partials + (size_t)blockIdx.x * 576 * 64;
+        if (has_work) {
+            mbar_wait(done, 0);
+            cfence_after();
+        }
+        // TMEM lane l of accumulator g: l < 64 -> tap 3*(g/2) + 2*(g%2), ci = l;  l >= 64 (g even only) -> next tap, ci = l - 64
+        for (int g = 0; g < 6; ++g) {
+            const int l = q * 32 + lane;
+            const int tap = 3 * (g >> 1) + 2 * (g & 1) + (l >> 6);
+            const bool valid = (l < 64) || ((g & 1) == 0);
+            const int ci = l & 63;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                if (has_work) ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 64 + c0, v);
+                if (valid) {
+                    float* o = dst + ((size_t)tap * 64 + ci) * 64 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(o + j) = has_work ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                                                   __uint_as_float(v[j + 3]))
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    cfence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// partials [nparts][tap][ci][o] -> dWp[o][tap][ci] (+)=
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // index into [tap][ci][o]
+    if (i >= 576 * 64) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * 576 * 64 + i];
+    const int o = i & 63, tc = i >> 6;
+    float* d = out + (size_t)o * 576 + tc;
+    *d = accumulate ? *d + (float)s : (float)s;
+}
+
+typedef CUresult (*CEncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CEncFn cenc() {
+    static CEncFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<CEncFn>(f);
+    }
+    return fn;
+}
+
+// channel-last image [B][H][W][64] bf16, box = 64 ch x box_w pixels of one row
+static int image_map(CUtensorMap* m, const void* base, int B, int H, int W, int box_w) {
+    CEncFn fn = cenc();
+    if (!fn) { set_last_error("cuTensorMapEncodeTiled unavailable"); return SARSSL_ERR_UNSUPPORTED; }
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1}, es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("conv tensor map failed (%d) B=%d H=%d W=%d box_w=%d", (int)r, B, H, W, box_w); return SARSSL_ERR_ARG; }
+    return SARSSL_OK;
+}
+
+}  // namespace sarssl
+
+using namespace sarssl;
+
+extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, int B, int H, int W, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(in && weight_packed && out && B > 0 && H > 0 && W > 0, "conv3x3_tc: bad arguments");
+    SARSSL_CHECK_ARG(aligned16(in) && aligned16(weight_packed) && aligned16(out), "conv3x3_tc: buffers must be 16-byte aligned");
+    CUtensorMap mi, mw;
+    int rc;
+    if ((rc = image_map(&mi, in, B, H, W, CBOXR))) return rc;
+    {
+        CEncFn fn = cenc();
+        cuuint64_t dims[2] = {576, 64}, strides[1] = {576 * 2};
+        cuuint32_t box[2] = {64, 64}, es[2] = {1, 1};
+        if (fn(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(weight_packed), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            set_last_error("conv3x3_tc: weight tensor map failed");
+            return SARSSL_ERR_ARG;
+        }
+    }
+    static bool configured = false;
+    if (!configured) { SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem)); configured = true; }
+    ConvP p;
+    p.out = static_cast<__nv_bfloat16*>(out); p.B = B; p.H = H; p.W = W;
+    p.tiles_w = (W + CW - 1) / CW; p.nseg_h = (H + CSEG - 1) / CSEG;
+    p.nunits = (long long)B * p.tiles_w * p.nseg_h;
+    const int grid = (int)(p.nunits < sm_count() ? p.nunits : sm_count());
+    conv3x3_tc_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(mi, mw, p);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void) { return (size_t)sm_count() * 576 * 64 * sizeof(float); }
+
+extern "C" int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dy && in && dweight_packed && workspace && B > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: bad arguments");
+    if (workspace_bytes < sarssl_conv3x3_wgrad_tc_workspace_bytes()) { set_last_error("conv3x3_wgrad_tc: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    CUtensorMap mi, md;
+    int rc;
+    if ((rc = image_map(&mi, in, B, H, W, GBOXR))) return rc;
+    if ((rc = image_map(&md, dy, B, H, W, GK))) return rc;
+    static bool configured = false;
+    if (!configured) { SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem)); configured = true; }
+    WgradP p;
+    p.partials = static_cast<float*>(workspace); p.B = B; p.H = H; p.W = W;
+    p.tiles_w = (W + GK - 1) / GK; p.nseg_h = (H + GSEG - 1) / GSEG;
+    p.nunits = (long long)B * p.tiles_w * p.nseg_h;
+    const int grid = (int)(p.nunits < sm_count() ? p.nunits : sm_count());
+    conv3x3_wgrad_tc_kernel<<<grid, kConvThreads, kWgradSmem, stream>>>(mi, md, p);
+    SARSSL_LAUNCH_CHECK();
+    conv_wgrad_reduce_kernel<<<(576 * 64 + 255) / 256, 256, 0, stream>>>(p.partials, grid, dweight_packed, accumulate);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}

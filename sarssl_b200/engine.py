@@ -134,11 +134,20 @@ class Engine:
         y1 = k.empty(P, CNN_CH)
         k.stem_expand(patches, mode, flag, ch, st.p(f"{pe}.0.weight"), y1, P, F, T)
         s1 = self._bn(f"{pe}.1", y1, P, CNN_CH, training)
-        y2 = k.empty(P, CNN_CH)
-        k.conv3x3(y1, s1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
+        y2, y3, z1, z2 = k.empty(P, CNN_CH), k.empty(P, CNN_CH), None, None
+        if k.conv_tc:            # tensor-core path: TMA feeds the MMA directly, so BatchNorm+ReLU is materialised once (bf16) first
+            z1 = k.empty(P, CNN_CH)
+            k.bn_act_fwd(y1, s1, ACT_RELU, z1, P, CNN_CH)
+            k.conv3x3_tc(z1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
+        else:                    # CUDA-core path applies BatchNorm+ReLU while loading the operand tile
+            k.conv3x3(y1, s1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
         s2 = self._bn(f"{pe}.4", y2, P, CNN_CH, training)
-        y3 = k.empty(P, CNN_CH)
-        k.conv3x3(y2, s2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
+        if k.conv_tc:
+            z2 = k.empty(P, CNN_CH)
+            k.bn_act_fwd(y2, s2, ACT_RELU, z2, P, CNN_CH)
+            k.conv3x3_tc(z2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
+        else:
+            k.conv3x3(y2, s2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
         s3 = self._bn(f"{pe}.7", y3, P, CNN_CH, training)
         y4 = k.empty(P, 4)
         k.stem_reduce(y3, s3, st.p(f"{pe}.9.weight"), y4, P)
@@ -148,7 +157,7 @@ class Engine:
         e = k.empty(M, D)
         k.linear(z4, self.W[f"{pe}.12.packed"], e, M, D, 4 * F)
         if sv is not None:
-            sv[pe] = dict(y1=y1, s1=s1, y2=y2, s2=s2, y3=y3, s3=s3, y4=y4, s4=s4, z4=z4)
+            sv[pe] = dict(y1=y1, s1=s1, y2=y2, s2=s2, y3=y3, s3=s3, y4=y4, s4=s4, z4=z4, z1=z1, z2=z2)
         return e
 
     def _ffn_fwd(self, pre, D, x, M, p_drop, site, rec):
@@ -372,11 +381,17 @@ class Engine:
         del dz4
         k.bn_act_bwd(dz, r["y3"], r["s3"], ACT_RELU, dz, st.g(f"{pe}.7.weight"), st.g(f"{pe}.7.bias"), P, CNN_CH)       # -> dy3
         dz_prev = k.empty(P, CNN_CH)
-        for i, y_in, s_in, y_bn, bn_key in ((6, r["y2"], r["s2"], r["y2"], f"{pe}.4"), (3, r["y1"], r["s1"], r["y1"], f"{pe}.1")):
+        for i, y_in, s_in, y_bn, bn_key, z_in in ((6, r["y2"], r["s2"], r["y2"], f"{pe}.4", r["z2"]), (3, r["y1"], r["s1"], r["y1"], f"{pe}.1", r["z1"])):
             dwpk = torch.empty(CNN_CH, 9, CNN_CH, dtype=torch.float32, device=self.dev)
-            k.conv3x3_wgrad(dz, y_in, s_in, dwpk, B, T, F)
+            if k.conv_tc:
+                k.conv3x3_wgrad_tc(dz, z_in, dwpk, B, T, F)
+            else:
+                k.conv3x3_wgrad(dz, y_in, s_in, dwpk, B, T, F)
             k.permute4(dwpk, st.g(f"{pe}.{i}.weight"), (CNN_CH, CNN_CH, 3, 3), (576, 1, 64, 192), accumulate=True)
-            k.conv3x3(dz, None, self.W[f"{pe}.{i}.bwd"], dz_prev, B, T, F)
+            if k.conv_tc:
+                k.conv3x3_tc(dz, self.W[f"{pe}.{i}.bwd"], dz_prev, B, T, F)
+            else:
+                k.conv3x3(dz, None, self.W[f"{pe}.{i}.bwd"], dz_prev, B, T, F)
             k.bn_act_bwd(dz_prev, y_bn, s_in, ACT_RELU, dz_prev, st.g(bn_key + ".weight"), st.g(bn_key + ".bias"), P, CNN_CH)
             dz, dz_prev = dz_prev, dz
         # 1x1 conv 4 -> 64 (no input gradient needed)

@@ -22,7 +22,7 @@ class KernelSet:
         self.tc_launches = 0
         self.use_tc = True
         nbytes = max(self.L.sarssl_reduce_workspace_bytes(4096), self.L.sarssl_stem_workspace_bytes(),
-                     self.L.sarssl_dwconv_wgrad_workspace_bytes(512, 31))
+                     self.L.sarssl_dwconv_wgrad_workspace_bytes(512, 31), self.L.sarssl_conv3x3_wgrad_tc_workspace_bytes())
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
 
     # ------------------------------------------------------------------ helpers
@@ -178,6 +178,19 @@ class KernelSet:
         self._ok(self.L.sarssl_stem_pw_wgrad(ptr(wide), sc, sh, ptr(narrow), mode, ptr(flag), ptr(ch), ptr(dw64x4), int(accumulate), P, W, H, self.dt,
                                              ptr(self.ws), self.ws.numel(), self.stream), "stem_pw_wgrad")
         self.launches += 1
+
+    @property
+    def conv_tc(self):
+        return self.use_tc and self.dtype == torch.bfloat16
+
+    def conv3x3_tc(self, x, wpacked, out, B, H, W):
+        self._ok(self.L.sarssl_conv3x3_tc(ptr(x), ptr(wpacked), ptr(out), B, H, W, self.stream), "conv3x3_tc")
+        self.tc_launches += 1
+
+    def conv3x3_wgrad_tc(self, dy, x, dwpacked, B, H, W):
+        self._ok(self.L.sarssl_conv3x3_wgrad_tc(ptr(dy), ptr(x), ptr(dwpacked), 0, B, H, W, ptr(self.ws), self.ws.numel(), self.stream), "conv3x3_wgrad_tc")
+        self.launches += 1
+        self.tc_launches += 1
 
     def conv3x3(self, x, stats, wpacked, out, B, H, W):
         sc = _addr(stats, 2 * 64) if stats is not None else None

@@ -1,0 +1,70 @@
+"""GPU: the CNN-stem kernels.  CUDA-core 3x3 conv / wgrad vs torch (CPU fp32 conv2d); tcgen05 versions vs the CUDA-core ones."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from sarssl_b200.kernels import KernelSet
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def pack(w):        # reference (o, ci, kh[bin], kw[frame]) -> [o][tap = kw*3 + kh][ci]   (image is [frame][bin])
+    return w.permute(0, 3, 2, 1).reshape(64, 9, 64).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 256), (1, 7, 40), (3, 5, 130)])
+def test_simt_conv3x3_and_wgrad_fp32_vs_torch(B, H, W):
+    k = KernelSet(DEV, torch.float32)
+    g = torch.Generator().manual_seed(B + H + W)
+    x = torch.randn(B, H, W, 64, generator=g)                    # our layout [b][frame][bin][c]
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    stats = torch.cat([torch.zeros(128), scale, shift])
+    z = torch.relu(x * scale + shift)
+    ref = F.conv2d(z.permute(0, 3, 2, 1), w, padding=1).permute(0, 3, 2, 1).contiguous()      # torch image is (c, bin, frame)
+    out = k.empty(B, H, W, 64)
+    k.conv3x3(x.to(DEV), stats.to(DEV), pack(w).to(DEV), out, B, H, W)
+    assert rel(out.cpu(), ref) < 1e-5
+    dy = torch.randn(B, H, W, 64, generator=g)
+    zz = z.permute(0, 3, 2, 1).clone().requires_grad_(True)
+    ww = w.clone().requires_grad_(True)
+    F.conv2d(zz, ww, padding=1).backward(dy.permute(0, 3, 2, 1))
+    dwp = torch.empty(64, 9, 64, device=DEV)
+    k.conv3x3_wgrad(dy.to(DEV), x.to(DEV), stats.to(DEV), dwp, B, H, W)
+    assert rel(dwp.cpu(), pack(ww.grad)) < 1e-4
+    # data gradient = the same kernel with the mirrored pack [ci][mirrored tap][o]
+    wb = w.flip(2, 3).permute(1, 3, 2, 0).reshape(64, 9, 64).contiguous()
+    dz = k.empty(B, H, W, 64)
+    k.conv3x3(dy.to(DEV), None, wb.to(DEV), dz, B, H, W)
+    assert rel(dz.cpu(), zz.grad.permute(0, 3, 2, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 1, 128), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 5, 64), (8, 256, 256)])
+def test_tc_conv3x3_matches_simt(B, H, W):
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(B * 7 + H + W)
+    x = torch.randn(B, H, W, 64, device=DEV, generator=g).bfloat16()
+    wp = (torch.randn(64, 9, 64, device=DEV, generator=g) / 24).bfloat16()
+    ref, out = torch.empty(B, H, W, 64, device=DEV, dtype=torch.bfloat16), torch.full((B, H, W, 64), 7.0, device=DEV, dtype=torch.bfloat16)
+    k.conv3x3(x, None, wp, ref, B, H, W)
+    k.conv3x3_tc(x, wp, out, B, H, W)
+    torch.cuda.synchronize()
+    assert rel(out.float(), ref.float()) < 3e-3, rel(out.float(), ref.float())     # both round the same fp32 sums to bf16
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 1, 64), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 70, 64), (8, 256, 256)])
+def test_tc_conv3x3_wgrad_matches_simt(B, H, W):
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(B * 5 + H + W)
+    z = torch.randn(B, H, W, 64, device=DEV, generator=g).bfloat16()
+    dy = (torch.randn(B, H, W, 64, device=DEV, generator=g) / (B * H * W) ** 0.5).bfloat16()
+    ref, out = torch.empty(64, 9, 64, device=DEV), torch.empty(64, 9, 64, device=DEV)
+    k.conv3x3_wgrad(dy, z, None, ref, B, H, W)
+    k.conv3x3_wgrad_tc(dy, z, out, B, H, W)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-4, rel(out, ref)
