@@ -229,7 +229,7 @@ def run_ours(args):
     xin = torch.randn(cb * NT * NF, 64, device=dev, generator=g).to(dtype)
     wpk = (torch.randn(64, 9, 64, device=dev, generator=g) / 24.0).to(dtype)
     yout = torch.empty_like(xin)
-    conv = lambda: k.conv3x3(xin, None, wpk, yout, cb, NT, NF)
+    conv = (lambda: k.conv3x3_tc(xin, wpk, yout, cb, NT, NF)) if dtype == torch.bfloat16 else (lambda: k.conv3x3(xin, None, wpk, yout, cb, NT, NF))
     for _ in range(3):
         conv()
     conv_ms = timed(conv, 5) / 5
@@ -266,7 +266,7 @@ def run_ours(args):
                 "gpu_launches": int(launches), "tensor_core_gemm_launches": int(eng.k.tc_launches),
                 "loss_first_step": loss_first, "loss_last_step": loss_last,
                 "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / pk["bf16_tflops_sustained"],
-                "roofline": {"bound": "tensor", "kernel": "conv3x3 64->64 implicit GEMM (forward)", "achieved": conv_tflops,
+                "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 conv 64->64 implicit GEMM, forward)" if dtype == torch.bfloat16 else "conv3x3_kernel (CUDA cores, fp32)", "achieved": conv_tflops,
                              "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"], "traffic": None,
                              "peak_source": pk["source"], "kernel_ms": conv_ms, "algorithmic_flops_per_launch": cb * CONV3_FLOP_PER_CLIP,
                              "clips_per_launch": cb},
