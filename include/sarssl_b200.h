@@ -200,12 +200,13 @@ int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long rows, int 
 
 /* relative-position attention glue                                         conformer/attention.py:87-97,105-113
  *   add_head_bias: qu = q + u_bias, qv = q + v_bias (q = first D columns of rows with stride ld)
- *   attn_softmax_fwd: prob[b][h][i][:] = softmax_j((content[b][h][i][j] + shift(pos[h][b])[i][j]) * scale)
+ *   attn_softmax_fwd: prob[b][h][i][:] = softmax_j((content[b][h][i][j] + shift(pos[h][b])[i][j]) * scale); attn_dropped
+ *                     (nullable) = Dropout(prob) with the mask keyed by the element offset (attention.py:98)
  *   attn_softmax_bwd: dattn (in place) -> dscore; dpos[h][b] = inverse shift of dscore; dropout mask regenerated */
 int sarssl_add_head_bias(const void* q, long long ld, const float* u_bias, const float* v_bias, void* qu, void* qv, long long rows, int D,
                          int dtype, cudaStream_t stream);
-int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, int B, int H, int T, float scale, int dtype,
-                            cudaStream_t stream);
+int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, void* attn_dropped, int B, int H, int T, float scale,
+                            float drop_p, unsigned long long seed, int dtype, cudaStream_t stream);
 int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void* dpos, int B, int H, int T, float scale, float drop_p,
                             unsigned long long seed, int dtype, cudaStream_t stream);
 int sarssl_add2(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int cols, int dtype,

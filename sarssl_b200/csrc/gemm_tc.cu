@@ -21,10 +21,11 @@ constexpr int TBM = 128, TBK = 64, kStages = 3, kTcThreads = 192;
 
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
-    long long ldc, ldr;
-    int M, N, K;
+    long long ldc, ldr, sCb1, sCb2;
+    int M, N, K, nb2, splitk, kb_per_split;
+    int a_z1, a_z2, b_z1, b_z2;          // 1 if the operand really advances along that batch axis (0: broadcast, coordinate stays 0)
     float alpha, beta;
-    int act, accumulate, c_is_bf16;
+    int act, accumulate, c_is_bf16, vec_ok;
     float drop_p; unsigned long long drop_seed;
 };
 
@@ -32,6 +33,11 @@ struct TcEpi {
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -101,7 +107,13 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
-    const int num_kb = (p.K + TBK - 1) / TBK;
+    // blockIdx.z = (batch z1, z2) x split-K slice
+    const int zs = blockIdx.z % p.splitk, zb = blockIdx.z / p.splitk;
+    const int z1 = zb / p.nb2, z2 = zb - z1 * p.nb2;
+    const int num_kb_total = (p.K + TBK - 1) / TBK;
+    const int kb_begin = zs * p.kb_per_split;
+    const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+    const int num_kb = kb_end - kb_begin;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -118,26 +130,28 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
+            const int az1 = z1 * p.a_z1, az2 = z2 * p.a_z2, bz1 = z1 * p.b_z1, bz2 = z2 * p.b_z2;
+            for (int i = 0; i < num_kb; ++i) {
+                const int kb = kb_begin + i;
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], kA + kB);
-                if (!A_MN) tma_load_2d(sA + s * kA, &tmA, kb * TBK, m0, &full[s]);
-                else { tma_load_2d(sA + s * kA, &tmA, m0, kb * TBK, &full[s]); tma_load_2d(sA + s * kA + kA / 2, &tmA, m0 + 64, kb * TBK, &full[s]); }
-                if (!B_MN) tma_load_2d(sB + s * kB, &tmB, kb * TBK, n0, &full[s]);
+                if (!A_MN) tma_load_4d(sA + s * kA, &tmA, kb * TBK, m0, az2, az1, &full[s]);
+                else { tma_load_4d(sA + s * kA, &tmA, m0, kb * TBK, az2, az1, &full[s]); tma_load_4d(sA + s * kA + kA / 2, &tmA, m0 + 64, kb * TBK, az2, az1, &full[s]); }
+                if (!B_MN) tma_load_4d(sB + s * kB, &tmB, kb * TBK, n0, bz2, bz1, &full[s]);
                 else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * kB + j * 8192, &tmB, n0 + 64 * j, kb * TBK, &full[s]);
+                    for (int j = 0; j < BN / 64; ++j) tma_load_4d(sB + s * kB + j * 8192, &tmB, n0 + 64 * j, kb * TBK, bz2, bz1, &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TBM, BN, A_MN, B_MN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kA), b_addr = smem_u32(sB + s * kB);
@@ -147,47 +161,143 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 2048 B per k step.
                     const uint64_t da = A_MN ? smem_desc(a_addr + k * 2048, 8192, 1024) : smem_desc(a_addr + k * 32, 16, 1024);
                     const uint64_t db = B_MN ? smem_desc(b_addr + k * 2048, 8192, 1024) : smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                    umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
                 }
                 umma_commit(&empty[s]);                 // stage reusable once these MMAs have read it
             }
             umma_commit(accum_full);                    // accumulator complete
         }
-    } else {
+    } else if (num_kb > 0) {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         mbar_wait(accum_full, 0);
         tc_fence_after();
         const int m = m0 + q * 32 + lane;
+        const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
         const bool drop = p.drop_p > 0.f;
+        const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+        const bool atomic = p.splitk > 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-            if (m < p.M) {
+            const int nb = n0 + c0;
+            if (m >= p.M || nb >= p.N) continue;
+            const long long off = zoff + (long long)m * p.ldc + nb;
+            const long long roff = zoff + (long long)m * p.ldr + nb;
+            if (p.vec_ok && nb + 32 <= p.N) {
+                // ---------------- vector path: 32 consecutive columns of one row
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n >= p.N) break;
-                    const long long off = (long long)m * p.ldc + n;
-                    float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? p.bias[n] : 0.f);
-                    if (p.pre) {
-                        if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.pre)[off] = __float2bfloat16_rn(v);
-                        else static_cast<float*>(p.pre)[off] = v;
+                for (int j = 0; j < 32; j += 4) {
+                    float4 bz = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j] = __uint_as_float(r[j]) * p.alpha + bz.x; v[j + 1] = __uint_as_float(r[j + 1]) * p.alpha + bz.y;
+                    v[j + 2] = __uint_as_float(r[j + 2]) * p.alpha + bz.z; v[j + 3] = __uint_as_float(r[j + 3]) * p.alpha + bz.w;
+                }
+                if (p.pre) {
+                    if (p.c_is_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            dst[j >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                                     *reinterpret_cast<uint32_t*>(&t3));
+                        }
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.pre) + off);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
-                    if (p.act == 1) v = fmaxf(v, 0.f);
-                    else if (p.act == 2) v = v / (1.0f + __expf(-v));
-                    if (drop) v = keep_mask(p.drop_seed, (unsigned long long)off, p.drop_p) ? v * keep_scale : 0.f;
-                    if (p.resid) {
-                        const long long roff = (long long)m * p.ldr + n;
-                        const float rv = p.c_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff]) : static_cast<const float*>(p.resid)[roff];
-                        v = rv + p.beta * v;
-                    } else v *= p.beta;
-                    if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16_rn(v);
-                    else {
-                        float* cp = static_cast<float*>(p.C) + off;
-                        *cp = p.accumulate ? *cp + v : v;
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                }
+                if (drop) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {              // off is even here (ldc % 8 == 0, nb % 32 == 0)
+                        const uint32_t kp = keep_pair(p.drop_seed, (unsigned long long)(off + j) >> 1, thr);
+                        v[j] = (kp & 1u) ? v[j] * keep_scale : 0.f;
+                        v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
                     }
+                }
+                if (p.resid) {
+                    if (p.c_is_bf16) {
+                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + roff);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 u = src[j >> 3];
+                            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z)), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+                            v[j] = f0.x + p.beta * v[j]; v[j + 1] = f0.y + p.beta * v[j + 1]; v[j + 2] = f1.x + p.beta * v[j + 2]; v[j + 3] = f1.y + p.beta * v[j + 3];
+                            v[j + 4] = f2.x + p.beta * v[j + 4]; v[j + 5] = f2.y + p.beta * v[j + 5]; v[j + 6] = f3.x + p.beta * v[j + 6]; v[j + 7] = f3.y + p.beta * v[j + 7];
+                        }
+                    } else {
+                        const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + roff);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 u = src[j >> 2];
+                            v[j] = u.x + p.beta * v[j]; v[j + 1] = u.y + p.beta * v[j + 1]; v[j + 2] = u.z + p.beta * v[j + 2]; v[j + 3] = u.w + p.beta * v[j + 3];
+                        }
+                    }
+                } else if (p.beta != 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= p.beta;
+                }
+                if (p.c_is_bf16) {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        dst[j >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                                 *reinterpret_cast<uint32_t*>(&t3));
+                    }
+                } else {
+                    float* cp = static_cast<float*>(p.C) + off;
+                    if (atomic) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(cp + j, v[j]);
+                    } else if (p.accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 u = *reinterpret_cast<float4*>(cp + j);
+                            u.x += v[j]; u.y += v[j + 1]; u.z += v[j + 2]; u.w += v[j + 3];
+                            *reinterpret_cast<float4*>(cp + j) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+                continue;
+            }
+            // ---------------- scalar path (ragged N or unaligned C)
+#pragma unroll 1
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                if (n >= p.N) break;
+                float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? p.bias[n] : 0.f);
+                if (p.pre) {
+                    if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.pre)[off + j] = __float2bfloat16_rn(v);
+                    else static_cast<float*>(p.pre)[off + j] = v;
+                }
+                if (p.act == 1) v = fmaxf(v, 0.f);
+                else if (p.act == 2) v = __fdividef(v, 1.0f + __expf(-v));
+                if (drop) v = keep_mask(p.drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
+                if (p.resid) {
+                    const float rv = p.c_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
+                    v = rv + p.beta * v;
+                } else v *= p.beta;
+                if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.C)[off + j] = __float2bfloat16_rn(v);
+                else {
+                    float* cp = static_cast<float*>(p.C) + off + j;
+                    if (atomic) atomicAdd(cp, v);
+                    else *cp = p.accumulate ? *cp + v : v;
                 }
             }
         }
@@ -212,29 +322,36 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major matrix [rows][cols] with row pitch ld (elements); box = box_cols x box_rows, 128B swizzle
-static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+// bf16 matrix [rows][cols] with row pitch ld (elements), replicated over two batch axes (element strides sb1, sb2; a zero
+// stride means "broadcast": that axis is collapsed to size 1).  box = box_cols x box_rows x 1 x 1, 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows, int nb1, long long sb1,
+                    int nb2, long long sb2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled unavailable"); return SARSSL_ERR_UNSUPPORTED; }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const bool use1 = nb1 > 1 && sb1 != 0, use2 = nb2 > 1 && sb2 != 0;
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(use2 ? nb2 : 1), (cuuint64_t)(use1 ? nb1 : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(use2 ? sb2 * 2 : ld * 2 * rows), (cuuint64_t)(use1 ? sb1 * 2 : ld * 2 * rows)};
+    cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d base=%p", (int)r, rows, cols, ld, box_cols, box_rows, base); return SARSSL_ERR_ARG; }
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d nb=%dx%d sb=%lld,%lld base=%p", (int)r, rows, cols, ld, box_cols,
+                       box_rows, nb1, nb2, sb1, sb2, base);
+        return SARSSL_ERR_UNSUPPORTED;
+    }
     return SARSSL_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
     static bool configured = false;
     const int smem = TcSmem<BN>::kBytes;
     if (!configured) {
         SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((e.N + BN - 1) / BN, (e.M + TBM - 1) / TBM);
+    dim3 grid((e.N + BN - 1) / BN, (e.M + TBM - 1) / TBM, nbatch * e.splitk);
     gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, smem, stream>>>(ma, mb, e);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
@@ -244,35 +361,56 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& 
 
 using namespace sarssl;
 
-// Same argument block as sarssl_gemm; requirements of the tensor-core path (otherwise SARSSL_ERR_UNSUPPORTED, and the caller
-// uses sarssl_gemm): bf16 operands, no batching, no A-side dropout, each operand either K-major (sXk == 1) or MN-major
-// (sAm == 1 / sBn == 1) - any mix -, leading dimensions multiples of 8 elements, 16-byte aligned bases.
+// Same argument block as sarssl_gemm.  Requirements of the tensor-core path (otherwise SARSSL_ERR_UNSUPPORTED and the caller
+// uses sarssl_gemm): bf16 operands, no A-side dropout, each operand K-major (unit stride along K) or MN-major (unit stride along
+// M / N), leading dimensions and batch strides multiples of 8 elements, 16-byte aligned bases.
 extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     SARSSL_CHECK_ARG(a && a->A && a->B && a->C, "gemm_tc: null pointer");
     const bool a_k = a->sAk == 1, a_mn = a->sAm == 1 && !a_k, b_k = a->sBk == 1, b_mn = a->sBn == 1 && !b_k;
-    if (a->ab_dtype != SARSSL_BF16 || a->nb1 != 1 || a->nb2 != 1 || a->a_drop_p > 0.f || !(a_k || a_mn) || !(b_k || b_mn)) {
-        set_last_error("gemm_tc: unsupported configuration (needs bf16, unbatched, unit stride along K or along M/N for each operand)");
+    if (a->ab_dtype != SARSSL_BF16 || a->a_drop_p > 0.f || !(a_k || a_mn) || !(b_k || b_mn) || a->nb1 < 1 || a->nb2 < 1) {
+        set_last_error("gemm_tc: unsupported configuration (needs bf16, no A-side dropout, unit stride along K or along M/N for each operand)");
         return SARSSL_ERR_UNSUPPORTED;
     }
     const long long lda = a_k ? a->sAm : a->sAk, ldb = b_k ? a->sBn : a->sBk;
-    if ((lda % 8) || (ldb % 8) || !aligned16(a->A) || !aligned16(a->B) || a->M < 1 || a->N < 1 || a->K < 1) {
-        set_last_error("gemm_tc: operands must be 16-byte aligned with leading dimensions multiple of 8");
+    if ((lda % 8) || (ldb % 8) || (a->sAb1 % 8) || (a->sAb2 % 8) || (a->sBb1 % 8) || (a->sBb2 % 8) || !aligned16(a->A) || !aligned16(a->B) || a->M < 1 ||
+        a->N < 1 || a->K < 1 || (long long)a->nb1 * a->nb2 > 16384) {
+        set_last_error("gemm_tc: operands must be 16-byte aligned with leading dimensions / batch strides multiple of 8");
         return SARSSL_ERR_UNSUPPORTED;
     }
+    const int nbatch = a->nb1 * a->nb2;
     TcEpi e;
     e.C = a->C; e.pre = a->pre_out; e.resid = a->resid; e.bias = a->bias; e.ldc = a->ldc; e.ldr = a->ldr ? a->ldr : a->ldc;
+    e.sCb1 = a->sCb1; e.sCb2 = a->sCb2; e.nb2 = a->nb2;
     e.M = a->M; e.N = a->N; e.K = a->K; e.alpha = a->alpha; e.beta = a->beta; e.act = a->act; e.accumulate = a->accumulate;
     e.c_is_bf16 = a->c_dtype == SARSSL_BF16; e.drop_p = a->drop_p; e.drop_seed = a->drop_seed;
+    e.a_z1 = (a->nb1 > 1 && a->sAb1 != 0); e.a_z2 = (a->nb2 > 1 && a->sAb2 != 0); e.b_z1 = (a->nb1 > 1 && a->sBb1 != 0); e.b_z2 = (a->nb2 > 1 && a->sBb2 != 0);
     if (e.accumulate && e.c_is_bf16) { set_last_error("gemm_tc: accumulate needs an fp32 C"); return SARSSL_ERR_UNSUPPORTED; }
+    const size_t esz = e.c_is_bf16 ? 2 : 4;
+    e.vec_ok = (a->ldc % 8 == 0) && (e.ldr % 8 == 0) && (a->sCb1 % 8 == 0) && (a->sCb2 % 8 == 0) && aligned16(a->C) && (!a->pre_out || aligned16(a->pre_out)) &&
+               (!a->resid || aligned16(a->resid)) && (!a->bias || aligned16(a->bias));
+    (void)esz;
     const bool bn64 = a->N <= 64;
     const int BN = bn64 ? 64 : 128;
+    // split-K: weight gradients (fp32 accumulate, plain epilogue) have few output tiles and a very long K
+    const int num_kb = (a->K + TBK - 1) / TBK;
+    int splitk = 1;
+    if (e.accumulate && !e.c_is_bf16 && !a->pre_out && !a->resid && !a->bias && a->act == 0 && a->drop_p == 0.f && nbatch == 1) {
+        const long long tiles = (long long)((a->N + BN - 1) / BN) * ((a->M + TBM - 1) / TBM);
+        const long long want = (2LL * sm_count() + tiles - 1) / tiles;
+        splitk = (int)(want < 1 ? 1 : want);
+        if (splitk > num_kb / 4) splitk = num_kb / 4 > 0 ? num_kb / 4 : 1;       // at least 4 k-blocks per slice
+    }
+    e.kb_per_split = (num_kb + splitk - 1) / splitk;
+    e.splitk = (num_kb + e.kb_per_split - 1) / e.kb_per_split;
     CUtensorMap ma, mb;
     int rc;
     // K-major operand: global [M or N rows][K cols], one box of 64 k x (128 | BN) rows.  MN-major: global [K rows][M or N cols], 64 x 64 boxes.
-    if ((rc = a_k ? make_map_2d(&ma, a->A, a->M, a->K, lda, TBK, TBM) : make_map_2d(&ma, a->A, a->K, a->M, lda, 64, TBK))) return rc;
-    if ((rc = b_k ? make_map_2d(&mb, a->B, a->N, a->K, ldb, TBK, BN) : make_map_2d(&mb, a->B, a->K, a->N, ldb, 64, TBK))) return rc;
-    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, e, stream) : launch_tc<128, false, false>(ma, mb, e, stream);
-    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, e, stream) : launch_tc<128, false, true>(ma, mb, e, stream);
-    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, e, stream) : launch_tc<128, true, false>(ma, mb, e, stream);
-    return bn64 ? launch_tc<64, true, true>(ma, mb, e, stream) : launch_tc<128, true, true>(ma, mb, e, stream);
+    if ((rc = a_k ? make_map(&ma, a->A, a->M, a->K, lda, TBK, TBM, a->nb1, a->sAb1, a->nb2, a->sAb2)
+                  : make_map(&ma, a->A, a->K, a->M, lda, 64, TBK, a->nb1, a->sAb1, a->nb2, a->sAb2))) return rc;
+    if ((rc = b_k ? make_map(&mb, a->B, a->N, a->K, ldb, TBK, BN, a->nb1, a->sBb1, a->nb2, a->sBb2)
+                  : make_map(&mb, a->B, a->K, a->N, ldb, 64, TBK, a->nb1, a->sBb1, a->nb2, a->sBb2))) return rc;
+    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, e, nbatch, stream) : launch_tc<128, false, false>(ma, mb, e, nbatch, stream);
+    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, e, nbatch, stream) : launch_tc<128, false, true>(ma, mb, e, nbatch, stream);
+    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, e, nbatch, stream) : launch_tc<128, true, false>(ma, mb, e, nbatch, stream);
+    return bn64 ? launch_tc<64, true, true>(ma, mb, e, nbatch, stream) : launch_tc<128, true, true>(ma, mb, e, nbatch, stream);
 }

@@ -5,10 +5,11 @@
 // All tensors are row-major [rows][cols] with fp32 or bf16 storage and fp32 math; every cross-CTA reduction goes
 // through per-CTA partials that a second kernel adds in a fixed order (deterministic, final sums in double).
 #include "common.cuh"
+#include "vec.cuh"
 
 namespace sarssl {
 
-constexpr int kLnMaxPerLane = 32;      // cols <= 1024
+constexpr int kLnChunks = 4;           // cols <= 1024, cols % 8 == 0: lane owns elements [c*256 + lane*8, +8) of every 256-column chunk c
 
 // ---------------------------------------------------------------- LayerNorm forward: one warp per row
 template <typename T>
@@ -19,29 +20,40 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, lo
     const int row = blockIdx.x * 8 + warp;
     if (row >= rows) return;
     const T* xr = x + (long long)row * ldx;
-    float v[kLnMaxPerLane];
+    float v[kLnChunks][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + i * 32;
-        v[i] = c < cols ? to_f32(xr[c]) : 0.f;
-        s += v[i];
+    for (int c = 0; c < kLnChunks; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < cols) {
+            Vec8<T>::load(xr + col, v[c]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[c][j];
+        }
     }
     const float mu = warp_sum(s) / cols;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + i * 32;
-        const float d = c < cols ? v[i] - mu : 0.f;
-        q += d * d;
+    for (int c = 0; c < kLnChunks; ++c) {
+        if (c * 256 + lane * 8 < cols) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mu; q += d * d; }
+        }
     }
     const float rs = rsqrtf(warp_sum(q) / cols + eps);
     if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
     T* orow = out + (long long)row * ldo;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + i * 32;
-        if (c < cols) orow[c] = from_f32<T>((v[i] - mu) * rs * gamma[c] + beta[c]);
+    for (int c = 0; c < kLnChunks; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < cols) {
+            float g[8], bt[8], o[8];
+            load8f(gamma + col, g);
+            load8f(beta + col, bt);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mu) * rs * g[j] + bt[j];
+            Vec8<T>::store(orow + col, o);
+        }
     }
 }
 
@@ -52,56 +64,73 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, l
                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                    const float* __restrict__ gamma, const T* __restrict__ add, T* __restrict__ dx,
                                                    float* __restrict__ partials, int rows, int cols) {
-    __shared__ float sh[8][64];
+    __shared__ float sh[8][2][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float dg[kLnMaxPerLane], db[kLnMaxPerLane];
+    float dg[kLnChunks][8], db[kLnChunks][8], gm[kLnChunks][8];
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    for (int c = 0; c < kLnChunks; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (col < cols) load8f(gamma + col, gm[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
+    }
     for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
         const T* dyr = dy + (long long)row * lddy;
         const T* xr = x + (long long)row * ldx;
         const float mu = mean[row], rs = rstd[row];
-        float g[kLnMaxPerLane], xh[kLnMaxPerLane];
+        float g[kLnChunks][8], xh[kLnChunks][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < kLnMaxPerLane; ++i) {
-            const int c = lane + i * 32;
-            if (c < cols) {
-                const float d = to_f32(dyr[c]);
-                xh[i] = (to_f32(xr[c]) - mu) * rs;
-                g[i] = d * gamma[c];
-                dg[i] += d * xh[i];
-                db[i] += d;
-                s1 += g[i];
-                s2 += g[i] * xh[i];
-            } else { g[i] = 0.f; xh[i] = 0.f; }
+        for (int c = 0; c < kLnChunks; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < cols) {
+                float d[8], xv[8];
+                Vec8<T>::load(dyr + col, d);
+                Vec8<T>::load(xr + col, xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[c][j] = (xv[j] - mu) * rs;
+                    g[c][j] = d[j] * gm[c][j];
+                    dg[c][j] += d[j] * xh[c][j];
+                    db[c][j] += d[j];
+                    s1 += g[c][j];
+                    s2 += g[c][j] * xh[c][j];
+                }
+            }
         }
         s1 = warp_sum(s1) / cols;
         s2 = warp_sum(s2) / cols;
 #pragma unroll
-        for (int i = 0; i < kLnMaxPerLane; ++i) {
-            const int c = lane + i * 32;
-            if (c < cols) {
-                float v = rs * (g[i] - s1 - xh[i] * s2);
-                if (add) v += to_f32(add[(long long)row * cols + c]);
-                dx[(long long)row * cols + c] = from_f32<T>(v);
+        for (int c = 0; c < kLnChunks; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < cols) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+                if (add) {
+                    float av[8];
+                    Vec8<T>::load(add + (long long)row * cols + col, av);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += av[j];
+                }
+                Vec8<T>::store(dx + (long long)row * cols + col, o);
             }
         }
     }
-    // reduce the 8 warps' dgamma/dbeta, 32 columns at a time
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        if (i * 32 >= cols) break;
-        sh[warp][lane] = dg[i];
-        sh[warp][32 + lane] = db[i];
-        __syncthreads();
-        if (warp == 0) {
-            float a = 0.f, b = 0.f;
+    // reduce the 8 warps' dgamma/dbeta, one 256-column chunk at a time
+    for (int c = 0; c < kLnChunks; ++c) {
+        if (c * 256 >= cols) break;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { a += sh[w][lane]; b += sh[w][32 + lane]; }
-            const int c = lane + i * 32;
-            if (c < cols) {
-                partials[((size_t)blockIdx.x * 2 + 0) * cols + c] = a;
-                partials[((size_t)blockIdx.x * 2 + 1) * cols + c] = b;
+        for (int j = 0; j < 8; ++j) { sh[warp][0][lane * 8 + j] = dg[c][j]; sh[warp][1][lane * 8 + j] = db[c][j]; }
+        __syncthreads();
+        {
+            const int col = c * 256 + threadIdx.x;
+            if (col < cols) {
+                float a = 0.f, bsum = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { a += sh[w][0][threadIdx.x]; bsum += sh[w][1][threadIdx.x]; }
+                partials[((size_t)blockIdx.x * 2 + 0) * cols + col] = a;
+                partials[((size_t)blockIdx.x * 2 + 1) * cols + col] = bsum;
             }
         }
         __syncthreads();
@@ -120,55 +149,91 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 }
 
 // ---------------------------------------------------------------- column sums: partial[cta][cols]
+// CTA = 256 threads = 32 column groups (8 columns each, one 16-byte load) x 8 row lanes; grid.x tiles the columns by 256,
+// grid.y strides the rows.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ partials, int rows, int cols) {
-    // thread t owns columns t, t+256, ...; rows strided over CTAs: coalesced along columns
-    for (int c = threadIdx.x; c < cols; c += 256) {
+    __shared__ float sh[8][256];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col = blockIdx.x * 256 + cg * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (col < cols) {
+        for (int r = blockIdx.y * 8 + rl; r < rows; r += gridDim.y * 8) {
+            float v[8];
+            Vec8<T>::load(x + (long long)r * ldx + col, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[rl][cg * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) {
         float s = 0.f;
-        for (int r = blockIdx.x; r < rows; r += gridDim.x) s += to_f32(x[(long long)r * ldx + c]);
-        partials[(size_t)blockIdx.x * cols + c] = s;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+        partials[(size_t)blockIdx.y * cols + c] = s;
     }
 }
 
 // ---------------------------------------------------------------- BatchNorm over channel-last data [rows][C]
-// mode 0: sums of y and y^2;  mode 1 (backward): sums of dv and dv*xhat where dv = dz * act'(bn(y))
+// mode 0: sums of y and y^2;  mode 1 (backward): sums of dv and dv*xhat where dv = dz * act'(bn(y)).
+// Each thread owns one group of 8 consecutive elements of the flattened tensor per iteration (a 16-byte load); the thread's
+// stride (gridDim.x * 256 * 8 elements) is a multiple of C or C a multiple of 8 groups, so its channel set is fixed:
+//   C % 8 == 0 : channels cbase .. cbase+7 with cbase = (group * 8) % C  -> requires (256 * 8 * gridDim.x) % C == 0
+//   C == 4     : channels 0..3 twice
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dz, const float* __restrict__ mean,
                                                       const float* __restrict__ rstd, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, int act, float* __restrict__ partials,
-                                                      long long rows, int C) {
-    __shared__ float sh[2][256];
-    const int tid = threadIdx.x;
-    const int cw = C < 256 ? C : 256;               // channels covered per pass
-    const int rpi = 256 / cw;                       // rows per iteration (C < 256)
-    const int c0 = tid % cw, rsub = tid / cw;
-    for (int cb = 0; cb < C; cb += 256) {
-        const int c = cb + c0;
-        float a = 0.f, b = 0.f;
-        if (c < C && rsub < rpi) {
-            float mu = 0.f, rs = 0.f, sc = 0.f, shf = 0.f;
-            if (MODE == 1) { mu = mean[c]; rs = rstd[c]; sc = scale[c]; shf = shift[c]; }
-            for (long long r = (long long)blockIdx.x * rpi + rsub; r < rows; r += (long long)gridDim.x * rpi) {
-                const float v = to_f32(y[r * C + c]);
-                if (MODE == 0) { a += v; b += v * v; }
-                else {
-                    float d = to_f32(dz[r * C + c]);
-                    const float u = v * sc + shf;
-                    if (act == 1) d = u > 0.f ? d : 0.f;
-                    else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); d *= sg * (1.0f + u * (1.0f - sg)); }
-                    a += d; b += d * (v - mu) * rs;
-                }
+                                                      long long total, int C) {
+    __shared__ float sa[256][9], sb[256][9];      // per-thread partials, combined in a fixed order below (deterministic)
+    const long long g0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * 256;
+    const int cbase = (C == 4) ? 0 : (int)((g0 * 8) % C);
+    float a[8], b[8], mu[8], rs[8], sc[8], shf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = 0.f; b[j] = 0.f;
+        const int c = (C == 4) ? (j & 3) : cbase + j;
+        if (MODE == 1) { mu[j] = mean[c]; rs[j] = rstd[c]; sc[j] = scale[c]; shf[j] = shift[c]; }
+    }
+    for (long long g = g0; g * 8 < total; g += gstride) {
+        float v[8];
+        Vec8<T>::load(y + g * 8, v);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += v[j]; b[j] += v[j] * v[j]; }
+        } else {
+            float d[8];
+            Vec8<T>::load(dz + g * 8, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float u = v[j] * sc[j] + shf[j];
+                float dv = d[j];
+                if (act == 1) dv = u > 0.f ? dv : 0.f;
+                else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); dv *= sg * (1.0f + u * (1.0f - sg)); }
+                a[j] += dv; b[j] += dv * (v[j] - mu[j]) * rs[j];
             }
         }
-        sh[0][tid] = a; sh[1][tid] = b;
-        __syncthreads();
-        if (tid < cw && cb + tid < C) {
-            float sa = 0.f, sb = 0.f;
-            for (int j = 0; j < rpi; ++j) { sa += sh[0][tid + j * cw]; sb += sh[1][tid + j * cw]; }
-            partials[((size_t)blockIdx.x * 2 + 0) * C + cb + tid] = sa;
-            partials[((size_t)blockIdx.x * 2 + 1) * C + cb + tid] = sb;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sa[threadIdx.x][j] = a[j]; sb[threadIdx.x][j] = b[j]; }
+    __syncthreads();
+    // channel c is held by threads t with (t*8) % C == (c/8)*8, slot c%8 (C % 8 == 0, blockIdx.x*2048 % C == 0); C == 4: every thread, slots c and c+4
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float ta = 0.f, tb = 0.f;
+        if (C == 4) {
+            for (int t = 0; t < 256; ++t) { ta += sa[t][c] + sa[t][c + 4]; tb += sb[t][c] + sb[t][c + 4]; }
+        } else {
+            const int per = C / 8;                  // threads t = c/8 + k*per
+            for (int t = c / 8; t < 256; t += per) { ta += sa[t][c & 7]; tb += sb[t][c & 7]; }
         }
-        __syncthreads();
+        partials[((size_t)blockIdx.x * 2 + 0) * C + c] = ta;
+        partials[((size_t)blockIdx.x * 2 + 1) * C + c] = tb;
     }
 }
 
@@ -211,32 +276,62 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
 
 // z = act(y * scale + shift)
 template <typename T>
-__global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                                  T* __restrict__ z, long long total, int C) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        float u = to_f32(y[i]) * scale[c] + shift[c];
-        if (act == 1) u = fmaxf(u, 0.f);
-        else if (act == 2) u = u / (1.0f + __expf(-u));
-        z[i] = from_f32<T>(u);
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                       T* __restrict__ z, long long total, int C) {
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < total; g += (long long)gridDim.x * 256) {
+        const int cbase = (C == 4) ? 0 : (int)((g * 8) % C);
+        float v[8];
+        Vec8<T>::load(y + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (C == 4) ? (j & 3) : cbase + j;
+            float u = v[j] * scale[c] + shift[c];
+            if (act == 1) u = fmaxf(u, 0.f);
+            else if (act == 2) u = __fdividef(u, 1.0f + __expf(-u));
+            v[j] = u;
+        }
+        Vec8<T>::store(z + g * 8, v);
     }
 }
 
 // dy = gamma * rstd * (dv - sum_dv/R - xhat * sum_dv_xhat/R),  dv = dz * act'(bn(y))
 template <typename T>
-__global__ void bn_act_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const float* __restrict__ sums, int act, T* __restrict__ dy, long long total, int C, float inv_rows) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const float v = to_f32(y[i]);
-        const float u = v * scale[c] + shift[c];
-        float d = to_f32(dz[i]);
-        if (act == 1) d = u > 0.f ? d : 0.f;
-        else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); d *= sg * (1.0f + u * (1.0f - sg)); }
-        const float xh = (v - mean[c]) * rstd[c];
-        dy[i] = from_f32<T>(scale[c] * (d - sums[c] * inv_rows - xh * sums[C + c] * inv_rows));
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       const float* __restrict__ sums, int act, T* __restrict__ dy, long long total, int C, float inv_rows) {
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < total; g += (long long)gridDim.x * 256) {
+        const int cbase = (C == 4) ? 0 : (int)((g * 8) % C);
+        float v[8], d[8];
+        Vec8<T>::load(y + g * 8, v);
+        Vec8<T>::load(dz + g * 8, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (C == 4) ? (j & 3) : cbase + j;
+            const float u = v[j] * scale[c] + shift[c];
+            float dv = d[j];
+            if (act == 1) dv = u > 0.f ? dv : 0.f;
+            else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); dv *= sg * (1.0f + u * (1.0f - sg)); }
+            const float xh = (v[j] - mean[c]) * rstd[c];
+            d[j] = scale[c] * (dv - sums[c] * inv_rows - xh * sums[C + c] * inv_rows);
+        }
+        Vec8<T>::store(dy + g * 8, d);
     }
+}
+
+// number of CTAs for the channel-last BN kernels: every thread must keep a fixed channel set, i.e. (grid * 2048) % C == 0
+static int bn_grid(long long total, int C) {
+    long long g = (total / 8 + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    if (C > 8 && (2048 % C) != 0) {              // C = 512, 768, ...: grid must be a multiple of C / gcd(C, 2048)
+        long long a = C, b2 = 2048;
+        while (b2) { long long t = a % b2; a = b2; b2 = t; }
+        const long long unit = C / a;
+        g = (g / unit) * unit;
+        if (g < unit) g = unit;
+    }
+    return (int)g;
 }
 
 static int capped_grid(long long work_items, int per_cta, int cap_mult) {
@@ -261,7 +356,8 @@ using namespace sarssl;
 extern "C" int sarssl_layernorm_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                                     float* mean, float* rstd, int rows, int cols, float eps, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(x && gamma && beta && out && rows > 0 && cols > 0, "layernorm_fwd: bad arguments");
-    SARSSL_CHECK_ARG(cols <= 32 * kLnMaxPerLane, "layernorm_fwd: cols=%d > %d", cols, 32 * kLnMaxPerLane);
+    SARSSL_CHECK_ARG(cols <= 256 * kLnChunks && cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm_fwd: cols=%d must be a multiple of 8, <= %d", cols,
+                     256 * kLnChunks);
     DISPATCH_T(dtype, (ln_fwd_kernel<T><<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const T*>(x), ldx, gamma, beta, static_cast<T*>(out), ldo,
                                                                         mean, rstd, rows, cols, eps)));
     SARSSL_LAUNCH_CHECK();
@@ -274,7 +370,8 @@ extern "C" int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* 
                                     const float* gamma, const void* add, void* dx, float* dgamma, float* dbeta, int rows, int cols, int dtype,
                                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
-    SARSSL_CHECK_ARG(cols <= 32 * kLnMaxPerLane, "layernorm_bwd: cols=%d too large", cols);
+    SARSSL_CHECK_ARG(cols <= 256 * kLnChunks && cols % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0, "layernorm_bwd: cols=%d must be a multiple of 8, <= %d", cols,
+                     256 * kLnChunks);
     const int grid = capped_grid(rows, 8 * 4, 4);
     if (workspace_bytes < (size_t)grid * 2 * cols * sizeof(float)) { set_last_error("layernorm_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
@@ -289,10 +386,13 @@ extern "C" int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* 
 extern "C" int sarssl_colsum(const void* x, long long ldx, float* out, int rows, int cols, int dtype, int accumulate, void* workspace,
                              size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(x && out && workspace && rows > 0 && cols > 0, "colsum: bad arguments");
-    const int grid = capped_grid(rows, 64, 4);
+    SARSSL_CHECK_ARG(cols % 8 == 0 && ldx % 8 == 0, "colsum: cols and ldx must be multiples of 8");
+    const int gx = (cols + 255) / 256;
+    int grid = capped_grid(rows, 64, 4) / gx;
+    if (grid < 1) grid = 1;
     if (workspace_bytes < (size_t)grid * cols * sizeof(float)) { set_last_error("colsum: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
-    DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), ldx, partials, rows, cols)));
+    DISPATCH_T(dtype, (colsum_kernel<T><<<dim3(gx, grid), 256, 0, stream>>>(static_cast<const T*>(x), ldx, partials, rows, cols)));
     SARSSL_LAUNCH_CHECK();
     reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partials, grid, cols, out, out, cols, accumulate);
     SARSSL_LAUNCH_CHECK();
@@ -304,12 +404,14 @@ extern "C" int sarssl_batchnorm_stats(const void* y, long long rows, int C, cons
                                       float* running_mean, float* running_var, long long* num_batches_tracked, float* stats, int training,
                                       int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(y && gamma && beta && running_mean && running_var && stats && workspace && rows > 0 && C > 0, "batchnorm_stats: bad arguments");
-    const int grid = capped_grid(rows, 512, 4);
+    SARSSL_CHECK_ARG(C == 4 || C % 8 == 0, "batchnorm: C=%d must be 4 or a multiple of 8", C);
+    SARSSL_CHECK_ARG((rows * C) % 8 == 0, "batchnorm: rows*C must be a multiple of 8");
+    const int grid = bn_grid(rows * C, C);
     if (workspace_bytes < (size_t)grid * 2 * C * sizeof(float)) { set_last_error("batchnorm_stats: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     if (training) {
         DISPATCH_T(dtype, (bn_reduce_kernel<T, 0><<<grid, 256, 0, stream>>>(static_cast<const T*>(y), nullptr, nullptr, nullptr, nullptr, nullptr, 0,
-                                                                          partials, rows, C)));
+                                                                          partials, rows * C, C)));
         SARSSL_LAUNCH_CHECK();
     }
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, grid, C, (double)rows, gamma, beta, eps, momentum, running_mean, running_var,
@@ -320,8 +422,9 @@ extern "C" int sarssl_batchnorm_stats(const void* y, long long rows, int C, cons
 
 extern "C" int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int act, void* z, long long rows, int C, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(y && stats && z && rows > 0 && C > 0, "batchnorm_act_fwd: bad arguments");
+    SARSSL_CHECK_ARG((C == 4 || C % 8 == 0) && (rows * C) % 8 == 0, "batchnorm_act_fwd: C=%d must be 4 or a multiple of 8", C);
     const long long total = rows * C;
-    const int grid = capped_grid(total, 1024, 16);
+    const int grid = capped_grid(total, 2048, 16);
     DISPATCH_T(dtype, (bn_act_fwd_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(y), stats + 2 * C, stats + 3 * C, act, static_cast<T*>(z),
                                                                      total, C)));
     SARSSL_LAUNCH_CHECK();
@@ -332,18 +435,19 @@ extern "C" int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int a
 extern "C" int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const float* stats, int act, void* dy, float* dgamma, float* dbeta,
                                         long long rows, int C, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(dz && y && stats && dy && dgamma && dbeta && workspace, "batchnorm_act_bwd: null pointer");
-    const int grid = capped_grid(rows, 512, 4);
+    SARSSL_CHECK_ARG((C == 4 || C % 8 == 0) && (rows * C) % 8 == 0, "batchnorm_act_bwd: C=%d must be 4 or a multiple of 8", C);
+    const int grid = bn_grid(rows * C, C);
     if (workspace_bytes < ((size_t)grid * 2 * C + 2 * C) * sizeof(float)) { set_last_error("batchnorm_act_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     float* sums = partials + (size_t)grid * 2 * C;
     const float *mean = stats, *rstd = stats + C, *scale = stats + 2 * C, *shift = stats + 3 * C;
     DISPATCH_T(dtype, (bn_reduce_kernel<T, 1><<<grid, 256, 0, stream>>>(static_cast<const T*>(y), static_cast<const T*>(dz), mean, rstd, scale, shift,
-                                                                      act, partials, rows, C)));
+                                                                      act, partials, rows * C, C)));
     SARSSL_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, grid, C, sums, dgamma, dbeta);
     SARSSL_LAUNCH_CHECK();
     const long long total = rows * C;
-    const int g2 = capped_grid(total, 1024, 16);
+    const int g2 = capped_grid(total, 2048, 16);
     DISPATCH_T(dtype, (bn_act_bwd_kernel<T><<<g2, 256, 0, stream>>>(static_cast<const T*>(dz), static_cast<const T*>(y), mean, rstd, scale, shift, sums,
                                                                    act, static_cast<T*>(dy), total, C, 1.0f / (float)rows)));
     SARSSL_LAUNCH_CHECK();

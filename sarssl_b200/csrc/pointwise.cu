@@ -5,71 +5,113 @@
 //   relative shift + softmax  conformer/attention.py:87-97,105-113 (scale 1/sqrt(d_model), attention.py:57,91)
 #include "common.cuh"
 #include "rng.cuh"
+#include "vec.cuh"
 
 namespace sarssl {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// All element-wise kernels below move 8 elements (16 bytes of bf16) per thread per iteration; n / D / cols are multiples of 8.
+
 // du = ds * dropmask(idx)/(1-p) * swish'(u)      (FFN: s = Dropout(Swish(u)), feed_forward.py:49-51)
 template <typename T>
-__global__ void swish_bwd_kernel(const T* __restrict__ ds, const T* __restrict__ u, T* __restrict__ du, long long n, float drop_p,
-                                 unsigned long long seed) {
+__global__ void __launch_bounds__(256) swish_bwd_kernel(const T* __restrict__ ds, const T* __restrict__ u, T* __restrict__ du, long long n, float drop_p,
+                                                      unsigned long long seed) {
     const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float d = to_f32(ds[i]);
-        if (drop_p > 0.f) d = keep_mask(seed, (unsigned long long)i, drop_p) ? d * ks : 0.f;
-        const float x = to_f32(u[i]), sg = sigmoidf_(x);
-        du[i] = from_f32<T>(d * sg * (1.0f + x * (1.0f - sg)));
+    const uint32_t thr = drop_threshold(drop_p);
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < n; g += (long long)gridDim.x * 256) {
+        float d[8], x[8];
+        Vec8<T>::load(ds + g * 8, d);
+        Vec8<T>::load(u + g * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            if (drop_p > 0.f) {
+                const uint32_t kp = keep_pair(seed, (unsigned long long)(g * 4 + (j >> 1)), thr);
+                d[j] = (kp & 1u) ? d[j] * ks : 0.f;
+                d[j + 1] = (kp & 2u) ? d[j + 1] * ks : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float sg = sigmoidf_(x[j]); d[j] *= sg * (1.0f + x[j] * (1.0f - sg)); }
+        Vec8<T>::store(du + g * 8, d);
     }
 }
 
 template <typename T>
-__global__ void relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, T* __restrict__ dy, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dy[i] = to_f32(z[i]) > 0.f ? dz[i] : from_f32<T>(0.f);
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, T* __restrict__ dy, long long n) {
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < n; g += (long long)gridDim.x * 256) {
+        float d[8], x[8];
+        Vec8<T>::load(dz + g * 8, d);
+        Vec8<T>::load(z + g * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = x[j] > 0.f ? d[j] : 0.f;
+        Vec8<T>::store(dy + g * 8, d);
+    }
 }
 
 // a[m][d] = g[m][d] * sigmoid(g[m][D + d])         (GLU over channels, convolution.py:139)
 template <typename T>
-__global__ void glu_fwd_kernel(const T* __restrict__ g, T* __restrict__ a, long long rows, int D) {
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ g, T* __restrict__ a, long long rows, int D) {
     const long long n = rows * D;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * 256 * 8) {
         const long long m = i / D; const int d = (int)(i - m * D);
-        a[i] = from_f32<T>(to_f32(g[m * 2 * D + d]) * sigmoidf_(to_f32(g[m * 2 * D + D + d])));
+        float x[8], gt[8];
+        Vec8<T>::load(g + m * 2 * D + d, x);
+        Vec8<T>::load(g + m * 2 * D + D + d, gt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= sigmoidf_(gt[j]);
+        Vec8<T>::store(a + i, x);
     }
 }
 template <typename T>
-__global__ void glu_bwd_kernel(const T* __restrict__ da, const T* __restrict__ g, T* __restrict__ dg, long long rows, int D) {
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ da, const T* __restrict__ g, T* __restrict__ dg, long long rows, int D) {
     const long long n = rows * D;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * 256 * 8) {
         const long long m = i / D; const int d = (int)(i - m * D);
-        const float x = to_f32(g[m * 2 * D + d]), gt = to_f32(g[m * 2 * D + D + d]), sg = sigmoidf_(gt), dd = to_f32(da[i]);
-        dg[m * 2 * D + d] = from_f32<T>(dd * sg);
-        dg[m * 2 * D + D + d] = from_f32<T>(dd * x * sg * (1.0f - sg));
+        float x[8], gt[8], dd[8], o1[8], o2[8];
+        Vec8<T>::load(g + m * 2 * D + d, x);
+        Vec8<T>::load(g + m * 2 * D + D + d, gt);
+        Vec8<T>::load(da + i, dd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float sg = sigmoidf_(gt[j]); o1[j] = dd[j] * sg; o2[j] = dd[j] * x[j] * sg * (1.0f - sg); }
+        Vec8<T>::store(dg + m * 2 * D + d, o1);
+        Vec8<T>::store(dg + m * 2 * D + D + d, o2);
     }
 }
 
 // qu = q + u_bias, qv = q + v_bias; q = first D columns of qkv rows (ld)        attention.py:87-88
 template <typename T>
-__global__ void add_head_bias_kernel(const T* __restrict__ q, long long ld, const float* __restrict__ u, const float* __restrict__ v,
-                                     T* __restrict__ qu, T* __restrict__ qv, long long rows, int D) {
+__global__ void __launch_bounds__(256) add_head_bias_kernel(const T* __restrict__ q, long long ld, const float* __restrict__ u, const float* __restrict__ v,
+                                                          T* __restrict__ qu, T* __restrict__ qv, long long rows, int D) {
     const long long n = rows * D;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * 256 * 8) {
         const long long m = i / D; const int d = (int)(i - m * D);
-        const float x = to_f32(q[m * ld + d]);
-        qu[i] = from_f32<T>(x + u[d]);
-        qv[i] = from_f32<T>(x + v[d]);
+        float x[8], ub[8], vb[8], o[8];
+        Vec8<T>::load(q + m * ld + d, x);
+        load8f(u + d, ub);
+        load8f(v + d, vb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = x[j] + ub[j];
+        Vec8<T>::store(qu + i, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = x[j] + vb[j];
+        Vec8<T>::store(qv + i, o);
     }
 }
 
 // out[m][c] (ldo) = a[m][c] (lda) + b[m][c] (ldb)
 template <typename T>
-__global__ void add2_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out, long long ldo,
-                            long long rows, int cols) {
+__global__ void __launch_bounds__(256) add2_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out,
+                                                 long long ldo, long long rows, int cols) {
     const long long n = rows * cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * 256 * 8) {
         const long long m = i / cols; const int c = (int)(i - m * cols);
-        out[m * ldo + c] = from_f32<T>(to_f32(a[m * lda + c]) + to_f32(b[m * ldb + c]));
+        float x[8], y[8];
+        Vec8<T>::load(a + m * lda + c, x);
+        Vec8<T>::load(b + m * ldb + c, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += y[j];
+        Vec8<T>::store(out + m * ldo + c, x);
     }
 }
 
@@ -78,7 +120,8 @@ __global__ void add2_kernel(const T* __restrict__ a, long long lda, const T* __r
 // one warp per score row
 template <typename T>
 __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const T* __restrict__ content, const T* __restrict__ pos, T* __restrict__ prob,
-                                                             int B, int H, int Tn, float scale) {
+                                                             T* __restrict__ attn, int B, int H, int Tn, float scale, float drop_p,
+                                                             unsigned long long seed) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= (long long)B * H * Tn) return;
@@ -105,11 +148,15 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const T* __restri
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     T* orow = prob + row * Tn;
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     for (int j = lane; j < Tn; j += 32) {
         float ps = 0.f;
         if (j <= i) ps = to_f32(pbase[(long long)i * Tn + (Tn - 1 - i + j)]);
         else if (j > i + 1) ps = to_f32(pbase[(long long)(i + 1) * Tn + (j - i - 2)]);
-        orow[j] = from_f32<T>(__expf((to_f32(crow[j]) + ps) * scale - mx) * inv);
+        const float pv = __expf((to_f32(crow[j]) + ps) * scale - mx) * inv;
+        orow[j] = from_f32<T>(pv);
+        if (attn != nullptr)        // Dropout(attn) (attention.py:98) materialised for the tensor-core context GEMM
+            attn[row * Tn + j] = from_f32<T>(keep_mask(seed, (unsigned long long)(row * Tn + j), drop_p) ? pv * ks : 0.f);
     }
 }
 
@@ -179,7 +226,7 @@ __global__ void fill_f32_kernel(float* p, float v, long long n) {
 }
 
 static int ew_grid(long long n) {
-    long long g = (n + 1023) / 1024;
+    long long g = (n + 2047) / 2048;
     const long long cap = (long long)sm_count() * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
@@ -197,7 +244,7 @@ using namespace sarssl;
 
 extern "C" int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, int dtype,
                                 cudaStream_t stream) {
-    SARSSL_CHECK_ARG(ds && u && du && n > 0, "swish_bwd: bad arguments");
+    SARSSL_CHECK_ARG(ds && u && du && n > 0 && n % 8 == 0, "swish_bwd: bad arguments (n must be a multiple of 8)");
     DISPATCH_T(dtype, (swish_bwd_kernel<T><<<ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(ds), static_cast<const T*>(u), static_cast<T*>(du), n,
                                                                           drop_p, seed)));
     SARSSL_LAUNCH_CHECK();
@@ -205,21 +252,21 @@ extern "C" int sarssl_swish_bwd(const void* ds, const void* u, void* du, long lo
 }
 
 extern "C" int sarssl_relu_bwd(const void* dz, const void* z, void* dy, long long n, int dtype, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(dz && z && dy && n > 0, "relu_bwd: bad arguments");
+    SARSSL_CHECK_ARG(dz && z && dy && n > 0 && n % 8 == 0, "relu_bwd: bad arguments (n must be a multiple of 8)");
     DISPATCH_T(dtype, (relu_bwd_kernel<T><<<ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(dz), static_cast<const T*>(z), static_cast<T*>(dy), n)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 extern "C" int sarssl_glu_fwd(const void* g, void* a, long long rows, int D, int dtype, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(g && a && rows > 0 && D > 0, "glu_fwd: bad arguments");
+    SARSSL_CHECK_ARG(g && a && rows > 0 && D > 0 && D % 8 == 0, "glu_fwd: bad arguments (D must be a multiple of 8)");
     DISPATCH_T(dtype, (glu_fwd_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(g), static_cast<T*>(a), rows, D)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 extern "C" int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long rows, int D, int dtype, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(da && g && dg && rows > 0 && D > 0, "glu_bwd: bad arguments");
+    SARSSL_CHECK_ARG(da && g && dg && rows > 0 && D > 0 && D % 8 == 0, "glu_bwd: bad arguments (D must be a multiple of 8)");
     DISPATCH_T(dtype, (glu_bwd_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(da), static_cast<const T*>(g), static_cast<T*>(dg),
                                                                                rows, D)));
     SARSSL_LAUNCH_CHECK();
@@ -228,7 +275,7 @@ extern "C" int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long
 
 extern "C" int sarssl_add_head_bias(const void* q, long long ld, const float* u_bias, const float* v_bias, void* qu, void* qv, long long rows, int D,
                                     int dtype, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(q && u_bias && v_bias && qu && qv && rows > 0 && D > 0, "add_head_bias: bad arguments");
+    SARSSL_CHECK_ARG(q && u_bias && v_bias && qu && qv && rows > 0 && D > 0 && D % 8 == 0 && ld % 8 == 0, "add_head_bias: bad arguments (D, ld multiples of 8)");
     DISPATCH_T(dtype, (add_head_bias_kernel<T><<<ew_grid(rows * D), 256, 0, stream>>>(static_cast<const T*>(q), ld, u_bias, v_bias, static_cast<T*>(qu),
                                                                                      static_cast<T*>(qv), rows, D)));
     SARSSL_LAUNCH_CHECK();
@@ -237,19 +284,20 @@ extern "C" int sarssl_add_head_bias(const void* q, long long ld, const float* u_
 
 extern "C" int sarssl_add2(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int cols, int dtype,
                            cudaStream_t stream) {
-    SARSSL_CHECK_ARG(a && b && out && rows > 0 && cols > 0, "add2: bad arguments");
+    SARSSL_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && cols % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "add2: bad arguments (multiples of 8)");
     DISPATCH_T(dtype, (add2_kernel<T><<<ew_grid(rows * cols), 256, 0, stream>>>(static_cast<const T*>(a), lda, static_cast<const T*>(b), ldb,
                                                                                static_cast<T*>(out), ldo, rows, cols)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
-extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, int B, int H, int T_, float scale, int dtype,
-                                       cudaStream_t stream) {
+extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, void* attn_dropped, int B, int H, int T_, float scale,
+                                       float drop_p, unsigned long long seed, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(content && pos && prob && B > 0 && H > 0 && T_ > 0, "attn_softmax_fwd: bad arguments");
     const long long rows = (long long)B * H * T_;
     DISPATCH_T(dtype, (attn_softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(content), static_cast<const T*>(pos),
-                                                                                                static_cast<T*>(prob), B, H, T_, scale)));
+                                                                                                static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_, scale,
+                                                                                                drop_p, seed)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
@@ -306,19 +354,27 @@ extern "C" int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t 
 namespace sarssl {
 // dst = alpha * src * dropout_mask(offset)/(1-p): re-applies a forward dropout mask to the incoming gradient
 template <typename T>
-__global__ void scale_dropout_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n, float alpha, float drop_p, unsigned long long seed) {
+__global__ void __launch_bounds__(256) scale_dropout_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n, float alpha, float drop_p,
+                                                          unsigned long long seed) {
     const float ks = drop_p > 0.f ? alpha / (1.0f - drop_p) : alpha;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float v = to_f32(src[i]);
-        v = (drop_p > 0.f && !keep_mask(seed, (unsigned long long)i, drop_p)) ? 0.f : v * ks;
-        dst[i] = from_f32<T>(v);
+    const uint32_t thr = drop_threshold(drop_p);
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < n; g += (long long)gridDim.x * 256) {
+        float v[8];
+        Vec8<T>::load(src + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const uint32_t kp = drop_p > 0.f ? keep_pair(seed, (unsigned long long)(g * 4 + (j >> 1)), thr) : 3u;
+            v[j] = (kp & 1u) ? v[j] * ks : 0.f;
+            v[j + 1] = (kp & 2u) ? v[j + 1] * ks : 0.f;
+        }
+        Vec8<T>::store(dst + g * 8, v);
     }
 }
 }  // namespace sarssl
 
 extern "C" int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, int dtype,
                                     cudaStream_t stream) {
-    SARSSL_CHECK_ARG(src && dst && n > 0, "scale_dropout: bad arguments");
+    SARSSL_CHECK_ARG(src && dst && n > 0 && n % 8 == 0, "scale_dropout: bad arguments (n must be a multiple of 8)");
     DISPATCH_T(dtype, (sarssl::scale_dropout_kernel<T><<<sarssl::ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(src), static_cast<T*>(dst), n, alpha,
                                                                                              drop_p, seed)));
     SARSSL_LAUNCH_CHECK();

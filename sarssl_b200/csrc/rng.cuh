@@ -1,23 +1,35 @@
 // Counter-based dropout RNG.  The reference uses torch.nn.Dropout (Philox, conformer/feed_forward.py:51,53,
 // attention.py:98,151, convolution.py:145); its stream cannot be matched bit for bit, so the CUDA path uses its own
 // stateless generator keyed by (seed, element offset): the backward pass regenerates the forward mask instead of
-// storing it.  keep probability = 1 - p; kept values are scaled by 1/(1-p) by the caller.
+// storing it.  One 32-bit hash serves two neighbouring elements (16 random bits each): an element is dropped when its
+// 16 bits are below p * 65536 (keep probability 1 - p to within 2^-16); kept values are scaled by 1/(1-p) by the caller.
 #pragma once
 #include <stdint.h>
 
 namespace sarssl {
 
-__host__ __device__ __forceinline__ uint32_t mix_hash(unsigned long long seed, unsigned long long idx) {
-    unsigned long long x = idx + seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;       // splitmix64 finaliser
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return (uint32_t)(x >> 32);
+__host__ __device__ __forceinline__ uint32_t hash_pair(unsigned long long seed, unsigned long long pair_idx) {
+    uint32_t x = (uint32_t)pair_idx ^ (uint32_t)seed;
+    uint32_t y = (uint32_t)(pair_idx >> 32) + (uint32_t)(seed >> 32) * 0x9E3779B1u;
+    x *= 0xCC9E2D51u; x = (x << 15) | (x >> 17); x *= 0x1B873593u;      // murmur3-style mixing of the low word
+    x ^= y * 0x85EBCA6Bu + 0x27D4EB2Fu;
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
 }
 
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.0f); }
+
+// keep decision for the element at `idx`
 __host__ __device__ __forceinline__ bool keep_mask(unsigned long long seed, unsigned long long idx, float p) {
-    // uniform in [0,1) with 24 bits; drop when u < p
-    return (float)(mix_hash(seed, idx) >> 8) * (1.0f / 16777216.0f) >= p;
+    const uint32_t h = hash_pair(seed, idx >> 1);
+    const uint32_t bits = (idx & 1ull) ? (h >> 16) : (h & 0xFFFFu);
+    return bits >= drop_threshold(p);
+}
+
+// keep decisions for the aligned pair (2*pair_idx, 2*pair_idx + 1): bit 0 / bit 1 of the result
+__host__ __device__ __forceinline__ uint32_t keep_pair(unsigned long long seed, unsigned long long pair_idx, uint32_t thr) {
+    const uint32_t h = hash_pair(seed, pair_idx);
+    return ((h & 0xFFFFu) >= thr ? 1u : 0u) | ((h >> 16) >= thr ? 2u : 0u);
 }
 
 }  // namespace sarssl

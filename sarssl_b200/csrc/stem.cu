@@ -5,6 +5,7 @@
 //   its weight gradient (split-K over pixels, fixed-order reduction), and the 1x1 conv 64 -> 4.
 // These are the exact-fp32 / reference-check versions; the bf16 tensor-core versions live in conv_tc.cu.
 #include "common.cuh"
+#include "vec.cuh"
 
 namespace sarssl {
 
@@ -40,12 +41,13 @@ __global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__
     const int sub = threadIdx.x & 7;
     for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (long long)gridDim.x * 32) {
         const float4 x = load_narrow<T>(in, p, mode, flag, ch, W, H);
-        T* o = out + p * 64 + sub * 8;
+        float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float* w = ws[sub * 8 + j];
-            o[j] = from_f32<T>(w[0] * x.x + w[1] * x.y + w[2] * x.z + w[3] * x.w);
+            o[j] = w[0] * x.x + w[1] * x.y + w[2] * x.z + w[3] * x.w;
         }
+        Vec8<T>::store(out + p * 64 + sub * 8, o);
     }
 }
 
@@ -65,11 +67,12 @@ __global__ void __launch_bounds__(256) pw_reduce_kernel(const T* __restrict__ in
         const long long p = ((long long)it * gridDim.x + blockIdx.x) * 32 + (threadIdx.x >> 3);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (p < P) {
-            const T* q = in + p * 64 + sub * 8;
+            float qv[8];
+            Vec8<T>::load(in + p * 64 + sub * 8, qv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int o = sub * 8 + j;
-                float v = to_f32(q[j]);
+                float v = qv[j];
                 if (tr) v = fmaxf(v * sc[o] + sh[o], 0.f);
                 a0 = fmaf(ws[0][o], v, a0); a1 = fmaf(ws[1][o], v, a1); a2 = fmaf(ws[2][o], v, a2); a3 = fmaf(ws[3][o], v, a3);
             }
@@ -102,10 +105,11 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
     for (long long p = (long long)blockIdx.x * 32 + pl; p < P; p += (long long)gridDim.x * 32) {
         const float4 x = load_narrow<T>(narrow, p, mode, flag, ch, W, H);
-        const T* q = wide + p * 64 + sub * 8;
+        float qv[8];
+        Vec8<T>::load(wide + p * 64 + sub * 8, qv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = to_f32(q[j]);
+            float v = qv[j];
             if (tr) v = fmaxf(v * sc[j] + sh[j], 0.f);
             acc[j][0] = fmaf(v, x.x, acc[j][0]); acc[j][1] = fmaf(v, x.y, acc[j][1]);
             acc[j][2] = fmaf(v, x.z, acc[j][2]); acc[j][3] = fmaf(v, x.w, acc[j][3]);

@@ -197,13 +197,15 @@ class Engine:
         content, pos, prob = k.empty(B, H, T, T), k.empty(H, B, T, T), k.empty(B, H, T, T)
         k.gemm(qu, qkv, content, T, T, dh, (D, 1), (3 * D, 1), T, b_off=D, batch=(B, H), sAb=(T * D, dh), sBb=(T * 3 * D, dh), sCb=(H * T * T, T * T))
         k.gemm(qv, pp, pos, T, T, dh, (D, 1), (D, 1), T, batch=(B, H), sAb=(T * D, dh), sBb=(0, dh), sCb=(T * T, B * T * T))
-        k.attn_softmax_fwd(content, pos, prob, B, H, T, 1.0 / math.sqrt(D))
-        del content, pos
         dp = (p_drop, _site_seed(self.step_seed, site[0])); site[0] += 1
         do = (p_drop, _site_seed(self.step_seed, site[0])); site[0] += 1
+        attn = k.empty(B, H, T, T) if p_drop > 0 else None            # Dropout(prob), materialised so the context GEMMs run on tensor cores
+        k.attn_softmax_fwd(content, pos, prob, attn, B, H, T, 1.0 / math.sqrt(D), dp)
+        del content, pos
+        if attn is None:
+            attn = prob
         ctx = k.empty(M, D)
-        k.gemm(prob, qkv, ctx, T, dh, T, (T, 1), (1, 3 * D), D, b_off=2 * D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * 3 * D, dh), sCb=(T * D, dh),
-               a_drop=dp)
+        k.gemm(attn, qkv, ctx, T, dh, T, (T, 1), (1, 3 * D), D, b_off=2 * D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * 3 * D, dh), sCb=(T * D, dh))
         x2 = k.empty(M, D)
         k.linear(ctx, self.w(a + ".out_proj.linear.weight"), x2, M, D, D, bias=st.p(a + ".out_proj.linear.bias"), resid=x1, ldr=D, beta=1.0, drop=do)
         # ---- convolution module                                                                  convolution.py:136-149
@@ -234,7 +236,7 @@ class Engine:
             k.layernorm_fwd(x4, D, st.p(s + ".4.weight"), st.p(s + ".4.bias"), buf, ld, mean5, rstd5, M, D, out_off=col)
             y = None
         if sv is not None:
-            rec.update(f1=f1, f2=f2, x1=x1, h2=h2, mean2=mean2, rstd2=rstd2, qkv=qkv, pp=pp, qu=qu, qv=qv, prob=prob, ctx=ctx, dp=dp, do=do,
+            rec.update(f1=f1, f2=f2, x1=x1, h2=h2, mean2=mean2, rstd2=rstd2, qkv=qkv, pp=pp, qu=qu, qv=qv, prob=prob, attn=attn, ctx=ctx, dp=dp, do=do,
                        x2=x2, h3=h3, mean3=mean3, rstd3=rstd3, g=g, ga=ga, cv=cv, sbn=sbn, z=z, dc=dc, x3=x3, x4=x4, mean5=mean5, rstd5=rstd5)
             sv[pre] = rec
         return y
@@ -333,8 +335,8 @@ class Engine:
         k.gemm(dctx, qkv, dattn, T, T, dh_, (D, 1), (3 * D, 1), T, b_off=2 * D, batch=(B, H), sAb=(T * D, dh_), sBb=(T * 3 * D, dh_), sCb=(H * T * T, T * T))
         dqkv = k.empty(M, 3 * D)
         # dV[b, j, h, :] = sum_i drop(prob)[b, h, i, j] * dctx[b, i, h, :]
-        k.gemm(prob, dctx, dqkv, T, dh_, T, (1, T), (1, D), 3 * D, c_off=2 * D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * D, dh_), sCb=(T * 3 * D, dh_),
-               a_drop=rec["dp"])
+        k.gemm(rec["attn"], dctx, dqkv, T, dh_, T, (1, T), (1, D), 3 * D, c_off=2 * D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * D, dh_),
+               sCb=(T * 3 * D, dh_))
         dpos = k.empty(H, B, T, T)
         k.attn_softmax_bwd(dattn, prob, dpos, B, H, T, 1.0 / math.sqrt(D), rec["dp"])                              # dattn now holds dscore
         dqu, dqv = do, dctx

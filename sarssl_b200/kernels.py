@@ -61,7 +61,7 @@ class KernelSet:
         g.alpha, g.beta = alpha, beta
         g.drop_p, g.drop_seed = drop
         g.a_drop_p, g.a_drop_seed = a_drop
-        if self.use_tc and A.dtype == torch.bfloat16 and batch == (1, 1) and a_drop[0] == 0.0:
+        if self.use_tc and A.dtype == torch.bfloat16 and a_drop[0] == 0.0:
             rc = self.L.sarssl_gemm_tc(C.byref(g), self.stream)      # tcgen05 path; -3 = shape/stride it does not take
             if rc == 0:
                 self.launches += 1
@@ -135,8 +135,9 @@ class KernelSet:
     def add2(self, a, lda, b, ldb, out, ldo, rows, cols, out_off=0):
         self._ok(self.L.sarssl_add2(ptr(a), lda, ptr(b), ldb, _addr(out, out_off), ldo, rows, cols, self.dt, self.stream), "add2")
 
-    def attn_softmax_fwd(self, content, pos, prob, B, H, T, scale):
-        self._ok(self.L.sarssl_attn_softmax_fwd(ptr(content), ptr(pos), ptr(prob), B, H, T, scale, self.dt, self.stream), "attn_softmax_fwd")
+    def attn_softmax_fwd(self, content, pos, prob, attn, B, H, T, scale, drop):
+        self._ok(self.L.sarssl_attn_softmax_fwd(ptr(content), ptr(pos), ptr(prob), ptr(attn), B, H, T, scale, drop[0], drop[1], self.dt, self.stream),
+                 "attn_softmax_fwd")
 
     def attn_softmax_bwd(self, dattn, prob, dpos, B, H, T, scale, drop):
         self._ok(self.L.sarssl_attn_softmax_bwd(ptr(dattn), ptr(prob), ptr(dpos), B, H, T, scale, drop[0], drop[1], self.dt, self.stream),
