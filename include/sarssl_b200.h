@@ -263,6 +263,17 @@ int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_s
                      float beta1, float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * A15  data-parallel gradient exchange (replaces nn.DataParallel, learner.py:25-31): NCCL sum all-reduce of contiguous buckets
+ * of the flat fp32 gradient arena; one communicator per process; the only process-global state of the library.
+ * ---------------------------------------------------------------------------------------------------------- */
+int sarssl_comm_unique_id_bytes(void);
+int sarssl_comm_get_unique_id(void* id_host);                 /* rank 0; distribute the bytes to the other ranks out of band */
+int sarssl_comm_init(int rank, int world, const void* id_host);
+int sarssl_comm_world_size(void);
+int sarssl_allreduce_sum_f32(float* buf, size_t n, cudaStream_t stream);
+int sarssl_comm_destroy(void);
+
+/* ------------------------------------------------------------------------------------------------------------
  * diagnostics
  * ---------------------------------------------------------------------------------------------------------- */
 /* Hardware probe used by tests/test_tc_probe_gpu.py: one UMMA tile whose A descriptor starts row_off (0..7) 128-byte rows into

@@ -137,13 +137,26 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, l
     }
 }
 
-// out[w] (+)= sum_p partials[p][w]  (double accumulation, fixed order)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[w] (+)= sum_p partials[p][w]  (double accumulation, fixed order).  32 consecutive outputs per warp: every lane walks the
+// partials of its own column (coalesced across the warp).
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out0,
                                        float* __restrict__ out1, int split, int accumulate) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= width) return;
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * width + w];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 3 < nparts; p += 4) {
+        s0 += (double)partials[(size_t)p * width + w]; s1 += (double)partials[(size_t)(p + 1) * width + w];
+        s2 += (double)partials[(size_t)(p + 2) * width + w]; s3 += (double)partials[(size_t)(p + 3) * width + w];
+    }
+    for (; p < nparts; ++p) s0 += (double)partials[(size_t)p * width + w];
+    const double s = (s0 + s1) + (s2 + s3);
     float* dst = (w < split) ? out0 + w : out1 + (w - split);
     *dst = accumulate ? *dst + (float)s : (float)s;
 }
@@ -237,41 +250,50 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
     }
 }
 
-// partials [nparts][2][C] -> batch statistics, affine scale/shift, running-stat update (momentum, unbiased variance)
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ num_batches, float* __restrict__ mean,
-                                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int training) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// partials [nparts][2][C] -> batch statistics, affine scale/shift, running-stat update (momentum, unbiased variance).
+// One warp per channel: lanes stride the partials, fixed-order double sums.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                                        float* __restrict__ running_var, long long* __restrict__ num_batches, float* __restrict__ mean,
+                                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift, int training) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     float mu, var;
     if (training) {
         double s = 0.0, q = 0.0;
-        for (int p = 0; p < nparts; ++p) { s += (double)partials[((size_t)p * 2 + 0) * C + c]; q += (double)partials[((size_t)p * 2 + 1) * C + c]; }
+        for (int p = lane; p < nparts; p += 32) { s += (double)partials[((size_t)p * 2 + 0) * C + c]; q += (double)partials[((size_t)p * 2 + 1) * C + c]; }
+        s = warp_sum_d(s); q = warp_sum_d(q);
         const double m = s / count;
         double v = q / count - m * m;
         if (v < 0.0) v = 0.0;
         mu = (float)m; var = (float)v;
-        const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
-        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mu;
-        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
-        if (c == 0 && num_batches) *num_batches += 1;
+        if (lane == 0) {
+            const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+            if (c == 0 && num_batches) *num_batches += 1;
+        }
     } else { mu = running_mean[c]; var = running_var[c]; }
-    const float rs = rsqrtf(var + eps);
-    mean[c] = mu; rstd[c] = rs;
-    scale[c] = gamma[c] * rs;
-    shift[c] = beta[c] - mu * gamma[c] * rs;
+    if (lane == 0) {
+        const float rs = rsqrtf(var + eps);
+        mean[c] = mu; rstd[c] = rs;
+        scale[c] = gamma[c] * rs;
+        shift[c] = beta[c] - mu * gamma[c] * rs;
+    }
 }
 
 // backward finalize: partials -> (sum_dv, sum_dv_xhat); dgamma += sum_dv_xhat, dbeta += sum_dv
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, float* __restrict__ sums,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, float* __restrict__ sums,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
-    for (int p = 0; p < nparts; ++p) { s += (double)partials[((size_t)p * 2 + 0) * C + c]; q += (double)partials[((size_t)p * 2 + 1) * C + c]; }
-    sums[c] = (float)s; sums[C + c] = (float)q;
-    dgamma[c] += (float)q; dbeta[c] += (float)s;
+    for (int p = lane; p < nparts; p += 32) { s += (double)partials[((size_t)p * 2 + 0) * C + c]; q += (double)partials[((size_t)p * 2 + 1) * C + c]; }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (lane == 0) {
+        sums[c] = (float)s; sums[C + c] = (float)q;
+        dgamma[c] += (float)q; dbeta[c] += (float)s;
+    }
 }
 
 // z = act(y * scale + shift)
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ d
 // number of CTAs for the channel-last BN kernels: every thread must keep a fixed channel set, i.e. (grid * 2048) % C == 0
 static int bn_grid(long long total, int C) {
     long long g = (total / 8 + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
+    const long long cap = (long long)sm_count() * 4;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     if (C > 8 && (2048 % C) != 0) {              // C = 512, 768, ...: grid must be a multiple of C / gcd(C, 2048)
@@ -414,7 +436,7 @@ extern "C" int sarssl_batchnorm_stats(const void* y, long long rows, int C, cons
                                                                           partials, rows * C, C)));
         SARSSL_LAUNCH_CHECK();
     }
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, grid, C, (double)rows, gamma, beta, eps, momentum, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, grid, C, (double)rows, gamma, beta, eps, momentum, running_mean, running_var,
                                                            num_batches_tracked, stats, stats + C, stats + 2 * C, stats + 3 * C, training);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
@@ -444,7 +466,7 @@ extern "C" int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const flo
     DISPATCH_T(dtype, (bn_reduce_kernel<T, 1><<<grid, 256, 0, stream>>>(static_cast<const T*>(y), static_cast<const T*>(dz), mean, rstd, scale, shift,
                                                                       act, partials, rows * C, C)));
     SARSSL_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, grid, C, sums, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, grid, C, sums, dgamma, dbeta);
     SARSSL_LAUNCH_CHECK();
     const long long total = rows * C;
     const int g2 = capped_grid(total, 2048, 16);

@@ -132,8 +132,14 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
 __global__ void stem_reduce_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out, int accumulate) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= width) return;
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * width + w];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 3 < nparts; p += 4) {
+        s0 += (double)partials[(size_t)p * width + w]; s1 += (double)partials[(size_t)(p + 1) * width + w];
+        s2 += (double)partials[(size_t)(p + 2) * width + w]; s3 += (double)partials[(size_t)(p + 3) * width + w];
+    }
+    for (; p < nparts; ++p) s0 += (double)partials[(size_t)p * width + w];
+    const double s = (s0 + s1) + (s2 + s3);
     out[w] = accumulate ? out[w] + (float)s : (float)s;
 }
 
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const T* __restrict_
 
 static int pix_grid(long long P) {
     long long g = (P + 31) / 32;
-    const long long cap = (long long)sm_count() * 8;
+    const long long cap = (long long)sm_count() * 4;
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 

@@ -242,8 +242,9 @@ class Engine:
         return y
 
     # ------------------------------------------------------------------------------------------------ backward
-    def backward(self, sv, gscale=None):
-        """Accumulates d loss / d parameter into the gradient arena.  gscale: device scalar multiplying the loss gradient."""
+    def backward(self, sv, gscale=None, on_ready=None):
+        """Accumulates d loss / d parameter into the gradient arena.  gscale: device scalar multiplying the loss gradient.
+        on_ready(name) is called when a gradient bucket (sarssl_b200/parallel.py) is complete, so its all-reduce can start."""
         k, st = self.k, self.store
         B, T, F = sv["B"], sv["T"], sv["F"]
         M = B * T
@@ -264,12 +265,17 @@ class Engine:
         dcat = k.empty(M, Dc)
         k.linear_dgrad(dh, self.w("decoder.proj.0.weight"), dcat, M, dff, Dc)
         del dh
+        ready = on_ready if on_ready is not None else (lambda name: None)
+        ready("decoder")
         for enc, D, nl, mode, col in ENCODERS:
             d = None
             for l in reversed(range(nl)):
                 last = l == nl - 1
                 d = self._block_bwd(f"{enc}.embed.layers.{l}", D, sv, B, T, dout=(dcat, col, Dc) if last else (d, 0, D))
+                if enc == "spat_encoder" and l == 1:
+                    ready("spat_blocks_1_2")
             self._stem_bwd(enc, D, mode, sv, d, B, T, F)
+            ready("spec_encoder" if enc == "spec_encoder" else "spat_stem_block_0")
 
     def _ffn_bwd(self, pre, D, rec, dxo, M):
         """dxo = gradient w.r.t. the module output x + 0.5*FFN(x); returns the gradient w.r.t. x."""

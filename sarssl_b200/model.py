@@ -63,7 +63,8 @@ class _PretrainFn(torch.autograd.Function):
         if ctx.saved is None:
             raise _lib.SarsslError("backward() through a forward that ran without gradient tracking (eval() or no_grad())")
         ctx.model.store.reattach_grads()
-        ctx.model.engine.backward(ctx.saved, gscale=g_loss.reshape(1).float().contiguous())
+        sync = getattr(ctx.model, "grad_sync", None)
+        ctx.model.engine.backward(ctx.saved, gscale=g_loss.reshape(1).float().contiguous(), on_ready=sync.bucket_ready if sync is not None else None)
         ctx.saved = None
         return None, None, None, None, None, None
 
@@ -115,6 +116,8 @@ class SARSSL(nn.Module):
         self.compute_dtype = torch.float32
         self.dropout_p = 0.1
         self.rng_state = None            # None: consume python's global `random` stream like the reference; else np.uint32[625]
+        self.grad_sync = None
+        self.dp = None                   # (rank, world) once data parallel: masks are drawn for the global batch and sliced
         self._anchor = torch.zeros((), requires_grad=True)
         self._last = None
 
@@ -153,7 +156,7 @@ class SARSSL(nn.Module):
         nb, nt, nf = patches.shape[:3]
         if (nf, nt) != tuple(self.sig_shape[:2]):
             raise _lib.SarsslError(f"input is {nf} bins x {nt} frames but the model was built for {self.sig_shape[:2]}")
-        pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state)
+        pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state, dp=self.dp)
         want = torch.is_grad_enabled() and self.training
         loss, diff = _PretrainFn.apply(self._anchor, self, patches, flag, cidx, want)
         vis = VisDict(self._last["pred"], patches, flag, cidx)
