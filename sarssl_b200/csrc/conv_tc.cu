@@ -35,6 +35,18 @@ __device__ __forceinline__ void ctma_load_4d(void* dst, const CUtensorMap* map, 
 __device__ __forceinline__ uint64_t cdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
+// descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | SWIZZLE_128B (bits 61-63).  The MMA-issuing thread
+// keeps `hi` and a per-operand base `lo` in registers and only adds a small constant per instruction.
+__device__ __forceinline__ uint32_t cdesc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ constexpr uint32_t cdesc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void cumma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void cumma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db),
                  "r"(idesc), "r"(acc) : "memory");
@@ -65,7 +77,8 @@ constexpr int CBOXB = CBOXR * 128;       // 17408 B (multiple of 1024)
 constexpr int CSLOTS = 6;                // ring of row boxes
 constexpr int CSEG = 32;                 // image rows per work unit (2 halo row loads amortised over 32 tiles)
 constexpr int CWB = 9 * 8192;            // resident weights
-constexpr int kConvSmem = CSLOTS * CBOXB + CWB + 1024 + 256;
+constexpr int COUTB = CW * 128;           // 16 KB output staging tile (x2)
+constexpr int kConvSmem = CSLOTS * CBOXB + CWB + 2 * COUTB + 1024 + 256;
 constexpr int kConvThreads = 192;
 
 struct ConvP {
@@ -74,12 +87,14 @@ struct ConvP {
     long long nunits;
 };
 
-__global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, ConvP p) {
+__global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                                                                const __grid_constant__ CUtensorMap tmOut, ConvP p) {
     extern __shared__ unsigned char raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* ring = smem;
     unsigned char* wsm = smem + CSLOTS * CBOXB;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + CSLOTS * CBOXB + CWB);
+    unsigned char* osm = smem + CSLOTS * CBOXB + CWB;            // 2 x 16 KB, 1024-aligned
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + CSLOTS * CBOXB + CWB + 2 * COUTB);
     uint64_t* empty = full + CSLOTS;
     uint64_t* wbar = empty + CSLOTS;
     uint64_t* tfull = wbar + 1;          // [2]
@@ -90,6 +105,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
         for (int s = 0; s < CSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(wbar, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
@@ -108,96 +124,115 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
         if (lane == 0) {
             mbar_expect_tx(wbar, CWB);
             for (int t = 0; t < 9; ++t) ctma_load_2d(wsm + t * 8192, &tmW, t * 64, 0, wbar);
-            long long ib = 0;                                   // global box counter
+            int s = 0;
+            uint32_t ephase = 0;                                // bit s = phase of empty[s] to wait for next (starts "already free")
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const long long r = u / p.nseg_h;
                 const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
                 const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
-                for (int row = h0 - 1; row <= h1; ++row, ++ib) {
-                    const int s = (int)(ib % CSLOTS);
-                    const uint32_t ph = (uint32_t)((ib / CSLOTS) & 1);
-                    mbar_wait(&empty[s], ph ^ 1);
+                for (int row = h0 - 1; row <= h1; ++row) {
+                    mbar_wait(&empty[s], ((ephase >> s) & 1u) ^ 1u);
+                    ephase ^= 1u << s;
                     mbar_expect_tx(&full[s], CBOXB);
                     ctma_load_4d(ring + s * CBOXB, &tmIn, 0, w0 - 1, row, b, &full[s]);
+                    if (++s == CSLOTS) s = 0;
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t hi = cdesc_hi(1024);
             mbar_wait(wbar, 0);
-            long long ib = 0, it = 0;                           // box / tile counters
-            const uint32_t w_addr = smem_u32(wsm);
+            const uint32_t w_lo = cdesc_lo(smem_u32(wsm), 16), ring_lo = cdesc_lo(smem_u32(ring), 16);
+            int slot0 = 0;                                      // ring slot of the oldest row box of the current tile
+            uint32_t fphase = 0;                                // bit s = phase of full[s] expected next
+            uint32_t it = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG);
                 const int ntile = h1 - h0;
                 for (int t = 0; t < ntile; ++t, ++it) {
-                    // rows needed: boxes ib+t, ib+t+1, ib+t+2; each box's full barrier is waited exactly once, in order
+                    // rows needed: slots slot0, slot0+1, slot0+2; each box's full barrier is waited exactly once, in order
                     for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
-                        const long long bi = ib + t + j;
-                        mbar_wait(&full[bi % CSLOTS], (uint32_t)((bi / CSLOTS) & 1));
+                        int sj = slot0 + j; if (sj >= CSLOTS) sj -= CSLOTS;
+                        mbar_wait(&full[sj], (fphase >> sj) & 1u);
+                        fphase ^= 1u << sj;
                     }
-                    const int acc = (int)(it & 1);
-                    mbar_wait(&tempty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                    const uint32_t acc = it & 1u;
+                    mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
                     cfence_after();
                     const uint32_t d = tmem + acc * 64;
 #pragma unroll
                     for (int dh = 0; dh < 3; ++dh) {
-                        const uint32_t a_addr = smem_u32(ring + ((ib + t + dh) % CSLOTS) * CBOXB);
+                        int sd = slot0 + dh; if (sd >= CSLOTS) sd -= CSLOTS;
+                        const uint32_t a_lo = ring_lo + (uint32_t)sd * (CBOXB >> 4);
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                cumma(d, cdesc(a_addr + dw * 128 + k * 32, 16, 1024), cdesc(w_addr + (dh * 3 + dw) * 8192 + k * 32, 16, 1024), idesc,
-                                      (uint32_t)((dh | dw | k) != 0));
+                                cumma2(d, a_lo + dw * 8 + k * 2, hi, w_lo + (dh * 3 + dw) * 512 + k * 2, hi, idesc, (uint32_t)((dh | dw | k) != 0));
                         }
                     }
-                    ccommit(&empty[(ib + t) % CSLOTS]);         // the oldest row is dead after this tile
-                    if (t == ntile - 1) { ccommit(&empty[(ib + t + 1) % CSLOTS]); ccommit(&empty[(ib + t + 2) % CSLOTS]); }
+                    ccommit(&empty[slot0]);                     // the oldest row is dead after this tile
+                    if (t == ntile - 1) {
+                        int s1 = slot0 + 1; if (s1 >= CSLOTS) s1 -= CSLOTS;
+                        int s2 = slot0 + 2; if (s2 >= CSLOTS) s2 -= CSLOTS;
+                        ccommit(&empty[s1]); ccommit(&empty[s2]);
+                        slot0 += 3; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
+                    } else { slot0 += 1; if (slot0 >= CSLOTS) slot0 -= CSLOTS; }
                     ccommit(&tfull[acc]);
                 }
-                ib += ntile + 2;
             }
         }
     } else {
         const int q = warp & 3;
-        long long it = 0;
+        const int row = q * 32 + lane;                          // pixel row of the tile = TMEM lane
+        uint32_t it = 0;
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const int hs = (int)(u % p.nseg_h);
             const long long r = u / p.nseg_h;
             const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
             const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
             for (int h = h0; h < h1; ++h, ++it) {
-                const int acc = (int)(it & 1);
-                mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
+                const uint32_t acc = it & 1u;
+                unsigned char* stage = osm + acc * COUTB;
+                // the TMA store that last read this staging buffer (2 tiles ago) must have finished reading it
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(&tfull[acc], (it >> 1) & 1u);
                 cfence_after();
-                const int w = w0 + q * 32 + lane;
-                __nv_bfloat16* orow = p.out + (((long long)b * p.H + h) * p.W + w) * 64;
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t v[32];
                     ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
-                    if (w < p.W) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(orow + c0 + j) = pk;
-                        }
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        const int chunk = (c0 + j) >> 3;                       // 16-byte chunk of the 128-byte pixel row
+                        *reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;     // 128B swizzle, as the TMA store expects
                     }
                 }
                 cfence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) mbar_arrive(&tempty[acc]);       // TMEM buffer free for the MMA warp
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmOut), "r"(0), "r"(w0), "r"(h), "r"(b),
+                                 "r"(smem_u32(stage)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
         }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     cfence_before();
     __syncthreads();
@@ -256,24 +291,26 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
 
     if (warp == 0) {
         if (lane == 0) {
-            long long ib = 0, id = 0;
+            int s = 0, sd = 0;
+            uint32_t ephase = 0, dephase = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const long long r = u / p.nseg_h;
                 const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
                 const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG), w0 = wt * GK;
                 // interleave: input rows h0-1, h0 first, then for each output row h: input row h+1 and dy row h
-                for (int row = h0 - 1; row <= h1; ++row, ++ib) {
-                    const int s = (int)(ib % GSLOTS);
-                    mbar_wait(&empty[s], (uint32_t)(((ib / GSLOTS) & 1) ^ 1));
+                for (int row = h0 - 1; row <= h1; ++row) {
+                    mbar_wait(&empty[s], ((ephase >> s) & 1u) ^ 1u);
+                    ephase ^= 1u << s;
                     mbar_expect_tx(&full[s], GBOXR * 128);
                     ctma_load_4d(ring + s * GBOXB, &tmIn, 0, w0 - 1, row, b, &full[s]);
+                    if (++s == GSLOTS) s = 0;
                     if (row >= h0 + 1) {                        // dy row (row - 1) is needed together with input row `row`
-                        const int sd = (int)(id % GDY);
-                        mbar_wait(&dempty[sd], (uint32_t)(((id / GDY) & 1) ^ 1));
+                        mbar_wait(&dempty[sd], ((dephase >> sd) & 1u) ^ 1u);
+                        dephase ^= 1u << sd;
                         mbar_expect_tx(&dfull[sd], 8192);
                         ctma_load_4d(dyr + sd * 8192, &tmDy, 0, w0, row - 1, b, &dfull[sd]);
-                        ++id;
+                        if (++sd == GDY) sd = 0;
                     }
                 }
             }
@@ -282,38 +319,48 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
         if (lane == 0) {
             // A (input taps) MN-major M = 128: two 64-channel groups LBO apart; B (dy) MN-major N = 64
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-            long long ib = 0, id = 0;
+            constexpr uint32_t hi = cdesc_hi(1024);
+            const uint32_t ring_lo = cdesc_lo(smem_u32(ring), 128), dy_lo0 = cdesc_lo(smem_u32(dyr), 8192);
+            int slot0 = 0, sd = 0;
+            uint32_t fphase = 0, dphase = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG);
                 const int ntile = h1 - h0;
-                for (int t = 0; t < ntile; ++t, ++id) {
+                for (int t = 0; t < ntile; ++t) {
                     for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
-                        const long long bi = ib + t + j;
-                        mbar_wait(&full[bi % GSLOTS], (uint32_t)((bi / GSLOTS) & 1));
+                        int sj = slot0 + j; if (sj >= GSLOTS) sj -= GSLOTS;
+                        mbar_wait(&full[sj], (fphase >> sj) & 1u);
+                        fphase ^= 1u << sj;
                     }
-                    const int sd = (int)(id % GDY);
-                    mbar_wait(&dfull[sd], (uint32_t)((id / GDY) & 1));
+                    mbar_wait(&dfull[sd], (dphase >> sd) & 1u);
+                    dphase ^= 1u << sd;
                     cfence_after();
-                    const uint32_t dy_addr = smem_u32(dyr + sd * 8192);
+                    const uint32_t dy_lo = dy_lo0 + (uint32_t)sd * (8192 >> 4);
+                    const uint32_t accf = any ? 1u : 0u;
 #pragma unroll
                     for (int dh = 0; dh < 3; ++dh) {
-                        const uint32_t a_addr = smem_u32(ring + ((ib + t + dh) % GSLOTS) * GBOXB);
+                        int sr = slot0 + dh; if (sr >= GSLOTS) sr -= GSLOTS;
+                        const uint32_t a_lo = ring_lo + (uint32_t)sr * (GBOXB >> 4);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {                  // taps (dw = -1, 0) together, then (dw = +1, -)
                             const uint32_t d = tmem + (dh * 2 + half) * 64;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                cumma(d, cdesc(a_addr + half * 256 + k * 2048, 128, 1024), cdesc(dy_addr + k * 2048, 8192, 1024), idesc,
-                                      (uint32_t)(any || k != 0));
+                                cumma2(d, a_lo + half * 16 + k * 128, hi, dy_lo + k * 128, hi, idesc, k == 0 ? accf : 1u);
                         }
                     }
                     any = true;
-                    ccommit(&empty[(ib + t) % GSLOTS]);
-                    if (t == ntile - 1) { ccommit(&empty[(ib + t + 1) % GSLOTS]); ccommit(&empty[(ib + t + 2) % GSLOTS]); }
+                    ccommit(&empty[slot0]);
+                    if (t == ntile - 1) {
+                        int s1 = slot0 + 1; if (s1 >= GSLOTS) s1 -= GSLOTS;
+                        int s2 = slot0 + 2; if (s2 >= GSLOTS) s2 -= GSLOTS;
+                        ccommit(&empty[s1]); ccommit(&empty[s2]);
+                        slot0 += 3; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
+                    } else { slot0 += 1; if (slot0 >= GSLOTS) slot0 -= GSLOTS; }
                     ccommit(&dempty[sd]);
+                    if (++sd == GDY) sd = 0;
                 }
-                ib += ntile + 2;
             }
             ccommit(done);
         }
@@ -396,9 +443,10 @@ using namespace sarssl;
 extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, int B, int H, int W, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight_packed && out && B > 0 && H > 0 && W > 0, "conv3x3_tc: bad arguments");
     SARSSL_CHECK_ARG(aligned16(in) && aligned16(weight_packed) && aligned16(out), "conv3x3_tc: buffers must be 16-byte aligned");
-    CUtensorMap mi, mw;
+    CUtensorMap mi, mw, mo;
     int rc;
     if ((rc = image_map(&mi, in, B, H, W, CBOXR))) return rc;
+    if ((rc = image_map(&mo, out, B, H, W, CW))) return rc;
     {
         CEncFn fn = cenc();
         cuuint64_t dims[2] = {576, 64}, strides[1] = {576 * 2};
@@ -416,7 +464,7 @@ extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void
     p.tiles_w = (W + CW - 1) / CW; p.nseg_h = (H + CSEG - 1) / CSEG;
     p.nunits = (long long)B * p.tiles_w * p.nseg_h;
     const int grid = (int)(p.nunits < sm_count() ? p.nunits : sm_count());
-    conv3x3_tc_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(mi, mw, p);
+    conv3x3_tc_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(mi, mw, mo, p);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

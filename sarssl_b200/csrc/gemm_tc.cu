@@ -60,6 +60,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same instruction with the two descriptors given as (lo, hi) words: the issuing thread keeps `hi` and a per-stage base `lo` in
+// registers and only adds a small constant per instruction (descriptor construction was the issue-rate bottleneck).
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -131,10 +142,10 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             const int az1 = z1 * p.a_z1, az2 = z2 * p.a_z2, bz1 = z1 * p.b_z1, bz2 = z2 * p.b_z2;
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < num_kb; ++i) {
                 const int kb = kb_begin + i;
-                const int s = i % kStages;
-                const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], kA + kB);
                 if (!A_MN) tma_load_4d(sA + s * kA, &tmA, kb * TBK, m0, az2, az1, &full[s]);
@@ -144,26 +155,28 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
 #pragma unroll
                     for (int j = 0; j < BN / 64; ++j) tma_load_4d(sB + s * kB + j * 8192, &tmB, n0 + 64 * j, kb * TBK, bz2, bz1, &full[s]);
                 }
+                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TBM, BN, A_MN, B_MN);
+            // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per 16-element k step inside the 128 B swizzle atom.
+            // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 2048 B per k step.
+            constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t a_step = A_MN ? (2048u >> 4) : (32u >> 4), b_step = B_MN ? (2048u >> 4) : (32u >> 4);
+            const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFF) | ((A_MN ? (8192u >> 4) : 1u) << 16);
+            const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFF) | ((B_MN ? (8192u >> 4) : 1u) << 16);
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < num_kb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * kA), b_addr = smem_u32(sB + s * kB);
+                const uint32_t a_lo = a_lo0 + (uint32_t)s * (kA >> 4), b_lo = b_lo0 + (uint32_t)s * (kB >> 4);
 #pragma unroll
-                for (int k = 0; k < TBK / 16; ++k) {
-                    // K-major: 8-row groups 1024 B apart, advance 32 B per 16-element k step inside the 128 B swizzle atom.
-                    // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 2048 B per k step.
-                    const uint64_t da = A_MN ? smem_desc(a_addr + k * 2048, 8192, 1024) : smem_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t db = B_MN ? smem_desc(b_addr + k * 2048, 8192, 1024) : smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
-                }
+                for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(tmem_base, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
                 umma_commit(&empty[s]);                 // stage reusable once these MMAs have read it
+                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
             umma_commit(accum_full);                    // accumulator complete
         }
