@@ -54,6 +54,13 @@ __device__ __forceinline__ void cumma(uint32_t tmem_d, uint64_t da, uint64_t db,
 __device__ __forceinline__ void ccommit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync); the rest of the MMA warp runs the same uniform loop so descriptor arithmetic stays in
+// uniform registers instead of being R2UR-broadcast before every instruction
+__device__ __forceinline__ bool celect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cfence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void cfence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ctmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t hi = cdesc_hi(1024);
             mbar_wait(wbar, 0);
@@ -164,25 +171,28 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
                     mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
                     cfence_after();
                     const uint32_t d = tmem + acc * 64;
+                    int s1 = slot0 + 1; if (s1 >= CSLOTS) s1 -= CSLOTS;
+                    int s2 = slot0 + 2; if (s2 >= CSLOTS) s2 -= CSLOTS;
+                    const uint32_t a_lo0 = ring_lo + (uint32_t)slot0 * (CBOXB >> 4), a_lo1 = ring_lo + (uint32_t)s1 * (CBOXB >> 4),
+                                   a_lo2 = ring_lo + (uint32_t)s2 * (CBOXB >> 4);
+                    const bool last = t == ntile - 1;
+                    if (celect_one()) {
 #pragma unroll
-                    for (int dh = 0; dh < 3; ++dh) {
-                        int sd = slot0 + dh; if (sd >= CSLOTS) sd -= CSLOTS;
-                        const uint32_t a_lo = ring_lo + (uint32_t)sd * (CBOXB >> 4);
+                        for (int dh = 0; dh < 3; ++dh) {
+                            const uint32_t a_lo = dh == 0 ? a_lo0 : (dh == 1 ? a_lo1 : a_lo2);
 #pragma unroll
-                        for (int dw = 0; dw < 3; ++dw) {
+                            for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                cumma2(d, a_lo + dw * 8 + k * 2, hi, w_lo + (dh * 3 + dw) * 512 + k * 2, hi, idesc, (uint32_t)((dh | dw | k) != 0));
+                                for (int k = 0; k < 4; ++k)
+                                    cumma2(d, a_lo + dw * 8 + k * 2, hi, w_lo + (dh * 3 + dw) * 512 + k * 2, hi, idesc, (uint32_t)((dh | dw | k) != 0));
+                            }
                         }
+                        ccommit(&empty[slot0]);                 // the oldest row is dead after this tile
+                        if (last) { ccommit(&empty[s1]); ccommit(&empty[s2]); }
+                        ccommit(&tfull[acc]);
                     }
-                    ccommit(&empty[slot0]);                     // the oldest row is dead after this tile
-                    if (t == ntile - 1) {
-                        int s1 = slot0 + 1; if (s1 >= CSLOTS) s1 -= CSLOTS;
-                        int s2 = slot0 + 2; if (s2 >= CSLOTS) s2 -= CSLOTS;
-                        ccommit(&empty[s1]); ccommit(&empty[s2]);
-                        slot0 += 3; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
-                    } else { slot0 += 1; if (slot0 >= CSLOTS) slot0 -= CSLOTS; }
-                    ccommit(&tfull[acc]);
+                    __syncwarp();
+                    slot0 += last ? 3 : 1; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
                 }
             }
         }
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // A (input taps) MN-major M = 128: two 64-channel groups LBO apart; B (dy) MN-major N = 64
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t hi = cdesc_hi(1024);
@@ -338,31 +348,35 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                     cfence_after();
                     const uint32_t dy_lo = dy_lo0 + (uint32_t)sd * (8192 >> 4);
                     const uint32_t accf = any ? 1u : 0u;
+                    int s1 = slot0 + 1; if (s1 >= GSLOTS) s1 -= GSLOTS;
+                    int s2 = slot0 + 2; if (s2 >= GSLOTS) s2 -= GSLOTS;
+                    const uint32_t a_lo0 = ring_lo + (uint32_t)slot0 * (GBOXB >> 4), a_lo1 = ring_lo + (uint32_t)s1 * (GBOXB >> 4),
+                                   a_lo2 = ring_lo + (uint32_t)s2 * (GBOXB >> 4);
+                    const bool last = t == ntile - 1;
+                    if (celect_one()) {
 #pragma unroll
-                    for (int dh = 0; dh < 3; ++dh) {
-                        int sr = slot0 + dh; if (sr >= GSLOTS) sr -= GSLOTS;
-                        const uint32_t a_lo = ring_lo + (uint32_t)sr * (GBOXB >> 4);
+                        for (int dh = 0; dh < 3; ++dh) {
+                            const uint32_t a_lo = dh == 0 ? a_lo0 : (dh == 1 ? a_lo1 : a_lo2);
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {                  // taps (dw = -1, 0) together, then (dw = +1, -)
-                            const uint32_t d = tmem + (dh * 2 + half) * 64;
+                            for (int half = 0; half < 2; ++half) {              // taps (dw = -1, 0) together, then (dw = +1, -)
+                                const uint32_t d = tmem + (dh * 2 + half) * 64;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                cumma2(d, a_lo + half * 16 + k * 128, hi, dy_lo + k * 128, hi, idesc, k == 0 ? accf : 1u);
+                                for (int k = 0; k < 4; ++k)
+                                    cumma2(d, a_lo + half * 16 + k * 128, hi, dy_lo + k * 128, hi, idesc, k == 0 ? accf : 1u);
+                            }
                         }
+                        ccommit(&empty[slot0]);
+                        if (last) { ccommit(&empty[s1]); ccommit(&empty[s2]); }
+                        ccommit(&dempty[sd]);
                     }
+                    __syncwarp();
                     any = true;
-                    ccommit(&empty[slot0]);
-                    if (t == ntile - 1) {
-                        int s1 = slot0 + 1; if (s1 >= GSLOTS) s1 -= GSLOTS;
-                        int s2 = slot0 + 2; if (s2 >= GSLOTS) s2 -= GSLOTS;
-                        ccommit(&empty[s1]); ccommit(&empty[s2]);
-                        slot0 += 3; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
-                    } else { slot0 += 1; if (slot0 >= GSLOTS) slot0 -= GSLOTS; }
-                    ccommit(&dempty[sd]);
+                    slot0 += last ? 3 : 1; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
                     if (++sd == GDY) sd = 0;
                 }
             }
-            ccommit(done);
+            if (celect_one()) ccommit(done);
+            __syncwarp();
         }
     }
     // every CTA writes its partial (zeros if it had no work) so the reduction can read a fixed number of partials

@@ -71,6 +71,11 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
         ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane issues
             constexpr uint32_t idesc = make_idesc(TBM, BN, A_MN, B_MN);
             // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per 16-element k step inside the 128 B swizzle atom.
             // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 2048 B per k step.
@@ -173,12 +178,15 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + (uint32_t)s * (kA >> 4), b_lo = b_lo0 + (uint32_t)s * (kB >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(tmem_base, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
-                umma_commit(&empty[s]);                 // stage reusable once these MMAs have read it
+                    for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(tmem_base, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
+                    umma_commit(&empty[s]);             // stage reusable once these MMAs have read it
+                    if (i == num_kb - 1) umma_commit(accum_full);      // accumulator complete
+                }
+                __syncwarp();
                 if (++s == kStages) { s = 0; ph ^= 1u; }
             }
-            umma_commit(accum_full);                    // accumulator complete
         }
     } else if (num_kb > 0) {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
