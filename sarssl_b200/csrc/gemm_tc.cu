@@ -7,8 +7,8 @@
 // weight gradients dW = dY^T X where the contraction runs over the token rows (MN-major operands, same kernel).
 //
 // One CTA computes a 128 x BN tile: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
-// elected lane issues UMMA 128xBNx16 instructions), warps 2-5 = epilogue (each owns the 32 TMEM lanes its warp-id % 4
-// selects).  A kStages-deep ring of 128B-swizzled shared-memory tiles is handed from TMA to MMA through full/empty
+// elected lane issues UMMA 128xBNx16 instructions), warps 2-9 = epilogue (each owns the 32 TMEM lanes its warp-id % 4
+// selects and half of the tile's columns).  A kStages-deep ring of 128B-swizzled shared-memory tiles is handed from TMA to MMA through full/empty
 // mbarriers; tcgen05.commit releases a stage when the MMAs reading it retire and finally signals the epilogue.
 // Two CTAs fit per SM (smem and TMEM), so one tile's epilogue overlaps the other's main loop.
 #include "common.cuh"
@@ -17,7 +17,7 @@
 
 namespace sarssl {
 
-constexpr int TBM = 128, TBK = 64, kStages = 3, kTcThreads = 192;
+constexpr int TBM = 128, TBK = 64, kStages = 3, kTcThreads = 320;      // 2 control warps + 8 epilogue warps
 
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         }
     } else if (num_kb > 0) {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+        const int chalf = (warp - 2) >> 2;              // two warps share a lane quarter: each takes half of the tile's columns
         mbar_wait(accum_full, 0);
         tc_fence_after();
         const int m = m0 + q * 32 + lane;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
         const bool atomic = p.splitk > 1;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
             const int nb = n0 + c0;

@@ -143,22 +143,25 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// out[w] (+)= sum_p partials[p][w]  (double accumulation, fixed order).  32 consecutive outputs per warp: every lane walks the
-// partials of its own column (coalesced across the warp).
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out0,
-                                       float* __restrict__ out1, int split, int accumulate) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= width) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = 0;
-    for (; p + 3 < nparts; p += 4) {
-        s0 += (double)partials[(size_t)p * width + w]; s1 += (double)partials[(size_t)(p + 1) * width + w];
-        s2 += (double)partials[(size_t)(p + 2) * width + w]; s3 += (double)partials[(size_t)(p + 3) * width + w];
+// out[w] (+)= sum_p partials[p][w]  (double accumulation, fixed order).  CTA = 32 columns x 8 partial slices: every thread walks
+// a slice of the partials of its column (coalesced across the 32 columns), the 8 slices are combined through shared memory.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out0,
+                                                            float* __restrict__ out1, int split, int accumulate) {
+    __shared__ double sh[8][33];
+    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int w = blockIdx.x * 32 + cl;
+    double s = 0.0;
+    if (w < width)
+        for (int p = sl; p < nparts; p += 8) s += (double)partials[(size_t)p * width + w];
+    sh[sl][cl] = s;
+    __syncthreads();
+    if (sl == 0 && w < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][cl];
+        float* dst = (w < split) ? out0 + w : out1 + (w - split);
+        *dst = accumulate ? *dst + (float)t : (float)t;
     }
-    for (; p < nparts; ++p) s0 += (double)partials[(size_t)p * width + w];
-    const double s = (s0 + s1) + (s2 + s3);
-    float* dst = (w < split) ? out0 + w : out1 + (w - split);
-    *dst = accumulate ? *dst + (float)s : (float)s;
 }
 
 // ---------------------------------------------------------------- column sums: partial[cta][cols]
@@ -400,7 +403,7 @@ extern "C" int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* 
     DISPATCH_T(dtype, (ln_bwd_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(dy), lddy, static_cast<const T*>(x), ldx, mean, rstd, gamma,
                                                                static_cast<const T*>(add), static_cast<T*>(dx), partials, rows, cols)));
     SARSSL_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(2 * cols + 255) / 256, 256, 0, stream>>>(partials, grid, 2 * cols, dgamma, dbeta, cols, 1);
+    reduce_partials_kernel<<<(2 * cols + 31) / 32, 256, 0, stream>>>(partials, grid, 2 * cols, dgamma, dbeta, cols, 1);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
@@ -416,7 +419,7 @@ extern "C" int sarssl_colsum(const void* x, long long ldx, float* out, int rows,
     float* partials = static_cast<float*>(workspace);
     DISPATCH_T(dtype, (colsum_kernel<T><<<dim3(gx, grid), 256, 0, stream>>>(static_cast<const T*>(x), ldx, partials, rows, cols)));
     SARSSL_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partials, grid, cols, out, out, cols, accumulate);
+    reduce_partials_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partials, grid, cols, out, out, cols, accumulate);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -39,15 +39,24 @@ __global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__
     if (threadIdx.x < 256) ws[threadIdx.x >> 2][threadIdx.x & 3] = Wt[threadIdx.x];
     __syncthreads();
     const int sub = threadIdx.x & 7;
-    for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (long long)gridDim.x * 32) {
-        const float4 x = load_narrow<T>(in, p, mode, flag, ch, W, H);
-        float o[8];
+    float wr[8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float* w = ws[sub * 8 + j];
-            o[j] = w[0] * x.x + w[1] * x.y + w[2] * x.z + w[3] * x.w;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[j][c] = ws[sub * 8 + j][c];
+    // 4 pixels per thread per iteration (independent loads in flight)
+    for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = (p0 + u < P) ? load_narrow<T>(in, p0 + u, mode, flag, ch, W, H) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u >= P) break;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
+            Vec8<T>::store(out + (p0 + u) * 64 + sub * 8, o);
         }
-        Vec8<T>::store(out + p * 64 + sub * 8, o);
     }
 }
 
@@ -62,29 +71,44 @@ __global__ void __launch_bounds__(256) pw_reduce_kernel(const T* __restrict__ in
     __syncthreads();
     const int sub = threadIdx.x & 7;
     const bool tr = scale != nullptr;
-    const long long iters = (P + (long long)gridDim.x * 32 - 1) / ((long long)gridDim.x * 32);
-    for (long long it = 0; it < iters; ++it) {
-        const long long p = ((long long)it * gridDim.x + blockIdx.x) * 32 + (threadIdx.x >> 3);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (p < P) {
-            float qv[8];
-            Vec8<T>::load(in + p * 64 + sub * 8, qv);
+    float wr[4][8], scr[8], shr[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int o = sub * 8 + j;
-                float v = qv[j];
-                if (tr) v = fmaxf(v * sc[o] + sh[o], 0.f);
-                a0 = fmaf(ws[0][o], v, a0); a1 = fmaf(ws[1][o], v, a1); a2 = fmaf(ws[2][o], v, a2); a3 = fmaf(ws[3][o], v, a3);
+    for (int j = 0; j < 8; ++j) {
+        scr[j] = sc[sub * 8 + j]; shr[j] = sh[sub * 8 + j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[c][j] = ws[c][sub * 8 + j];
+    }
+    const long long per_iter = (long long)gridDim.x * 128;
+    const long long iters = (P + per_iter - 1) / per_iter;
+    for (long long it = 0; it < iters; ++it) {
+        const long long p0 = (it * gridDim.x + blockIdx.x) * 128 + (threadIdx.x >> 3) * 4;      // 4 consecutive pixels per 8-thread group
+        float qv[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u < P) Vec8<T>::load(in + (p0 + u) * 64 + sub * 8, qv[u]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qv[u][j] = 0.f;
             }
         }
 #pragma unroll
-        for (int s = 4; s > 0; s >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, s); a1 += __shfl_xor_sync(0xffffffffu, a1, s);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, s); a3 += __shfl_xor_sync(0xffffffffu, a3, s);
-        }
-        if (p < P && sub == 0) {
-            T* o = out + p * 4;
-            o[0] = from_f32<T>(a0); o[1] = from_f32<T>(a1); o[2] = from_f32<T>(a2); o[3] = from_f32<T>(a3);
+        for (int u = 0; u < 4; ++u) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = qv[u][j];
+                if (tr) v = fmaxf(v * scr[j] + shr[j], 0.f);
+                a0 = fmaf(wr[0][j], v, a0); a1 = fmaf(wr[1][j], v, a1); a2 = fmaf(wr[2][j], v, a2); a3 = fmaf(wr[3][j], v, a3);
+            }
+#pragma unroll
+            for (int sft = 4; sft > 0; sft >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, sft); a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, sft); a3 += __shfl_xor_sync(0xffffffffu, a3, sft);
+            }
+            if (p0 + u < P && sub == 0) {
+                T* o = out + (p0 + u) * 4;
+                o[0] = from_f32<T>(a0); o[1] = from_f32<T>(a1); o[2] = from_f32<T>(a2); o[3] = from_f32<T>(a3);
+            }
         }
     }
 }
@@ -103,16 +127,29 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-    for (long long p = (long long)blockIdx.x * 32 + pl; p < P; p += (long long)gridDim.x * 32) {
-        const float4 x = load_narrow<T>(narrow, p, mode, flag, ch, W, H);
-        float qv[8];
-        Vec8<T>::load(wide + p * 64 + sub * 8, qv);
+    for (long long p0 = ((long long)blockIdx.x * 32 + pl) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
+        float4 x[4];
+        float qv[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float v = qv[j];
-            if (tr) v = fmaxf(v * sc[j] + sh[j], 0.f);
-            acc[j][0] = fmaf(v, x.x, acc[j][0]); acc[j][1] = fmaf(v, x.y, acc[j][1]);
-            acc[j][2] = fmaf(v, x.z, acc[j][2]); acc[j][3] = fmaf(v, x.w, acc[j][3]);
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u < P) {
+                x[u] = load_narrow<T>(narrow, p0 + u, mode, flag, ch, W, H);
+                Vec8<T>::load(wide + (p0 + u) * 64 + sub * 8, qv[u]);
+            } else {
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qv[u][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = qv[u][j];
+                if (tr) v = fmaxf(v * sc[j] + sh[j], 0.f);
+                acc[j][0] = fmaf(v, x[u].x, acc[j][0]); acc[j][1] = fmaf(v, x[u].y, acc[j][1]);
+                acc[j][2] = fmaf(v, x[u].z, acc[j][2]); acc[j][3] = fmaf(v, x[u].w, acc[j][3]);
+            }
         }
     }
 #pragma unroll
@@ -263,7 +300,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const T* __restrict_
 }
 
 static int pix_grid(long long P) {
-    long long g = (P + 31) / 32;
+    long long g = (P + 127) / 128;
     const long long cap = (long long)sm_count() * 4;
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
