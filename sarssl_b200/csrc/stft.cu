@@ -21,6 +21,7 @@
 //   * generic path (any channel count, any length): spectrum kernel -> clip scale kernel -> pair/normalise.
 #include "common.cuh"
 #include "fft512.cuh"
+#include "fft512w.cuh"
 #include "../../include/sarssl_b200.h"
 
 namespace sarssl {
@@ -151,6 +152,115 @@ __global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const flo
             float4 o = sm.out[i];
             o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
             st_stream_f4(dst + i, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------- second-generation fused kernel: one warp per transform (fft512w.cuh), no block barriers inside the FFT ----------------
+struct WarpSmem {
+    float2 in[(kFPI + 1) * kHop];                 // 18 KB   staged samples (ch0, ch1)
+    float2 tb[8][kWTransFloat2];                  // 33 KB   per-warp transpose buffer, re-used as the frame's staged (un-scaled) output
+    float win[kFftN];                             // 2 KB    periodic Hann
+    float red[32];
+    uint64_t bar;
+    int item;
+    float scale;
+};
+
+__global__ void __launch_bounds__(256, 2) stft_frontend_warp_kernel(const float* __restrict__ sig, float4* __restrict__ out, float* partials,
+                                                                  unsigned* counters, int nb, long long nsample, int nt, int ipc, float eps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    WarpFftLane lc;
+    lc.init(lane);
+    for (int i = tid; i < kFftN; i += 256) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int nitems = nb * ipc;
+    const int k1 = lane & 15, h = lane >> 4;
+    const int kbase = h == 0 ? k1 : (((16 - k1) & 15) + 128);       // bin of out[j] is kbase + 16*j
+    float2* tb = sm.tb[warp];
+    float4* stage = reinterpret_cast<float4*>(tb);                    // 256 float4 (bins 1..256) fit in the 528-float2 buffer
+    for (;;) {
+        if (tid == 0) sm.item = (int)atomicAdd(&counters[0], 1u);
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= nitems) break;
+        const int b = item / ipc, fb = item - b * ipc;
+        const int f0 = fb * kFPI;
+        const int nfr = min(kFPI, nt - f0);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(nfr + 1) * kHop * sizeof(float2);
+            mbar_expect_tx(&sm.bar, bytes);
+            tma_bulk_g2s(sm.in, sig + ((size_t)b * nsample + (size_t)f0 * kHop) * 2, bytes, &sm.bar);
+        }
+        mbar_wait(&sm.bar, phase);
+        phase ^= 1u;
+
+        float part = 0.f;
+        if (warp < nfr) {                                             // one frame per warp
+            const float2* frame = sm.in + warp * kHop;
+            float2 v[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const float2 sx = frame[32 * n1 + lane];
+                const float w = sm.win[32 * n1 + lane];
+                v[n1] = make_float2(sx.x * w, sx.y * w);
+            }
+            wfft_stage1(v, lc, tb, lane);
+            __syncwarp();
+            wfft_stage2(v, tb, lane);
+            wfft_combine(v, lane);                                    // (shuffles: every lane is past its transpose-buffer loads)
+            float4 o[8], nyq;
+            wfft_split_all(v, lane, o, nyq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kbase + 16 * j;
+                part += sqrtf(o[j].x * o[j].x + o[j].z * o[j].z);
+                if (k >= 1) stage[k - 1] = o[j];
+            }
+            if (lane == 16) {
+                part += sqrtf(nyq.x * nyq.x + nyq.z * nyq.z);
+                stage[255] = nyq;
+            }
+        }
+        const float total = block_sum(part, sm.red);
+        if (tid == 0) {
+            partials[(size_t)b * ipc + fb] = total;
+            __threadfence();
+            atomicAdd(&counters[2 + b], 1u);
+            unsigned spins = 0;
+            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)ipc) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) {
+                    atomicExch(&counters[1], 1u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.f;
+            for (int i = tid; i < ipc; i += 32) s += __ldcg(&partials[(size_t)b * ipc + i]);
+            s = warp_sum(s);
+            if (tid == 0) sm.scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
+        }
+        __syncthreads();
+        if (warp < nfr) {
+            const float scale = sm.scale;
+            float4* dst = out + ((size_t)b * nt + f0 + warp) * kHop;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float4 o = stage[lane + 32 * r];
+                o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+                st_stream_f4(dst + lane + 32 * r, o);
+            }
         }
         __syncthreads();
     }
@@ -292,23 +402,31 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     float* scale = reinterpret_cast<float*>(ws + off);
     off += ((size_t)nb * sizeof(float) + 255) / 256 * 256;
 
-    static int max_ctas_per_sm = -1;
-    const size_t smem = sizeof(FusedSmem);
-    if (max_ctas_per_sm < 0) {
-        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // force_generic: 0 = warp-per-transform fused kernel, 2 = first-generation fused kernel (64-lane groups), 1 = generic three-kernel path
+    static int max_ctas_v1 = -1, max_ctas_v2 = -1;
+    const bool v1 = force_generic == 2;
+    const size_t smem = v1 ? sizeof(FusedSmem) : sizeof(WarpSmem);
+    if (max_ctas_v1 < 0) {
+        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
         int n = 0;
-        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_fused_kernel, kThreads, smem));
-        max_ctas_per_sm = n;
+        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_fused_kernel, kThreads, sizeof(FusedSmem)));
+        max_ctas_v1 = n;
+        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp_kernel, 256, sizeof(WarpSmem)));
+        max_ctas_v2 = n;
     }
+    const int max_ctas_per_sm = v1 ? max_ctas_v1 : max_ctas_v2;
     const long long resident = (long long)max_ctas_per_sm * sm_count();
     // the bulk-TMA staging needs 16-byte aligned clip starts: nsample * 2 floats * 4 B -> nsample even
-    const bool fused_ok = !force_generic && nch == 2 && (nsample % 2 == 0) && resident >= ipc && max_ctas_per_sm > 0;
+    const bool fused_ok = force_generic != 1 && nch == 2 && (nsample % 2 == 0) && resident >= ipc && max_ctas_per_sm > 0;
     SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
     if (fused_ok) {
         const long long items = (long long)nb * ipc;
         const int grid = (int)(items < resident ? items : resident);
-        stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb,
-                                                                     nsample, nt, ipc, eps);
+        if (v1)
+            stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
+        else
+            stft_frontend_warp_kernel<<<grid, 256, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
         SARSSL_LAUNCH_CHECK();
         return SARSSL_OK;
     }

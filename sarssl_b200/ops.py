@@ -55,11 +55,12 @@ def stft_frontend(signal, eps=1e-6, win_len=WIN, hop=HOP, nfft=NFFT, force_gener
     if out is None:
         out = torch.empty((nb * (nch - 1), nt, nfft // 2, 2, 2), dtype=torch.float32, device=signal.device)
     L = lib()
-    generic = bool(force_generic)
+    variant = int(force_generic)       # 0: warp-per-transform fused kernel, 1: generic three-kernel path, 2: first-generation fused kernel
+    generic = variant == 1
     for _ in range(2):
         nbytes = L.sarssl_stft_workspace_bytes(nb, nsample, nch, int(generic))
         ws = _workspace(signal.device, nbytes, "stft")
-        rc = L.sarssl_stft_frontend(ptr(signal), ptr(out), nb, nsample, nch, win_len, hop, nfft, float(eps), int(generic), ptr(ws),
+        rc = L.sarssl_stft_frontend(ptr(signal), ptr(out), nb, nsample, nch, win_len, hop, nfft, float(eps), 1 if generic else variant, ptr(ws),
                                     ws.numel(), stream_ptr(signal.device))
         if rc == -2 and not generic:       # SARSSL_ERR_WORKSPACE: the generic path was selected on the host, retry with its size
             generic = True

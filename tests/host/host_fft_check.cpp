@@ -37,3 +37,60 @@ int main() {
     printf("max abs err %.3e (max |X| %.3f)\n", maxerr, maxref);
     return maxerr < 1e-4 * maxref ? 0 : 1;
 }
+
+// ---- warp-per-transform variant (fft512w.cuh): emulate 32 lanes; the shuffle steps are re-stated from the documented algebra ----
+#include "fft512w.cuh"
+static int check_warp_fft() {
+    std::vector<float> x0(512), x1(512);
+    srand(11);
+    for (int n = 0; n < 512; ++n) { x0[n] = (rand() / (float)RAND_MAX) - 0.5f; x1[n] = (rand() / (float)RAND_MAX) - 0.5f; }
+    static float2 tb[kWTransFloat2];
+    WarpFftLane lanes[32];
+    float2 v[32][16];
+    const double PI = 3.14159265358979323846;
+    for (int l = 0; l < 32; ++l) lanes[l].init(l);
+    for (int l = 0; l < 32; ++l) for (int n1 = 0; n1 < 16; ++n1) {
+        int n = 32 * n1 + l; float w = (float)(0.5 - 0.5 * cos(2 * PI * n / 512));
+        v[l][n1] = make_float2(x0[n] * w, x1[n] * w);
+    }
+    for (int l = 0; l < 32; ++l) wfft_stage1(v[l], lanes[l], tb, l);
+    for (int l = 0; l < 32; ++l) wfft_stage2(v[l], tb, l);
+    // combine (lane ^ 16): Z[k1 + 256 h + 16 s]
+    float2 Z[32][16];
+    for (int l = 0; l < 32; ++l) for (int s = 0; s < 16; ++s) {
+        float2 mine = v[l][s], oth = v[l ^ 16][s];
+        Z[l][s] = (l >= 16) ? make_float2(oth.x - mine.x, oth.y - mine.y) : make_float2(mine.x + oth.x, mine.y + oth.y);
+    }
+    double maxerr = 0, maxref = 0;
+    for (int l = 0; l < 32; ++l) for (int s = 0; s < 16; ++s) {
+        int k = (l & 15) + 256 * (l >> 4) + 16 * s;
+        std::complex<double> X = 0;
+        for (int n = 0; n < 512; ++n) {
+            double w = 0.5 - 0.5 * cos(2 * PI * n / 512);
+            X += std::complex<double>(x0[n] * w, x1[n] * w) * std::polar(1.0, -2 * PI * n * k / 512.0);
+        }
+        maxerr = fmax(maxerr, fmax(fabs(Z[l][s].x - X.real()), fabs(Z[l][s].y - X.imag()))); maxref = fmax(maxref, std::abs(X));
+    }
+    // mirror algebra used by wfft_split_all: Z[512 - k] location
+    int bad = 0;
+    for (int l = 0; l < 16; ++l) for (int j = 0; j < 8; ++j) {           // h = 0 lanes, bins k = k1 + 16 j
+        int k1 = l, k = k1 + 16 * j, partner = ((16 - k1) & 15) + 16;
+        if (k == 0) continue;
+        int mk = 512 - k;
+        float2 want = Z[(mk & 15) + 16 * (mk >= 256)][(mk % 256) / 16];
+        float2 got = (k1 == 0) ? Z[partner][8 + (8 - j)] : Z[partner][8 + (7 - j)];
+        if (got.x != want.x || got.y != want.y) ++bad;
+    }
+    for (int l = 16; l < 32; ++l) for (int j = 0; j < 8; ++j) {          // h = 1 lanes, bins of k1' = (16 - p) & 15, s = j + 8
+        int p = l & 15, k1 = (16 - p) & 15, k = k1 + 16 * (j + 8);
+        int mk = 512 - k;
+        float2 want = Z[(mk & 15) + 16 * (mk >= 256)][(mk % 256) / 16];
+        float2 got = (p == 0) ? Z[l][8 - j] : Z[l][7 - j];
+        float2 zz = Z[k1][8 + j];                                        // what the exchange delivers as Z[k]
+        float2 zw = Z[(k & 15) + 16 * (k >= 256)][(k % 256) / 16];
+        if (got.x != want.x || got.y != want.y || zz.x != zw.x || zz.y != zw.y) ++bad;
+    }
+    printf("warp fft: max abs err %.3e (max |Z| %.3f), mirror-map mismatches %d\n", maxerr, maxref, bad);
+    return (maxerr < 1e-4 * maxref && bad == 0) ? 0 : 1;
+}
+struct RunWarpCheck { RunWarpCheck() { if (check_warp_fft()) { fprintf(stderr, "warp fft check FAILED\n"); exit(2); } } } run_warp_check_instance;
