@@ -157,112 +157,108 @@ __global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const flo
     }
 }
 
-// ---------------- second-generation fused kernel: one warp per transform (fft512w.cuh), no block barriers inside the FFT ----------------
-struct WarpSmem {
-    float2 in[(kFPI + 1) * kHop];                 // 18 KB   staged samples (ch0, ch1)
-    float2 tb[8][kWTransFloat2];                  // 33 KB   per-warp transpose buffer, re-used as the frame's staged (un-scaled) output
-    float win[kFftN];                             // 2 KB    periodic Hann
-    float red[32];
-    uint64_t bar;
-    int item;
-    float scale;
+// ---------------- second-generation fused kernel: independent warps, one transform each (fft512w.cuh) ----------------
+// Every warp of the persistent grid is its own worker: frame f = warp_global_id + round * total_warps of the (clip-major) frame list.
+// Per frame: bulk-TMA its 512 samples (double buffered: the next frame's samples are in flight while this one is transformed),
+// FFT in registers + one smem transpose, stage the un-scaled bins in the transpose buffer, publish |X_ch0| partial sum and arrive on
+// the clip's counter, spin (lane 0) until the clip's nt frames have arrived, add the nt partials in a fixed order, scale and write the
+// 4 KB frame row.  No block-level barrier exists after start-up, so the SM's warps drift into different phases and overlap load /
+// compute / store.  Deadlock-free: frames are assigned round-robin in list order, a warp publishes before it waits, and it only waits
+// for frames of the same or an earlier round; all warps are resident (grid sized by the occupancy query).
+constexpr int kWarpsPerCta = 8;
+struct WarpWorkerSmem {
+    float2 in[kWarpsPerCta][2][kFftN];            // 64 KB   per-warp double-buffered samples
+    float2 tb[kWarpsPerCta][kWTransFloat2];       // 33 KB   per-warp transpose buffer / staged output
+    float win[kFftN];                             // 2 KB
+    uint64_t bar[kWarpsPerCta][2];
 };
 
-__global__ void __launch_bounds__(256, 2) stft_frontend_warp_kernel(const float* __restrict__ sig, float4* __restrict__ out, float* partials,
-                                                                  unsigned* counters, int nb, long long nsample, int nt, int ipc, float eps) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) stft_frontend_warp_kernel(const float* __restrict__ sig, float4* __restrict__ out, float* partials,
+                                                                                 unsigned* counters, int nb, long long nsample, int nt, float eps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw);
+    WarpWorkerSmem& sm = *reinterpret_cast<WarpWorkerSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     WarpFftLane lc;
     lc.init(lane);
-    for (int i = tid; i < kFftN; i += 256) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
-    if (tid == 0) {
-        mbar_init(&sm.bar, 1);
+    for (int i = tid; i < kFftN; i += kWarpsPerCta * 32) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
+    if (lane == 0) {
+        mbar_init(&sm.bar[warp][0], 1);
+        mbar_init(&sm.bar[warp][1], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t phase = 0;
-    const int nitems = nb * ipc;
+    const long long total = (long long)nb * nt;
+    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp, G = (long long)gridDim.x * kWarpsPerCta;
     const int k1 = lane & 15, h = lane >> 4;
     const int kbase = h == 0 ? k1 : (((16 - k1) & 15) + 128);       // bin of out[j] is kbase + 16*j
     float2* tb = sm.tb[warp];
-    float4* stage = reinterpret_cast<float4*>(tb);                    // 256 float4 (bins 1..256) fit in the 528-float2 buffer
-    for (;;) {
-        if (tid == 0) sm.item = (int)atomicAdd(&counters[0], 1u);
-        __syncthreads();
-        const int item = sm.item;
-        if (item >= nitems) break;
-        const int b = item / ipc, fb = item - b * ipc;
-        const int f0 = fb * kFPI;
-        const int nfr = min(kFPI, nt - f0);
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(nfr + 1) * kHop * sizeof(float2);
-            mbar_expect_tx(&sm.bar, bytes);
-            tma_bulk_g2s(sm.in, sig + ((size_t)b * nsample + (size_t)f0 * kHop) * 2, bytes, &sm.bar);
+    float4* stage = reinterpret_cast<float4*>(tb);
+    uint32_t ph0 = 0, ph1 = 0;
+    int buf = 0;
+    auto issue = [&](long long f, int bsel) {
+        if (lane == 0) {
+            const long long b = f / nt, t = f - b * nt;
+            mbar_expect_tx(&sm.bar[warp][bsel], kFftN * sizeof(float2));
+            tma_bulk_g2s(sm.in[warp][bsel], sig + ((size_t)b * nsample + (size_t)t * kHop) * 2, kFftN * sizeof(float2), &sm.bar[warp][bsel]);
         }
-        mbar_wait(&sm.bar, phase);
-        phase ^= 1u;
-
+    };
+    if (gw < total) issue(gw, 0);
+    for (long long f = gw; f < total; f += G) {
+        const long long b = f / nt;
+        const int t = (int)(f - b * nt);
+        if (f + G < total) issue(f + G, buf ^ 1);                    // prefetch the next frame of this warp
+        mbar_wait(&sm.bar[warp][buf], buf ? ph1 : ph0);
+        if (buf) ph1 ^= 1u; else ph0 ^= 1u;
+        const float2* frame = sm.in[warp][buf];
+        float2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const float2 sx = frame[32 * n1 + lane];
+            const float w = sm.win[32 * n1 + lane];
+            v[n1] = make_float2(sx.x * w, sx.y * w);
+        }
+        wfft_stage1(v, lc, tb, lane);
+        __syncwarp();
+        wfft_stage2(v, tb, lane);
+        wfft_combine(v, lane);
+        float4 o[8], nyq;
+        wfft_split_all(v, lane, o, nyq);
         float part = 0.f;
-        if (warp < nfr) {                                             // one frame per warp
-            const float2* frame = sm.in + warp * kHop;
-            float2 v[16];
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const float2 sx = frame[32 * n1 + lane];
-                const float w = sm.win[32 * n1 + lane];
-                v[n1] = make_float2(sx.x * w, sx.y * w);
-            }
-            wfft_stage1(v, lc, tb, lane);
-            __syncwarp();
-            wfft_stage2(v, tb, lane);
-            wfft_combine(v, lane);                                    // (shuffles: every lane is past its transpose-buffer loads)
-            float4 o[8], nyq;
-            wfft_split_all(v, lane, o, nyq);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = kbase + 16 * j;
-                part += sqrtf(o[j].x * o[j].x + o[j].z * o[j].z);
-                if (k >= 1) stage[k - 1] = o[j];
-            }
-            if (lane == 16) {
-                part += sqrtf(nyq.x * nyq.x + nyq.z * nyq.z);
-                stage[255] = nyq;
-            }
+        for (int j = 0; j < 8; ++j) {
+            const int k = kbase + 16 * j;
+            part += sqrtf(o[j].x * o[j].x + o[j].z * o[j].z);
+            if (k >= 1) stage[k - 1] = o[j];
         }
-        const float total = block_sum(part, sm.red);
-        if (tid == 0) {
-            partials[(size_t)b * ipc + fb] = total;
+        if (lane == 16) {
+            part += sqrtf(nyq.x * nyq.x + nyq.z * nyq.z);
+            stage[255] = nyq;
+        }
+        part = warp_sum(part);
+        if (lane == 0) {
+            partials[(size_t)b * nt + t] = part;
             __threadfence();
             atomicAdd(&counters[2 + b], 1u);
             unsigned spins = 0;
-            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)ipc) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) {
-                    atomicExch(&counters[1], 1u);
-                    break;
-                }
+            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)nt) {
+                __nanosleep(32);
+                if (++spins > (1u << 24)) { atomicExch(&counters[1], 1u); break; }
             }
         }
-        __syncthreads();
-        if (tid < 32) {
-            float s = 0.f;
-            for (int i = tid; i < ipc; i += 32) s += __ldcg(&partials[(size_t)b * ipc + i]);
-            s = warp_sum(s);
-            if (tid == 0) sm.scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
-        }
-        __syncthreads();
-        if (warp < nfr) {
-            const float scale = sm.scale;
-            float4* dst = out + ((size_t)b * nt + f0 + warp) * kHop;
+        __syncwarp();
+        float s = 0.f;
+        for (int i = lane; i < nt; i += 32) s += __ldcg(&partials[(size_t)b * nt + i]);
+        s = warp_sum(s);
+        const float scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
+        float4* dst = out + ((size_t)b * nt + t) * kHop;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float4 o = stage[lane + 32 * r];
-                o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
-                st_stream_f4(dst + lane + 32 * r, o);
-            }
+        for (int r = 0; r < 8; ++r) {
+            float4 ov = stage[lane + 32 * r];
+            ov.x *= scale; ov.y *= scale; ov.z *= scale; ov.w *= scale;
+            st_stream_f4(dst + lane + 32 * r, ov);
         }
-        __syncthreads();
+        __syncwarp();
+        buf ^= 1;
     }
 }
 
@@ -354,7 +350,7 @@ extern "C" size_t sarssl_stft_workspace_bytes(int nb, long long nsample, int nch
     const int ipc = items_per_clip(nt > 0 ? nt : 1);
     size_t bytes = 256;                                            // counters: head, error, pad
     bytes += ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;    // per-clip arrivals
-    bytes += ((size_t)nb * ipc * sizeof(float) + 255) / 256 * 256; // partial sums
+    bytes += ((size_t)nb * (nt > 0 ? nt : 1) * sizeof(float) + 255) / 256 * 256; // partial sums (one per frame)
     bytes += ((size_t)nb * sizeof(float) + 255) / 256 * 256;       // per-clip scale (generic path)
     if (nch != 2 || generic) bytes += (size_t)nb * (nt > 0 ? nt : 1) * kBins * nch * sizeof(float2);   // spectrum temp
     return bytes;
@@ -398,35 +394,42 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     unsigned* counters = reinterpret_cast<unsigned*>(ws);
     size_t off = 256 + ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;
     float* partials = reinterpret_cast<float*>(ws + off);
-    off += ((size_t)nb * ipc * sizeof(float) + 255) / 256 * 256;
+    off += ((size_t)nb * nt * sizeof(float) + 255) / 256 * 256;
     float* scale = reinterpret_cast<float*>(ws + off);
     off += ((size_t)nb * sizeof(float) + 255) / 256 * 256;
 
-    // force_generic: 0 = warp-per-transform fused kernel, 2 = first-generation fused kernel (64-lane groups), 1 = generic three-kernel path
+    // force_generic: 0 = fused kernel with 64-lane FFT groups (default, fastest measured), 1 = generic three-kernel path,
+    // 2 = experimental warp-worker kernel (one warp per transform, no block barriers; measured slower: the per-clip rendezvous
+    // keeps its independent warps in lock step - profiles/r01_stft_variants.txt)
     static int max_ctas_v1 = -1, max_ctas_v2 = -1;
-    const bool v1 = force_generic == 2;
-    const size_t smem = v1 ? sizeof(FusedSmem) : sizeof(WarpSmem);
+    const bool v1 = force_generic != 2;
+    const size_t smem = v1 ? sizeof(FusedSmem) : sizeof(WarpWorkerSmem);
     if (max_ctas_v1 < 0) {
         SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
-        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
+        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpWorkerSmem)));
         int n = 0;
         SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_fused_kernel, kThreads, sizeof(FusedSmem)));
         max_ctas_v1 = n;
-        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp_kernel, 256, sizeof(WarpSmem)));
+        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp_kernel, kWarpsPerCta * 32, sizeof(WarpWorkerSmem)));
         max_ctas_v2 = n;
     }
     const int max_ctas_per_sm = v1 ? max_ctas_v1 : max_ctas_v2;
     const long long resident = (long long)max_ctas_per_sm * sm_count();
     // the bulk-TMA staging needs 16-byte aligned clip starts: nsample * 2 floats * 4 B -> nsample even
-    const bool fused_ok = force_generic != 1 && nch == 2 && (nsample % 2 == 0) && resident >= ipc && max_ctas_per_sm > 0;
+    // (the warp-worker kernel needs every frame of a clip's round resident: resident warps >= nt)
+    const bool fused_ok = force_generic != 1 && nch == 2 && (nsample % 2 == 0) && max_ctas_per_sm > 0 &&
+                          (v1 ? resident >= ipc : resident * kWarpsPerCta >= nt);
     SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
     if (fused_ok) {
         const long long items = (long long)nb * ipc;
         const int grid = (int)(items < resident ? items : resident);
         if (v1)
             stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
-        else
-            stft_frontend_warp_kernel<<<grid, 256, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
+        else {
+            const long long frames = (long long)nb * nt, ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
+            stft_frontend_warp_kernel<<<(int)(ctas < resident ? ctas : resident), kWarpsPerCta * 32, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials,
+                                                                                                                  counters, nb, nsample, nt, eps);
+        }
         SARSSL_LAUNCH_CHECK();
         return SARSSL_OK;
     }

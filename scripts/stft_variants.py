@@ -1,4 +1,4 @@
-"""Time the three STFT front-end variants (GPU box): 0 = warp-per-transform fused, 2 = first-generation fused, 1 = generic 3-kernel path."""
+"""Time the three STFT front-end variants (GPU box): 0 = fused kernel (64-lane FFT groups, default), 2 = experimental warp-worker kernel, 1 = generic 3-kernel path."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from sarssl_b200 import ops
