@@ -181,6 +181,10 @@ int sarssl_colsum(const void* x, long long ldx, float* out, int rows, int cols, 
 int sarssl_batchnorm_stats(const void* y, long long rows, int C, const float* gamma, const float* beta, float eps, float momentum,
                            float* running_mean, float* running_var, long long* num_batches_tracked, float* stats, int training, int dtype,
                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/*   the same from per-CTA partial sums [nparts][2][C] produced elsewhere (training mode only) */
+int sarssl_batchnorm_finalize(const float* partials, int nparts, long long rows, int C, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, long long* num_batches_tracked, float* stats,
+                              cudaStream_t stream);
 /*   z = act(y*scale + shift), act: SARSSL_ACT_RELU (stem) / SARSSL_ACT_SWISH (conv module) / NONE */
 int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int act, void* z, long long rows, int C, int dtype, cudaStream_t stream);
 /*   dz -> dy through the activation and the batch-statistics normalisation; dgamma/dbeta accumulated */
@@ -250,7 +254,10 @@ int sarssl_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, 
 /* Tensor-core versions (bf16 only): tcgen05 implicit GEMM, TMA row boxes shared by the three horizontal taps, weights
  * resident in shared memory, persistent CTAs.  `in` must already be the post-BatchNorm/ReLU activation (or dy for the data
  * gradient, with the mirrored weight pack).  wgrad workspace: sarssl_conv3x3_wgrad_tc_workspace_bytes(). */
-int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, int B, int H, int W, cudaStream_t stream);
+/*   bn_partials (nullable): sarssl_conv3x3_tc_grid(B,H,W) x 2 x 64 floats receive per-CTA sums of out / out^2 (fused BatchNorm batch
+ *   statistics of the conv output); turn them into stats with sarssl_batchnorm_finalize. */
+int sarssl_conv3x3_tc_grid(int B, int H, int W);
+int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, int B, int H, int W, cudaStream_t stream);
 size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void);
 int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
                             size_t workspace_bytes, cudaStream_t stream);

@@ -90,6 +90,7 @@ constexpr int kConvThreads = 192;
 
 struct ConvP {
     __nv_bfloat16* out;
+    float* bn_partials;                  // nullable: [gridDim.x][2][64] per-CTA sums of out and out^2 (BatchNorm batch statistics of the conv output)
     int B, H, W, tiles_w, nseg_h;
     long long nunits;
 };
@@ -199,6 +200,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;                          // pixel row of the tile = TMEM lane
+        // fused BatchNorm statistics: thread (channel sc, row half sh) adds its 64 staged bf16 values of every tile
+        const int et = (warp - 2) * 32 + lane, sc = et & 63, sh = et >> 6;
+        float bn_s = 0.f, bn_q = 0.f;
         uint32_t it = 0;
         for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
             const int hs = (int)(u % p.nseg_h);
@@ -240,9 +244,29 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
                                  "r"(smem_u32(stage)) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                if (p.bn_partials != nullptr) {
+                    const int rmax = min(64, p.W - w0 - sh * 64);                 // rows beyond the image edge hold garbage
+                    const unsigned char* colp = stage + ((sc & 7) << 1);
+                    for (int r = 0; r < rmax; ++r) {
+                        const int rr = sh * 64 + r;
+                        const float xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + (((sc >> 3) ^ (rr & 7)) << 4)));
+                        bn_s += xv; bn_q += xv * xv;
+                    }
+                }
             }
         }
         if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.bn_partials != nullptr) {
+            // combine the two row halves through the (now idle) staging buffer, fixed order
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* red = reinterpret_cast<float*>(osm);
+            red[et * 2] = bn_s; red[et * 2 + 1] = bn_q;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (sh == 0) {
+                p.bn_partials[((size_t)blockIdx.x * 2 + 0) * 64 + sc] = red[sc * 2] + red[(64 + sc) * 2];
+                p.bn_partials[((size_t)blockIdx.x * 2 + 1) * 64 + sc] = red[sc * 2 + 1] + red[(64 + sc) * 2 + 1];
+            }
+        }
     }
     cfence_before();
     __syncthreads();
@@ -454,7 +478,12 @@ static int image_map(CUtensorMap* m, const void* base, int B, int H, int W, int 
 
 using namespace sarssl;
 
-extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, int B, int H, int W, cudaStream_t stream) {
+extern "C" int sarssl_conv3x3_tc_grid(int B, int H, int W) {
+    const long long nunits = (long long)B * ((W + CW - 1) / CW) * ((H + CSEG - 1) / CSEG);
+    return (int)(nunits < sm_count() ? nunits : sm_count());
+}
+
+extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, int B, int H, int W, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight_packed && out && B > 0 && H > 0 && W > 0, "conv3x3_tc: bad arguments");
     SARSSL_CHECK_ARG(aligned16(in) && aligned16(weight_packed) && aligned16(out), "conv3x3_tc: buffers must be 16-byte aligned");
     CUtensorMap mi, mw, mo;
@@ -474,10 +503,10 @@ extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void
     static bool configured = false;
     if (!configured) { SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem)); configured = true; }
     ConvP p;
-    p.out = static_cast<__nv_bfloat16*>(out); p.B = B; p.H = H; p.W = W;
+    p.out = static_cast<__nv_bfloat16*>(out); p.bn_partials = bn_partials; p.B = B; p.H = H; p.W = W;
     p.tiles_w = (W + CW - 1) / CW; p.nseg_h = (H + CSEG - 1) / CSEG;
     p.nunits = (long long)B * p.tiles_w * p.nseg_h;
-    const int grid = (int)(p.nunits < sm_count() ? p.nunits : sm_count());
+    const int grid = sarssl_conv3x3_tc_grid(B, H, W);
     conv3x3_tc_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(mi, mw, mo, p);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;

@@ -17,7 +17,7 @@
 
 namespace sarssl {
 
-constexpr int TBM = 128, TBK = 64, kStages = 3, kTcThreads = 320;      // 2 control warps + 8 epilogue warps
+constexpr int TBM = 128, TBK = 64, kTcThreads = 320;      // 2 control warps + 8 epilogue warps
 
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
@@ -102,18 +102,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int NS>
 struct TcSmem {
     static constexpr int kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
-    static constexpr int kBytes = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kBytes = NS * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // A_MN / B_MN: operand is MN-major (rows of the global matrix run along the contraction dimension), used by weight gradients.
-template <int BN, bool A_MN, bool B_MN>
+// NS = pipeline stages: 3 for long K; 2 for K <= 512 (4-8 k-blocks), which lets three CTAs share an SM so that more epilogue warps
+// are in flight - those GEMMs are epilogue / store bound.
+template <int BN, bool A_MN, bool B_MN, int NS>
 __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kA = TcSmem<BN>::kABytes, kB = TcSmem<BN>::kBBytes;
+    constexpr int kA = TcSmem<BN, NS>::kABytes, kB = TcSmem<BN, NS>::kBBytes;
+    constexpr int kStages = NS;
     unsigned char* sA = smem;
     unsigned char* sB = smem + kStages * kA;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * (kA + kB));
@@ -365,18 +368,24 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return SARSSL_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int NS>
+static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
     static bool configured = false;
-    const int smem = TcSmem<BN>::kBytes;
+    const int smem = TcSmem<BN, NS>::kBytes;
     if (!configured) {
-        SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid((e.N + BN - 1) / BN, (e.M + TBM - 1) / TBM, nbatch * e.splitk);
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kTcThreads, smem, stream>>>(ma, mb, e);
+    gemm_tc_kernel<BN, A_MN, B_MN, NS><<<grid, kTcThreads, smem, stream>>>(ma, mb, e);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
+    if (e.kb_per_split <= 8) return launch_tc_ns<BN, A_MN, B_MN, 2>(ma, mb, e, nbatch, stream);
+    return launch_tc_ns<BN, A_MN, B_MN, 3>(ma, mb, e, nbatch, stream);
 }
 
 }  // namespace sarssl

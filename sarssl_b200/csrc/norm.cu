@@ -445,6 +445,18 @@ extern "C" int sarssl_batchnorm_stats(const void* y, long long rows, int C, cons
     return SARSSL_OK;
 }
 
+// same as sarssl_batchnorm_stats, but the per-CTA partial sums [nparts][2][C] (sum, sum of squares) were produced by another kernel
+// (the tensor-core conv epilogue)
+extern "C" int sarssl_batchnorm_finalize(const float* partials, int nparts, long long rows, int C, const float* gamma, const float* beta, float eps,
+                                         float momentum, float* running_mean, float* running_var, long long* num_batches_tracked, float* stats,
+                                         cudaStream_t stream) {
+    SARSSL_CHECK_ARG(partials && gamma && beta && running_mean && running_var && stats && nparts > 0 && rows > 0 && C > 0, "batchnorm_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, nparts, C, (double)rows, gamma, beta, eps, momentum, running_mean, running_var,
+                                                       num_batches_tracked, stats, stats + C, stats + 2 * C, stats + 3 * C, 1);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
 extern "C" int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int act, void* z, long long rows, int C, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(y && stats && z && rows > 0 && C > 0, "batchnorm_act_fwd: bad arguments");
     SARSSL_CHECK_ARG((C == 4 || C % 8 == 0) && (rows * C) % 8 == 0, "batchnorm_act_fwd: C=%d must be 4 or a multiple of 8", C);

@@ -126,6 +126,10 @@ class Engine:
         return self.k.bn_stats(y, rows, C, st.p(key + ".weight"), st.p(key + ".bias"), st.b(key + ".running_mean"), st.b(key + ".running_var"),
                                st.b(key + ".num_batches_tracked"), training)
 
+    def _bn_args(self, key):
+        st = self.store
+        return (st.p(key + ".weight"), st.p(key + ".bias"), st.b(key + ".running_mean"), st.b(key + ".running_var"), st.b(key + ".num_batches_tracked"))
+
     def _stem_fwd(self, enc, D, mode, patches, flag, ch, B, T, F, training, sv):
         """model.py:50-64,203-208: 1x1 (4->64) BN ReLU, 3x3 BN ReLU, 3x3 BN ReLU, 1x1 (64->4) BN ReLU, (F x 1) patch conv -> (B*T, D)."""
         k, st = self.k, self.store
@@ -138,17 +142,21 @@ class Engine:
         if k.conv_tc:            # tensor-core path: TMA feeds the MMA directly, so BatchNorm+ReLU is materialised once (bf16) first
             z1 = k.empty(P, CNN_CH)
             k.bn_act_fwd(y1, s1, ACT_RELU, z1, P, CNN_CH)
-            k.conv3x3_tc(z1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
+            s2 = k.conv3x3_tc(z1, self.W[f"{pe}.3.fwd"], y2, B, T, F, bn=self._bn_args(f"{pe}.4") if training else None)    # BN statistics fused in the epilogue
         else:                    # CUDA-core path applies BatchNorm+ReLU while loading the operand tile
             k.conv3x3(y1, s1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
-        s2 = self._bn(f"{pe}.4", y2, P, CNN_CH, training)
+            s2 = None
+        if s2 is None:
+            s2 = self._bn(f"{pe}.4", y2, P, CNN_CH, training)
         if k.conv_tc:
             z2 = k.empty(P, CNN_CH)
             k.bn_act_fwd(y2, s2, ACT_RELU, z2, P, CNN_CH)
-            k.conv3x3_tc(z2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
+            s3 = k.conv3x3_tc(z2, self.W[f"{pe}.6.fwd"], y3, B, T, F, bn=self._bn_args(f"{pe}.7") if training else None)
         else:
             k.conv3x3(y2, s2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
-        s3 = self._bn(f"{pe}.7", y3, P, CNN_CH, training)
+            s3 = None
+        if s3 is None:
+            s3 = self._bn(f"{pe}.7", y3, P, CNN_CH, training)
         y4 = k.empty(P, 4)
         k.stem_reduce(y3, s3, st.p(f"{pe}.9.weight"), y4, P)
         s4 = self._bn(f"{pe}.10", y4, P, 4, training)

@@ -184,9 +184,21 @@ class KernelSet:
     def conv_tc(self):
         return self.use_tc and self.dtype == torch.bfloat16
 
-    def conv3x3_tc(self, x, wpacked, out, B, H, W):
-        self._ok(self.L.sarssl_conv3x3_tc(ptr(x), ptr(wpacked), ptr(out), B, H, W, self.stream), "conv3x3_tc")
+    def conv3x3_tc(self, x, wpacked, out, B, H, W, bn=None):
+        """bn = (gamma, beta, running_mean, running_var, num_batches_tracked): also returns the BatchNorm batch statistics of `out`,
+        reduced inside the conv epilogue (no extra pass over the tensor)."""
+        partials = None
+        if bn is not None:
+            nparts = self.L.sarssl_conv3x3_tc_grid(B, H, W)
+            partials = torch.empty(nparts * 128, dtype=torch.float32, device=self.dev)
+        self._ok(self.L.sarssl_conv3x3_tc(ptr(x), ptr(wpacked), ptr(out), ptr(partials), B, H, W, self.stream), "conv3x3_tc")
         self.tc_launches += 1
+        if bn is None:
+            return None
+        stats = torch.empty(4 * 64, dtype=torch.float32, device=self.dev)
+        self._ok(self.L.sarssl_batchnorm_finalize(ptr(partials), nparts, B * H * W, 64, ptr(bn[0]), ptr(bn[1]), 1e-5, 0.1, ptr(bn[2]), ptr(bn[3]), ptr(bn[4]),
+                                                  ptr(stats), self.stream), "batchnorm_finalize")
+        return stats
 
     def conv3x3_wgrad_tc(self, dy, x, dwpacked, B, H, W):
         self._ok(self.L.sarssl_conv3x3_wgrad_tc(ptr(dy), ptr(x), ptr(dwpacked), 0, B, H, W, ptr(self.ws), self.ws.numel(), self.stream), "conv3x3_wgrad_tc")

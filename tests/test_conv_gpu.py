@@ -52,9 +52,16 @@ def test_tc_conv3x3_matches_simt(B, H, W):
     wp = (torch.randn(64, 9, 64, device=DEV, generator=g) / 24).bfloat16()
     ref, out = torch.empty(B, H, W, 64, device=DEV, dtype=torch.bfloat16), torch.full((B, H, W, 64), 7.0, device=DEV, dtype=torch.bfloat16)
     k.conv3x3(x, None, wp, ref, B, H, W)
-    k.conv3x3_tc(x, wp, out, B, H, W)
+    gamma, beta = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV)
+    rm, rv, nbt = torch.zeros(64, device=DEV), torch.ones(64, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+    stats = k.conv3x3_tc(x, wp, out, B, H, W, bn=(gamma, beta, rm, rv, nbt))
     torch.cuda.synchronize()
     assert rel(out.float(), ref.float()) < 3e-3, rel(out.float(), ref.float())     # both round the same fp32 sums to bf16
+    # fused BatchNorm statistics of the (bf16-rounded) conv output
+    o = out.float().reshape(-1, 64)
+    mean, var = o.mean(0), o.var(0, unbiased=False)
+    assert torch.allclose(stats[:64], mean, rtol=1e-3, atol=1e-4) and torch.allclose(stats[64:128], torch.rsqrt(var + 1e-5), rtol=2e-3)
+    assert int(nbt) == 1 and torch.allclose(rm, 0.1 * mean, rtol=1e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 1, 64), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 70, 64), (8, 256, 256)])
