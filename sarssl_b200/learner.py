@@ -10,9 +10,10 @@ import torch
 
 from . import ops
 from ._lib import SarsslError
+from .checkpoint import CheckpointMixin
 
 
-class Learner(ABC):
+class Learner(CheckpointMixin, ABC):
     """learner.py:13-50."""
 
     def __init__(self, model):
