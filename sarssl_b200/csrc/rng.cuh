@@ -8,12 +8,14 @@
 
 namespace sarssl {
 
+// 2 multiplies + 3 xor-shifts on the low word of the pair index ("lowbias32"-style finaliser); the seed and the high word of the index
+// enter through `seedmix`, which compilers hoist out of vector loops (it only changes every 2^33 elements).
 __host__ __device__ __forceinline__ uint32_t hash_pair(unsigned long long seed, unsigned long long pair_idx) {
-    uint32_t x = (uint32_t)pair_idx ^ (uint32_t)seed;
-    uint32_t y = (uint32_t)(pair_idx >> 32) + (uint32_t)(seed >> 32) * 0x9E3779B1u;
-    x *= 0xCC9E2D51u; x = (x << 15) | (x >> 17); x *= 0x1B873593u;      // murmur3-style mixing of the low word
-    x ^= y * 0x85EBCA6Bu + 0x27D4EB2Fu;
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    const uint32_t seedmix = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u) ^ ((uint32_t)(pair_idx >> 32) * 0x85EBCA6Bu);
+    uint32_t x = ((uint32_t)pair_idx * 0xCC9E2D51u) ^ seedmix;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12; x *= 0x297A2D39u;
+    x ^= x >> 15;
     return x;
 }
 
