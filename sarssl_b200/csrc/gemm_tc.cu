@@ -25,7 +25,7 @@ struct TcEpi {
     int M, N, K, nb2, splitk, kb_per_split;
     int a_z1, a_z2, b_z1, b_z2;          // 1 if the operand really advances along that batch axis (0: broadcast, coordinate stays 0)
     float alpha, beta;
-    int act, accumulate, c_is_bf16, vec_ok;
+    int act, accumulate, c_is_bf16, vec_ok, tma_store;
     float drop_p; unsigned long long drop_seed;
 };
 
@@ -112,7 +112,8 @@ struct TcSmem {
 // NS = pipeline stages: 3 for long K; 2 for K <= 512 (4-8 k-blocks), which lets three CTAs share an SM so that more epilogue warps
 // are in flight - those GEMMs are epilogue / store bound.
 template <int BN, bool A_MN, bool B_MN, int NS>
-__global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpi p) {
+__global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpi p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kA = TcSmem<BN, NS>::kABytes, kB = TcSmem<BN, NS>::kBBytes;
@@ -207,12 +208,14 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
             const int nb = n0 + c0;
-            if (m >= p.M || nb >= p.N) continue;
+            if (!p.tma_store && (m >= p.M || nb >= p.N)) continue;
+            if (p.tma_store && nb >= p.N) continue;              // (N % 32 == 0 on this path: whole chunks only)
             const long long off = zoff + (long long)m * p.ldc + nb;
             const long long roff = zoff + (long long)m * p.ldr + nb;
             if (p.vec_ok && nb + 32 <= p.N) {
                 // ---------------- vector path: 32 consecutive columns of one row
                 float v[32];
+                const bool row_ok = m < p.M;                     // rows past M only exist to fill the staged tile; TMA clips them
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 bz = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -221,13 +224,17 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                 }
                 if (p.pre) {
                     if (p.c_is_bf16) {
+                        // tma_store: stage the tile 128B-swizzled in the (now idle) B-operand ring: box c0/64, row = TMEM lane, 16-byte chunk ^ (row & 7)
+                        unsigned char* sbox = sB + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
                         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
                             __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            dst[j >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
-                                                     *reinterpret_cast<uint32_t*>(&t3));
+                            const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                                        *reinterpret_cast<uint32_t*>(&t3));
+                            if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
+                            else dst[j >> 3] = pk;
                         }
                     } else {
                         float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.pre) + off);
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                         v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
                     }
                 }
-                if (p.resid) {
+                if (p.resid && row_ok) {
                     if (p.c_is_bf16) {
                         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + roff);
 #pragma unroll
@@ -269,18 +276,21 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                             v[j] = u.x + p.beta * v[j]; v[j + 1] = u.y + p.beta * v[j + 1]; v[j + 2] = u.z + p.beta * v[j + 2]; v[j + 3] = u.w + p.beta * v[j + 3];
                         }
                     }
-                } else if (p.beta != 1.0f) {
+                } else if (p.beta != 1.0f && !p.resid) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= p.beta;
                 }
                 if (p.c_is_bf16) {
+                    unsigned char* sbox = sA + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;          // C tile staged in the idle A-operand ring
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
                         __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        dst[j >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
-                                                 *reinterpret_cast<uint32_t*>(&t3));
+                        const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                                    *reinterpret_cast<uint32_t*>(&t3));
+                        if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
+                        else dst[j >> 3] = pk;
                     }
                 } else {
                     float* cp = static_cast<float*>(p.C) + off;
@@ -327,6 +337,27 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             }
         }
     }
+    if (p.tma_store && num_kb > 0) {
+        // all 8 epilogue warps have staged their part: make the generic-proxy writes visible to the async proxy, then one thread stores
+        if (warp >= 2) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) {
+                    if (n0 + 64 * j < p.N) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmC), "r"(n0 + 64 * j), "r"(m0), "r"(z2),
+                                     "r"(z1), "r"(smem_u32(sA + j * (TBM * 128))) : "memory");
+                        if (p.pre)
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmPre), "r"(n0 + 64 * j), "r"(m0),
+                                         "r"(z2), "r"(z1), "r"(smem_u32(sB + j * (TBM * 128))) : "memory");
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, BN);
@@ -369,7 +400,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 template <int BN, bool A_MN, bool B_MN, int NS>
-static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
+static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, int nbatch, cudaStream_t stream) {
     static bool configured = false;
     const int smem = TcSmem<BN, NS>::kBytes;
     if (!configured) {
@@ -377,15 +408,15 @@ static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const TcEp
         configured = true;
     }
     dim3 grid((e.N + BN - 1) / BN, (e.M + TBM - 1) / TBM, nbatch * e.splitk);
-    gemm_tc_kernel<BN, A_MN, B_MN, NS><<<grid, kTcThreads, smem, stream>>>(ma, mb, e);
+    gemm_tc_kernel<BN, A_MN, B_MN, NS><<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, mp, e);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcEpi& e, int nbatch, cudaStream_t stream) {
-    if (e.kb_per_split <= 8) return launch_tc_ns<BN, A_MN, B_MN, 2>(ma, mb, e, nbatch, stream);
-    return launch_tc_ns<BN, A_MN, B_MN, 3>(ma, mb, e, nbatch, stream);
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, int nbatch, cudaStream_t stream) {
+    if (e.kb_per_split <= 8) return launch_tc_ns<BN, A_MN, B_MN, 2>(ma, mb, mc, mp, e, nbatch, stream);
+    return launch_tc_ns<BN, A_MN, B_MN, 3>(ma, mb, mc, mp, e, nbatch, stream);
 }
 
 }  // namespace sarssl
@@ -433,15 +464,24 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     }
     e.kb_per_split = (num_kb + splitk - 1) / splitk;
     e.splitk = (num_kb + e.kb_per_split - 1) / e.kb_per_split;
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mc, mp;
     int rc;
+    // bf16 outputs leave through a swizzled shared-memory stage + TMA store (full 128-byte lines instead of 16-byte pieces per thread);
+    // the stage re-uses the operand rings, which needs 2 x (128 rows x 128 B) per 64 columns: both rings are >= 32 KB
+    e.tma_store = e.c_is_bf16 && e.vec_ok && (a->N % 32 == 0);
+    memset(&mc, 0, sizeof(mc));
+    memset(&mp, 0, sizeof(mp));
+    if (e.tma_store) {
+        if ((rc = make_map(&mc, a->C, a->M, a->N, a->ldc, 64, TBM, a->nb1, a->sCb1, a->nb2, a->sCb2))) return rc;
+        if (a->pre_out && (rc = make_map(&mp, a->pre_out, a->M, a->N, a->ldc, 64, TBM, a->nb1, a->sCb1, a->nb2, a->sCb2))) return rc;
+    }
     // K-major operand: global [M or N rows][K cols], one box of 64 k x (128 | BN) rows.  MN-major: global [K rows][M or N cols], 64 x 64 boxes.
     if ((rc = a_k ? make_map(&ma, a->A, a->M, a->K, lda, TBK, TBM, a->nb1, a->sAb1, a->nb2, a->sAb2)
                   : make_map(&ma, a->A, a->K, a->M, lda, 64, TBK, a->nb1, a->sAb1, a->nb2, a->sAb2))) return rc;
     if ((rc = b_k ? make_map(&mb, a->B, a->N, a->K, ldb, TBK, BN, a->nb1, a->sBb1, a->nb2, a->sBb2)
                   : make_map(&mb, a->B, a->K, a->N, ldb, 64, TBK, a->nb1, a->sBb1, a->nb2, a->sBb2))) return rc;
-    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, e, nbatch, stream) : launch_tc<128, false, false>(ma, mb, e, nbatch, stream);
-    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, e, nbatch, stream) : launch_tc<128, false, true>(ma, mb, e, nbatch, stream);
-    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, e, nbatch, stream) : launch_tc<128, true, false>(ma, mb, e, nbatch, stream);
-    return bn64 ? launch_tc<64, true, true>(ma, mb, e, nbatch, stream) : launch_tc<128, true, true>(ma, mb, e, nbatch, stream);
+    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, false, false>(ma, mb, mc, mp, e, nbatch, stream);
+    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, false, true>(ma, mb, mc, mp, e, nbatch, stream);
+    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, true, false>(ma, mb, mc, mp, e, nbatch, stream);
+    return bn64 ? launch_tc<64, true, true>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, true, true>(ma, mb, mc, mp, e, nbatch, stream);
 }
