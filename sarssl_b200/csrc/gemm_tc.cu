@@ -6,11 +6,13 @@
 // data gradients (K-major operands: activations [M][K] and weights [N][K], or pre-transposed weights for dgrad), and the
 // weight gradients dW = dY^T X where the contraction runs over the token rows (MN-major operands, same kernel).
 //
-// One CTA computes a 128 x BN tile: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
-// elected lane issues UMMA 128xBNx16 instructions), warps 2-9 = epilogue (each owns the 32 TMEM lanes its warp-id % 4
-// selects and half of the tile's columns).  A kStages-deep ring of 128B-swizzled shared-memory tiles is handed from TMA to MMA through full/empty
-// mbarriers; tcgen05.commit releases a stage when the MMAs reading it retire and finally signals the epilogue.
-// Two CTAs fit per SM (smem and TMEM), so one tile's epilogue overlaps the other's main loop.
+// Persistent: one CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running CTAs share A rows through L2).
+// warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues UMMA
+// 128xBNx16 instructions), warps 2-9 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects and half of the tile's columns).
+// A ring of 128B-swizzled shared-memory stages is handed from TMA to MMA through full/empty mbarriers; tcgen05.commit releases a
+// stage when the MMAs reading it retire and signals the epilogue when a tile's accumulator is complete.  The accumulator is double
+// buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> bias / activation / dropout / residual -> bf16 -> swizzled smem
+// stage -> TMA store) overlaps the main loop of tile i+1; short-K GEMMs are no longer dominated by per-CTA set-up.
 #include "common.cuh"
 #include "rng.cuh"
 #include <cuda.h>
@@ -22,7 +24,8 @@ constexpr int TBM = 128, TBK = 64, kTcThreads = 320;      // 2 control warps + 8
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
     long long ldc, ldr, sCb1, sCb2;
-    int M, N, K, nb2, splitk, kb_per_split;
+    int M, N, K, nb2, splitk, kb_per_split, tiles_m, tiles_n;
+    long long ntiles;
     int a_z1, a_z2, b_z1, b_z2;          // 1 if the operand really advances along that batch axis (0: broadcast, coordinate stays 0)
     float alpha, beta;
     int act, accumulate, c_is_bf16, vec_ok, tma_store;
@@ -105,7 +108,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 template <int BN, int NS>
 struct TcSmem {
     static constexpr int kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
-    static constexpr int kBytes = NS * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStageC = (BN / 64) * (TBM * 128);       // bf16 output tile, 128B-swizzled boxes of 64 columns
+    static constexpr int kBytes = NS * (kABytes + kBBytes) + 2 * kStageC + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // A_MN / B_MN: operand is MN-major (rows of the global matrix run along the contraction dimension), used by weight gradients.
@@ -116,55 +120,64 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                                                            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpi p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kA = TcSmem<BN, NS>::kABytes, kB = TcSmem<BN, NS>::kBBytes;
+    constexpr int kA = TcSmem<BN, NS>::kABytes, kB = TcSmem<BN, NS>::kBBytes, kSC = TcSmem<BN, NS>::kStageC;
     constexpr int kStages = NS;
     unsigned char* sA = smem;
     unsigned char* sB = smem + kStages * kA;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * (kA + kB));
+    unsigned char* stC = smem + kStages * (kA + kB);              // staged C tile
+    unsigned char* stP = stC + kSC;                               // staged pre-activation tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(stP + kSC);
     uint64_t* empty = full + kStages;
-    uint64_t* accum_full = empty + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+    uint64_t* tfull = empty + kStages;                            // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;                                 // [2] accumulator drained (8 epilogue warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
-    // blockIdx.z = (batch z1, z2) x split-K slice
-    const int zs = blockIdx.z % p.splitk, zb = blockIdx.z / p.splitk;
-    const int z1 = zb / p.nb2, z2 = zb - z1 * p.nb2;
     const int num_kb_total = (p.K + TBK - 1) / TBK;
-    const int kb_begin = zs * p.kb_per_split;
-    const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-    const int num_kb = kb_end - kb_begin;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accum_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);          // BN fp32 columns x 128 lanes
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);      // two accumulators of BN fp32 columns x 128 lanes
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile id -> (batch/split slice zz, m tile, n tile); n fastest
+    auto decode = [&](long long t, int& zz, int& m0, int& n0) {
+        n0 = (int)(t % p.tiles_n) * BN; t /= p.tiles_n;
+        m0 = (int)(t % p.tiles_m) * TBM;
+        zz = (int)(t / p.tiles_m);
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            const int az1 = z1 * p.a_z1, az2 = z2 * p.a_z2, bz1 = z1 * p.b_z1, bz2 = z2 * p.b_z2;
             int s = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < num_kb; ++i) {
-                const int kb = kb_begin + i;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], kA + kB);
-                if (!A_MN) tma_load_4d(sA + s * kA, &tmA, kb * TBK, m0, az2, az1, &full[s]);
-                else { tma_load_4d(sA + s * kA, &tmA, m0, kb * TBK, az2, az1, &full[s]); tma_load_4d(sA + s * kA + kA / 2, &tmA, m0 + 64, kb * TBK, az2, az1, &full[s]); }
-                if (!B_MN) tma_load_4d(sB + s * kB, &tmB, kb * TBK, n0, bz2, bz1, &full[s]);
-                else {
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                int zz, m0, n0;
+                decode(t, zz, m0, n0);
+                const int zs = zz % p.splitk, zb = zz / p.splitk;
+                const int z1 = zb / p.nb2, z2 = zb - z1 * p.nb2;
+                const int az1 = z1 * p.a_z1, az2 = z2 * p.a_z2, bz1 = z1 * p.b_z1, bz2 = z2 * p.b_z2;
+                const int kb_begin = zs * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], kA + kB);
+                    if (!A_MN) tma_load_4d(sA + s * kA, &tmA, kb * TBK, m0, az2, az1, &full[s]);
+                    else { tma_load_4d(sA + s * kA, &tmA, m0, kb * TBK, az2, az1, &full[s]); tma_load_4d(sA + s * kA + kA / 2, &tmA, m0 + 64, kb * TBK, az2, az1, &full[s]); }
+                    if (!B_MN) tma_load_4d(sB + s * kB, &tmB, kb * TBK, n0, bz2, bz1, &full[s]);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_4d(sB + s * kB + j * 8192, &tmB, n0 + 64 * j, kb * TBK, bz2, bz1, &full[s]);
+                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sB + s * kB + j * 8192, &tmB, n0 + 64 * j, kb * TBK, bz2, bz1, &full[s]);
+                    }
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
-                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -177,56 +190,133 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFF) | ((A_MN ? (8192u >> 4) : 1u) << 16);
             const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFF) | ((B_MN ? (8192u >> 4) : 1u) << 16);
             int s = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < num_kb; ++i) {
-                mbar_wait(&full[s], ph);
+            uint32_t ph = 0, it = 0;
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+                int zz, m0, n0;
+                decode(t, zz, m0, n0);
+                const int zs = zz % p.splitk;
+                const int kb_begin = zs * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+                const int num_kb = kb_end - kb_begin;
+                const uint32_t acc = it & 1u;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t a_lo = a_lo0 + (uint32_t)s * (kA >> 4), b_lo = b_lo0 + (uint32_t)s * (kB >> 4);
-                if (elect_one()) {
+                const uint32_t d = tmem_base + acc * BN;
+                for (int i = 0; i < num_kb; ++i) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (kA >> 4), b_lo = b_lo0 + (uint32_t)s * (kB >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(tmem_base, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
-                    umma_commit(&empty[s]);             // stage reusable once these MMAs have read it
-                    if (i == num_kb - 1) umma_commit(accum_full);      // accumulator complete
+                        for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(d, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
+                        umma_commit(&empty[s]);             // stage reusable once these MMAs have read it
+                        if (i == num_kb - 1) umma_commit(&tfull[acc]);     // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++s == kStages) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (num_kb > 0) {
+    } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const int chalf = (warp - 2) >> 2;              // two warps share a lane quarter: each takes half of the tile's columns
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
-        const int m = m0 + q * 32 + lane;
-        const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
         const bool drop = p.drop_p > 0.f;
         const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
         const bool atomic = p.splitk > 1;
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+            int zz, m0, n0;
+            decode(t, zz, m0, n0);
+            const int zb = zz / p.splitk;
+            const int z1 = zb / p.nb2, z2 = zb - z1 * p.nb2;
+            const uint32_t acc = it & 1u;
+            if (p.tma_store) {                          // the previous tile's TMA store must have finished reading the staging buffers
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(&tfull[acc], (it >> 1) & 1u);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
 #pragma unroll 1
-        for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-            const int nb = n0 + c0;
-            if (!p.tma_store && (m >= p.M || nb >= p.N)) continue;
-            if (p.tma_store && nb >= p.N) continue;              // (N % 32 == 0 on this path: whole chunks only)
-            const long long off = zoff + (long long)m * p.ldc + nb;
-            const long long roff = zoff + (long long)m * p.ldr + nb;
-            if (p.vec_ok && nb + 32 <= p.N) {
-                // ---------------- vector path: 32 consecutive columns of one row
-                float v[32];
-                const bool row_ok = m < p.M;                     // rows past M only exist to fill the staged tile; TMA clips them
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
+                const int nb = n0 + c0;
+                if (!p.tma_store && (m >= p.M || nb >= p.N)) continue;
+                if (p.tma_store && nb >= p.N) continue;              // (N % 32 == 0 on this path: whole chunks only)
+                const long long off = zoff + (long long)m * p.ldc + nb;
+                const long long roff = zoff + (long long)m * p.ldr + nb;
+                if (p.vec_ok && nb + 32 <= p.N) {
+                    // ---------------- vector path: 32 consecutive columns of one row
+                    float v[32];
+                    const bool row_ok = m < p.M;                     // rows past M only exist to fill the staged tile; TMA clips them
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 bz = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[j] = __uint_as_float(r[j]) * p.alpha + bz.x; v[j + 1] = __uint_as_float(r[j + 1]) * p.alpha + bz.y;
-                    v[j + 2] = __uint_as_float(r[j + 2]) * p.alpha + bz.z; v[j + 3] = __uint_as_float(r[j + 3]) * p.alpha + bz.w;
-                }
-                if (p.pre) {
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 bz = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j] = __uint_as_float(r[j]) * p.alpha + bz.x; v[j + 1] = __uint_as_float(r[j + 1]) * p.alpha + bz.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) * p.alpha + bz.z; v[j + 3] = __uint_as_float(r[j + 3]) * p.alpha + bz.w;
+                    }
+                    if (p.pre) {
+                        if (p.c_is_bf16) {
+                            unsigned char* sbox = stP + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
+                            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                                            *reinterpret_cast<uint32_t*>(&t3));
+                                if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
+                                else dst[j >> 3] = pk;
+                            }
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.pre) + off);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                    }
+                    if (drop) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {              // off is even here (ldc % 8 == 0, nb % 32 == 0)
+                            const uint32_t kp = keep_pair(p.drop_seed, (unsigned long long)(off + j) >> 1, thr);
+                            v[j] = (kp & 1u) ? v[j] * keep_scale : 0.f;
+                            v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
+                        }
+                    }
+                    if (p.resid && row_ok) {
+                        if (p.c_is_bf16) {
+                            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + roff);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 u = src[j >> 3];
+                                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z)), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+                                v[j] = f0.x + p.beta * v[j]; v[j + 1] = f0.y + p.beta * v[j + 1]; v[j + 2] = f1.x + p.beta * v[j + 2]; v[j + 3] = f1.y + p.beta * v[j + 3];
+                                v[j + 4] = f2.x + p.beta * v[j + 4]; v[j + 5] = f2.y + p.beta * v[j + 5]; v[j + 6] = f3.x + p.beta * v[j + 6]; v[j + 7] = f3.y + p.beta * v[j + 7];
+                            }
+                        } else {
+                            const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + roff);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 u = src[j >> 2];
+                                v[j] = u.x + p.beta * v[j]; v[j + 1] = u.y + p.beta * v[j + 1]; v[j + 2] = u.z + p.beta * v[j + 2]; v[j + 3] = u.w + p.beta * v[j + 3];
+                            }
+                        }
+                    } else if (p.beta != 1.0f && !p.resid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= p.beta;
+                    }
                     if (p.c_is_bf16) {
-                        // tma_store: stage the tile 128B-swizzled in the (now idle) B-operand ring: box c0/64, row = TMEM lane, 16-byte chunk ^ (row & 7)
-                        unsigned char* sbox = sB + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
+                        unsigned char* sbox = stC + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
@@ -237,130 +327,76 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                             else dst[j >> 3] = pk;
                         }
                     } else {
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.pre) + off);
+                        float* cp = static_cast<float*>(p.C) + off;
+                        if (atomic) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                }
-                if (p.act == 1) {
+                            for (int j = 0; j < 32; ++j) atomicAdd(cp + j, v[j]);
+                        } else if (p.accumulate) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                } else if (p.act == 2) {
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 u = *reinterpret_cast<float4*>(cp + j);
+                                u.x += v[j]; u.y += v[j + 1]; u.z += v[j + 2]; u.w += v[j + 3];
+                                *reinterpret_cast<float4*>(cp + j) = u;
+                            }
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
-                }
-                if (drop) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {              // off is even here (ldc % 8 == 0, nb % 32 == 0)
-                        const uint32_t kp = keep_pair(p.drop_seed, (unsigned long long)(off + j) >> 1, thr);
-                        v[j] = (kp & 1u) ? v[j] * keep_scale : 0.f;
-                        v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
-                    }
-                }
-                if (p.resid && row_ok) {
-                    if (p.c_is_bf16) {
-                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + roff);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 u = src[j >> 3];
-                            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-                            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z)), f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
-                            v[j] = f0.x + p.beta * v[j]; v[j + 1] = f0.y + p.beta * v[j + 1]; v[j + 2] = f1.x + p.beta * v[j + 2]; v[j + 3] = f1.y + p.beta * v[j + 3];
-                            v[j + 4] = f2.x + p.beta * v[j + 4]; v[j + 5] = f2.y + p.beta * v[j + 5]; v[j + 6] = f3.x + p.beta * v[j + 6]; v[j + 7] = f3.y + p.beta * v[j + 7];
-                        }
-                    } else {
-                        const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + roff);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 u = src[j >> 2];
-                            v[j] = u.x + p.beta * v[j]; v[j + 1] = u.y + p.beta * v[j + 1]; v[j + 2] = u.z + p.beta * v[j + 2]; v[j + 3] = u.w + p.beta * v[j + 3];
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
-                } else if (p.beta != 1.0f && !p.resid) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= p.beta;
+                    continue;
                 }
-                if (p.c_is_bf16) {
-                    unsigned char* sbox = sA + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;          // C tile staged in the idle A-operand ring
-                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
-                                                    *reinterpret_cast<uint32_t*>(&t3));
-                        if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
-                        else dst[j >> 3] = pk;
-                    }
-                } else {
-                    float* cp = static_cast<float*>(p.C) + off;
-                    if (atomic) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(cp + j, v[j]);
-                    } else if (p.accumulate) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 u = *reinterpret_cast<float4*>(cp + j);
-                            u.x += v[j]; u.y += v[j + 1]; u.z += v[j + 2]; u.w += v[j + 3];
-                            *reinterpret_cast<float4*>(cp + j) = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                }
-                continue;
-            }
-            // ---------------- scalar path (ragged N or unaligned C)
+                // ---------------- scalar path (ragged N or unaligned C)
 #pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                if (n >= p.N) break;
-                float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? p.bias[n] : 0.f);
-                if (p.pre) {
-                    if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.pre)[off + j] = __float2bfloat16_rn(v);
-                    else static_cast<float*>(p.pre)[off + j] = v;
-                }
-                if (p.act == 1) v = fmaxf(v, 0.f);
-                else if (p.act == 2) v = __fdividef(v, 1.0f + __expf(-v));
-                if (drop) v = keep_mask(p.drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
-                if (p.resid) {
-                    const float rv = p.c_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
-                    v = rv + p.beta * v;
-                } else v *= p.beta;
-                if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.C)[off + j] = __float2bfloat16_rn(v);
-                else {
-                    float* cp = static_cast<float*>(p.C) + off + j;
-                    if (atomic) atomicAdd(cp, v);
-                    else *cp = p.accumulate ? *cp + v : v;
-                }
-            }
-        }
-    }
-    if (p.tma_store && num_kb > 0) {
-        // all 8 epilogue warps have staged their part: make the generic-proxy writes visible to the async proxy, then one thread stores
-        if (warp >= 2) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-#pragma unroll
-                for (int j = 0; j < BN / 64; ++j) {
-                    if (n0 + 64 * j < p.N) {
-                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmC), "r"(n0 + 64 * j), "r"(m0), "r"(z2),
-                                     "r"(z1), "r"(smem_u32(sA + j * (TBM * 128))) : "memory");
-                        if (p.pre)
-                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmPre), "r"(n0 + 64 * j), "r"(m0),
-                                         "r"(z2), "r"(z1), "r"(smem_u32(sB + j * (TBM * 128))) : "memory");
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    if (n >= p.N) break;
+                    float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? p.bias[n] : 0.f);
+                    if (p.pre) {
+                        if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.pre)[off + j] = __float2bfloat16_rn(v);
+                        else static_cast<float*>(p.pre)[off + j] = v;
+                    }
+                    if (p.act == 1) v = fmaxf(v, 0.f);
+                    else if (p.act == 2) v = __fdividef(v, 1.0f + __expf(-v));
+                    if (drop) v = keep_mask(p.drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
+                    if (p.resid) {
+                        const float rv = p.c_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
+                        v = rv + p.beta * v;
+                    } else v *= p.beta;
+                    if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.C)[off + j] = __float2bfloat16_rn(v);
+                    else {
+                        float* cp = static_cast<float*>(p.C) + off + j;
+                        if (atomic) atomicAdd(cp, v);
+                        else *cp = p.accumulate ? *cp + v : v;
                     }
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+            // accumulator drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (p.tma_store) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) {
+                        if (n0 + 64 * j < p.N) {
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmC), "r"(n0 + 64 * j), "r"(m0),
+                                         "r"(z2), "r"(z1), "r"(smem_u32(stC + j * (TBM * 128))) : "memory");
+                            if (p.pre)
+                                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmPre), "r"(n0 + 64 * j),
+                                             "r"(m0), "r"(z2), "r"(z1), "r"(smem_u32(stP + j * (TBM * 128))) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
         }
+        if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------------------------------------
@@ -400,23 +436,22 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 template <int BN, bool A_MN, bool B_MN, int NS>
-static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, int nbatch, cudaStream_t stream) {
+static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, cudaStream_t stream) {
     static bool configured = false;
     const int smem = TcSmem<BN, NS>::kBytes;
     if (!configured) {
         SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((e.N + BN - 1) / BN, (e.M + TBM - 1) / TBM, nbatch * e.splitk);
+    const int grid = (int)(e.ntiles < sm_count() ? e.ntiles : sm_count());
     gemm_tc_kernel<BN, A_MN, B_MN, NS><<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, mp, e);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, int nbatch, cudaStream_t stream) {
-    if (e.kb_per_split <= 8) return launch_tc_ns<BN, A_MN, B_MN, 2>(ma, mb, mc, mp, e, nbatch, stream);
-    return launch_tc_ns<BN, A_MN, B_MN, 3>(ma, mb, mc, mp, e, nbatch, stream);
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, cudaStream_t stream) {
+    return launch_tc_ns<BN, A_MN, B_MN, 4>(ma, mb, mc, mp, e, stream);
 }
 
 }  // namespace sarssl
@@ -464,10 +499,12 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     }
     e.kb_per_split = (num_kb + splitk - 1) / splitk;
     e.splitk = (num_kb + e.kb_per_split - 1) / e.kb_per_split;
+    e.tiles_m = (a->M + TBM - 1) / TBM;
+    e.tiles_n = (a->N + BN - 1) / BN;
+    e.ntiles = (long long)e.tiles_m * e.tiles_n * nbatch * e.splitk;
     CUtensorMap ma, mb, mc, mp;
     int rc;
     // bf16 outputs leave through a swizzled shared-memory stage + TMA store (full 128-byte lines instead of 16-byte pieces per thread);
-    // the stage re-uses the operand rings, which needs 2 x (128 rows x 128 B) per 64 columns: both rings are >= 32 KB
     e.tma_store = e.c_is_bf16 && e.vec_ok && (a->N % 32 == 0);
     memset(&mc, 0, sizeof(mc));
     memset(&mp, 0, sizeof(mp));
@@ -480,8 +517,8 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
                   : make_map(&ma, a->A, a->K, a->M, lda, 64, TBK, a->nb1, a->sAb1, a->nb2, a->sAb2))) return rc;
     if ((rc = b_k ? make_map(&mb, a->B, a->N, a->K, ldb, TBK, BN, a->nb1, a->sBb1, a->nb2, a->sBb2)
                   : make_map(&mb, a->B, a->K, a->N, ldb, 64, TBK, a->nb1, a->sBb1, a->nb2, a->sBb2))) return rc;
-    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, false, false>(ma, mb, mc, mp, e, nbatch, stream);
-    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, false, true>(ma, mb, mc, mp, e, nbatch, stream);
-    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, true, false>(ma, mb, mc, mp, e, nbatch, stream);
-    return bn64 ? launch_tc<64, true, true>(ma, mb, mc, mp, e, nbatch, stream) : launch_tc<128, true, true>(ma, mb, mc, mp, e, nbatch, stream);
+    if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, false>(ma, mb, mc, mp, e, stream);
+    if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, true>(ma, mb, mc, mp, e, stream);
+    if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, true, false>(ma, mb, mc, mp, e, stream);
+    return bn64 ? launch_tc<64, true, true>(ma, mb, mc, mp, e, stream) : launch_tc<128, true, true>(ma, mb, mc, mp, e, stream);
 }
