@@ -8,7 +8,7 @@
 //
 // Persistent: one CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running CTAs share A rows through L2).
 // warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues UMMA
-// 128xBNx16 instructions), warps 2-9 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects and half of the tile's columns).
+// 128xBNx16 instructions), warps 2-17 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects and one 32-column chunk).
 // A ring of 128B-swizzled shared-memory stages is handed from TMA to MMA through full/empty mbarriers; tcgen05.commit releases a
 // stage when the MMAs reading it retire and signals the epilogue when a tile's accumulator is complete.  The accumulator is double
 // buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> bias / activation / dropout / residual -> bf16 -> swizzled smem
@@ -19,7 +19,7 @@
 
 namespace sarssl {
 
-constexpr int TBM = 128, TBK = 64, kTcThreads = 320;      // 2 control warps + 8 epilogue warps
+constexpr int TBM = 128, TBK = 64, kEpiWarps = 16, kTcThreads = 64 + 32 * kEpiWarps;      // 2 control warps + 16 epilogue warps
 
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
     uint64_t* full = reinterpret_cast<uint64_t*>(stP + kSC);
     uint64_t* empty = full + kStages;
     uint64_t* tfull = empty + kStages;                            // [2] accumulator ready
-    uint64_t* tempty = tfull + 2;                                 // [2] accumulator drained (8 epilogue warps arrive)
+    uint64_t* tempty = tfull + 2;                                 // [2] accumulator drained (every epilogue warp arrives)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);      // two accumulators of BN fp32 columns x 128 lanes
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         }
     } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
-        const int chalf = (warp - 2) >> 2;              // two warps share a lane quarter: each takes half of the tile's columns
+        const int cpart = (warp - 2) >> 2;              // four warps share a lane quarter: each takes one 32-column chunk (BN = 64: parts 2, 3 idle)
         const bool drop = p.drop_p > 0.f;
         const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             const uint32_t acc = it & 1u;
             if (p.tma_store) {                          // the previous tile's TMA store must have finished reading the staging buffers
                 if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             }
             mbar_wait(&tfull[acc], (it >> 1) & 1u);
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
             const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
 #pragma unroll 1
-            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = cpart * 32; c0 < BN; c0 += 128) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
                 const int nb = n0 + c0;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (p.tma_store) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (warp == 2 && lane == 0) {
 #pragma unroll
                     for (int j = 0; j < BN / 64; ++j) {
