@@ -8,7 +8,7 @@
 //
 // Persistent: one CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running CTAs share A rows through L2).
 // warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues UMMA
-// 128xBNx16 instructions), warps 2-17 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects and one 32-column chunk).
+// 128xBNx16 instructions), warps 2-9 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 selects and every other 32-column chunk).
 // A ring of 128B-swizzled shared-memory stages is handed from TMA to MMA through full/empty mbarriers; tcgen05.commit releases a
 // stage when the MMAs reading it retire and signals the epilogue when a tile's accumulator is complete.  The accumulator is double
 // buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> bias / activation / dropout / residual -> bf16 -> swizzled smem
@@ -19,7 +19,7 @@
 
 namespace sarssl {
 
-constexpr int TBM = 128, TBK = 64, kEpiWarps = 16, kTcThreads = 64 + 32 * kEpiWarps;      // 2 control warps + 16 epilogue warps
+constexpr int TBM = 128, TBK = 64, kEpiWarps = 8, kTcThreads = 64 + 32 * kEpiWarps;       // 2 control warps + 8 epilogue warps (16 measured slightly slower)
 
 struct TcEpi {
     void* C; void* pre; const void* resid; const float* bias;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         }
     } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
-        const int cpart = (warp - 2) >> 2;              // four warps share a lane quarter: each takes one 32-column chunk (BN = 64: parts 2, 3 idle)
+        const int cpart = (warp - 2) >> 2;              // warps sharing a lane quarter interleave the tile's 32-column chunks
         const bool drop = p.drop_p > 0.f;
         const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             const int m = m0 + q * 32 + lane;
             const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
 #pragma unroll 1
-            for (int c0 = cpart * 32; c0 < BN; c0 += 128) {
+            for (int c0 = cpart * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
                 const int nb = n0 + c0;
