@@ -17,12 +17,19 @@ template <typename T>
 __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
     if (mode == 0) {
         const T* q = static_cast<const T*>(in) + p * 4;
-        return make_float4(to_f32(q[0]), to_f32(q[1]), to_f32(q[2]), to_f32(q[3]));
+        if (sizeof(T) == 2) {                                   // 4 x bf16 = one 8-byte load
+            const uint2 u = *reinterpret_cast<const uint2*>(q);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            return make_float4(a.x, a.y, b.x, b.y);
+        }
+        return *reinterpret_cast<const float4*>(q);
     }
     float4 x = *reinterpret_cast<const float4*>(static_cast<const float*>(in) + p * 4);
-    const long long row = p / W;
+    // (pixel counts stay far below 2^32: 32-bit divisions, a shift when W is a power of two)
+    const unsigned up = (unsigned)p, uw = (unsigned)W;
+    const unsigned row = ((uw & (uw - 1)) == 0) ? (up >> (31 - __clz((int)uw))) : up / uw;
     const bool pm = flag[row] != 0;
-    const int mc = ch[row / H];
+    const int mc = ch[row / (unsigned)H];
     if (mode == 1) {
         const int keep = pm ? 1 - mc : mc;
         if (keep == 0) { x.y = 0.f; x.w = 0.f; } else { x.x = 0.f; x.z = 0.f; }
@@ -311,7 +318,7 @@ using namespace sarssl;
 
 extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
                                   long long P, int W, int H, int dtype, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0, "stem_expand: bad arguments");
+    SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0 && P < 0xFFFFFFFFLL, "stem_expand: bad arguments (P must be in (0, 2^32))");
     SARSSL_CHECK_ARG(mode == 0 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
     if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
     else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
@@ -340,7 +347,7 @@ extern "C" size_t sarssl_stem_workspace_bytes(void) {
 extern "C" int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, const float* wide_shift, const void* narrow, int mode,
                                     const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
                                     int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0, "stem_pw_wgrad: bad arguments");
+    SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_pw_wgrad: bad arguments (P must be in (0, 2^32))");
     const int grid = pix_grid(P);
     if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
