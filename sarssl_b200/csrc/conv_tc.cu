@@ -86,7 +86,8 @@ constexpr int CSEG = 32;                 // image rows per work unit (2 halo row
 constexpr int CWB = 9 * 8192;            // resident weights
 constexpr int COUTB = CW * 128;           // 16 KB output staging tile (x2)
 constexpr int kConvSmem = CSLOTS * CBOXB + CWB + 2 * COUTB + 1024 + 256;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;          // weight-gradient kernel: 2 control + 4 epilogue warps
+constexpr int kConvFwdThreads = 320;       // forward kernel: 2 control + 8 epilogue warps (the epilogue paces the tile rate)
 
 struct ConvP {
     __nv_bfloat16* out;
@@ -95,7 +96,7 @@ struct ConvP {
     long long nunits;
 };
 
-__global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmOut, ConvP p) {
     extern __shared__ unsigned char raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
         for (int s = 0; s < CSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(wbar, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -199,8 +200,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
         }
     } else {
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;                      // two warps share a lane quarter: channels [32*chalf, 32*chalf + 32)
         const int row = q * 32 + lane;                          // pixel row of the tile = TMEM lane
-        // fused BatchNorm statistics: thread (channel sc, row half sh) adds its 64 staged bf16 values of every tile
+        // fused BatchNorm statistics: thread (channel sc, row quarter sh) adds its 32 staged bf16 values of every tile
         const int et = (warp - 2) * 32 + lane, sc = et & 63, sh = et >> 6;
         float bn_s = 0.f, bn_q = 0.f;
         uint32_t it = 0;
@@ -214,11 +216,11 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
                 unsigned char* stage = osm + acc * COUTB;
                 // the TMA store that last read this staging buffer (2 tiles ago) must have finished reading it
                 if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 mbar_wait(&tfull[acc], (it >> 1) & 1u);
                 cfence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
+                {
+                    const int c0 = chalf * 32;
                     uint32_t v[32];
                     ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
 #pragma unroll
@@ -238,17 +240,17 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);       // TMEM buffer free for the MMA warp
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (warp == 2 && lane == 0) {
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmOut), "r"(0), "r"(w0), "r"(h), "r"(b),
                                  "r"(smem_u32(stage)) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (p.bn_partials != nullptr) {
-                    const int rmax = min(64, p.W - w0 - sh * 64);                 // rows beyond the image edge hold garbage
+                    const int rmax = min(32, p.W - w0 - sh * 32);                 // rows beyond the image edge hold garbage
                     const unsigned char* colp = stage + ((sc & 7) << 1);
                     for (int r = 0; r < rmax; ++r) {
-                        const int rr = sh * 64 + r;
+                        const int rr = sh * 32 + r;
                         const float xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + (((sc >> 3) ^ (rr & 7)) << 4)));
                         bn_s += xv; bn_q += xv * xv;
                     }
@@ -257,14 +259,14 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_tc_kernel(const __grid_c
         }
         if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.bn_partials != nullptr) {
-            // combine the two row halves through the (now idle) staging buffer, fixed order
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // combine the four row quarters through the (now idle) staging buffer, fixed order
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             float* red = reinterpret_cast<float*>(osm);
             red[et * 2] = bn_s; red[et * 2 + 1] = bn_q;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (sh == 0) {
-                p.bn_partials[((size_t)blockIdx.x * 2 + 0) * 64 + sc] = red[sc * 2] + red[(64 + sc) * 2];
-                p.bn_partials[((size_t)blockIdx.x * 2 + 1) * 64 + sc] = red[sc * 2 + 1] + red[(64 + sc) * 2 + 1];
+                p.bn_partials[((size_t)blockIdx.x * 2 + 0) * 64 + sc] = (red[sc * 2] + red[(64 + sc) * 2]) + (red[(128 + sc) * 2] + red[(192 + sc) * 2]);
+                p.bn_partials[((size_t)blockIdx.x * 2 + 1) * 64 + sc] = (red[sc * 2 + 1] + red[(64 + sc) * 2 + 1]) + (red[(128 + sc) * 2 + 1] + red[(192 + sc) * 2 + 1]);
             }
         }
     }
@@ -507,7 +509,7 @@ extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void
     p.tiles_w = (W + CW - 1) / CW; p.nseg_h = (H + CSEG - 1) / CSEG;
     p.nunits = (long long)B * p.tiles_w * p.nseg_h;
     const int grid = sarssl_conv3x3_tc_grid(B, H, W);
-    conv3x3_tc_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(mi, mw, mo, p);
+    conv3x3_tc_kernel<<<grid, kConvFwdThreads, kConvSmem, stream>>>(mi, mw, mo, p);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
