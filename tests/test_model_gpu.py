@@ -172,6 +172,20 @@ def test_bf16_mode_loss_and_gradients():
     assert errs[len(errs) // 2] <= 1.25 * autos[len(autos) // 2] + 5e-3, (errs[len(errs) // 2], autos[len(autos) // 2])
 
 
+@pytest.mark.parametrize("nb,nt", [(2, 12), (1, 249)])
+def test_bf16_ragged_frame_counts(nb, nt):
+    """Frame counts that are not multiples of 8 / 128 (4.000 s clips give nt = 249): the tensor-core kernels clip
+    their tiles, the attention GEMMs whose leading dimension is not 16-byte aligned take the CUDA-core kernel."""
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=4)
+    m = build(nt, dtype=torch.bfloat16)
+    loss, diff, vis = run_ours(m, sig, 13)
+    rl, rd, rvis, sd, taps = run_oracle(sig, nt, 7, 13)
+    assert abs(float(loss) - float(rl)) < 2e-2 * float(rl) and abs(float(diff) - float(rd)) < 1e-4 * float(rd)
+    assert rel(vis["pred"].float().cpu(), rvis["pred"]) < 3e-2
+    gdec = m.store.p("decoder.proj.2.weight").grad.cpu()
+    assert rel(gdec, sd["decoder.proj.2.weight"].grad) < 5e-2
+
+
 def test_dropout_statistics_and_train_step():
     """Dropout on: the loss stays finite, differs between steps (new masks), and a few fused-Adam steps reduce it."""
     nb, nt = 4, 16
