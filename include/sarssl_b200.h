@@ -80,6 +80,13 @@ int sarssl_stft_frontend_error_flag(const void* workspace, int* flag_host, cudaS
 int sarssl_istft(const float* spec, float* sig, int nb, int nt, int nch, long long stride_b, long long stride_t, long long stride_k,
                  long long stride_c, int win_len, int hop, int nfft, cudaStream_t stream);
 
+/* iSTFT of a patch-layout spectrogram (nb, nt, 256, 2, 2) = bins 1..256 with an implied zero DC bin - what
+ * pretrain_evaluate inverts (learner.py:581-590) -> sig (nb, (nt+1)*256, 2) */
+int sarssl_istft_patches(const float* patches, float* sig, int nb, int nt, cudaStream_t stream);
+
+/* x /= max(x) over n floats (pretrain_evaluate, learner.py:584,590); workspace >= 4 KB */
+int sarssl_normalize_by_max(float* x, long long n, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * A4  mask indices: CPython `random` (MT19937) bit-exact, host side       common/utils_module.py:255-272,305-308
  * ---------------------------------------------------------------------------------------------------------- */
@@ -116,6 +123,11 @@ size_t sarssl_masked_loss_workspace_bytes(int nb, int nt);
 int sarssl_masked_loss(const void* pred, int pred_dtype, const float* patches, const uint8_t* frame_flag, const int32_t* ch_idx,
                        float* out2, void* dpred, int nb, int nt, int nf, int nmasked, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream);
+/* pretrain_evaluate's error sums (learner.py:592-602) over patch-layout fp32 tensors (nb, nt, nf, 2, 2):
+ *   sums2[0] = sum (pred - gt)^2 over all elements, sums2[1] = the same over masked frame x masked microphone.
+ *   workspace: sarssl_masked_loss_workspace_bytes(nb, nt). */
+int sarssl_eval_mse_sums(const float* pred, const float* gt, const uint8_t* frame_flag, const int32_t* ch_idx, float* sums2, int nb, int nt, int nf,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* dpred[masked rows] *= *gscale_dev  (upstream gradient of the scalar loss, read on the device: no host sync) */
 int sarssl_scale_masked_rows(void* dpred, int dtype, const uint8_t* frame_flag, const float* gscale_dev, int nb, int nt, int nf,
                              cudaStream_t stream);

@@ -19,6 +19,9 @@ constexpr int kIThreads = kIGroups * kFftLanes;
 __device__ __forceinline__ void igroup_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kFftLanes) : "memory"); }
 
 // spec element (b, t, k, ch) at spec[b*sb + t*st + k*sk + ch*sc] (strides in complex elements)
+// PATCH = true: `spec` is the patch layout float4 [b][t][256] = (re0, re1, im0, im1) of bins 1..256 with an implied zero DC bin
+// (what pretrain_evaluate feeds the iSTFT, learner.py:581-590); nch == 2.
+template <bool PATCH>
 __global__ void __launch_bounds__(kIThreads) istft_kernel(const float2* __restrict__ spec, float* __restrict__ sig, int nb, int nt,
                                                         int nch, long long sb, long long st, long long sk, long long sc,
                                                         int npair, int cps) {
@@ -48,8 +51,17 @@ __global__ void __launch_bounds__(kIThreads) istft_kernel(const float2* __restri
             for (int r = 0; r < 8; ++r) {
                 const int n = l + 64 * r;                   // bin index 0..511 of conj(Z)
                 const int k = n <= 256 ? n : 512 - n;
-                float2 a = base[(size_t)k * sk + (size_t)c0 * sc];
-                float2 c = c1 < nch ? base[(size_t)k * sk + (size_t)c1 * sc] : make_float2(0.f, 0.f);
+                float2 a, c;
+                if (PATCH) {
+                    if (k == 0) { a = make_float2(0.f, 0.f); c = a; }
+                    else {
+                        const float4 q = reinterpret_cast<const float4*>(spec)[((size_t)b * nt + t) * 256 + (k - 1)];
+                        a = make_float2(q.x, q.z); c = make_float2(q.y, q.w);
+                    }
+                } else {
+                    a = base[(size_t)k * sk + (size_t)c0 * sc];
+                    c = c1 < nch ? base[(size_t)k * sk + (size_t)c1 * sc] : make_float2(0.f, 0.f);
+                }
                 if (k == 0 || k == 256) { a.y = 0.f; c.y = 0.f; }
                 if (n > 256) { a.y = -a.y; c.y = -c.y; }    // Hermitian extension X[n] = conj(X[512-n])
                 // Z = a + i*c ; feed conj(Z)
@@ -100,8 +112,60 @@ extern "C" int sarssl_istft(const float* spec, float* sig, int nb, int nt, int n
         return SARSSL_ERR_UNSUPPORTED;
     }
     const int npair = (nch + 1) / 2, cps = (nt + 1 + kSegPerCta - 1) / kSegPerCta;
-    istft_kernel<<<nb * cps * npair, kIThreads, 0, stream>>>(reinterpret_cast<const float2*>(spec), sig, nb, nt, nch, stride_b, stride_t,
-                                                            stride_k, stride_c, npair, cps);
+    istft_kernel<false><<<nb * cps * npair, kIThreads, 0, stream>>>(reinterpret_cast<const float2*>(spec), sig, nb, nt, nch, stride_b, stride_t,
+                                                                   stride_k, stride_c, npair, cps);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// iSTFT of a patch-layout spectrogram (nb, nt, 256, 2, 2) with zero DC -> sig (nb, (nt+1)*256, 2)
+extern "C" int sarssl_istft_patches(const float* patches, float* sig, int nb, int nt, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(patches && sig && nb > 0 && nt > 0, "istft_patches: bad arguments");
+    SARSSL_CHECK_ARG(aligned16(patches), "istft_patches: patches must be 16-byte aligned");
+    const int cps = (nt + 1 + kSegPerCta - 1) / kSegPerCta;
+    istft_kernel<true><<<nb * cps, kIThreads, 0, stream>>>(reinterpret_cast<const float2*>(patches), sig, nb, nt, 2, 0, 0, 0, 0, 1, cps);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+namespace sarssl {
+__global__ void __launch_bounds__(256) max_partial_kernel(const float* __restrict__ x, long long n, float* __restrict__ partials) {
+    __shared__ float red[32];
+    float m = -INFINITY;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) m = fmaxf(m, x[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 8 ? red[threadIdx.x] : -INFINITY;
+        m = warp_max(m);
+        if (threadIdx.x == 0) partials[blockIdx.x] = m;
+    }
+}
+__global__ void __launch_bounds__(256) scale_by_max_kernel(float* __restrict__ x, long long n, const float* __restrict__ partials, int nparts) {
+    __shared__ float s_inv;
+    if (threadIdx.x < 32) {
+        float m = -INFINITY;
+        for (int i = threadIdx.x; i < nparts; i += 32) m = fmaxf(m, partials[i]);
+        m = warp_max(m);
+        if (threadIdx.x == 0) s_inv = 1.0f / m;
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) x[i] *= inv;
+}
+}  // namespace sarssl
+
+// x /= max(x)  (pretrain_evaluate normalises the reconstructed signals by their global maximum, learner.py:584,590); workspace >= 4 KB
+extern "C" int sarssl_normalize_by_max(float* x, long long n, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(x && workspace && n > 0, "normalize_by_max: bad arguments");
+    long long g = (n + 2047) / 2048;
+    if (g > 1024) g = 1024;
+    if (workspace_bytes < (size_t)g * sizeof(float)) { set_last_error("normalize_by_max: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    float* partials = static_cast<float*>(workspace);
+    sarssl::max_partial_kernel<<<(unsigned)g, 256, 0, stream>>>(x, n, partials);
+    SARSSL_LAUNCH_CHECK();
+    sarssl::scale_by_max_kernel<<<(unsigned)g, 256, 0, stream>>>(x, n, partials, (int)g);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -102,6 +102,35 @@ __global__ void scale_masked_rows_kernel(T* __restrict__ dpred, const uint8_t* _
     }
 }
 
+// pretrain_evaluate metrics (learner.py:592-602) over patch-layout tensors: sums[0] = sum (pred-gt)^2 over everything,
+// sums[1] = the same restricted to masked frame x masked channel (where the reference's dense mask is 0).  Per-CTA partials, fixed order.
+__global__ void __launch_bounds__(256) eval_mse_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const uint8_t* __restrict__ frame_flag,
+                                                     const int32_t* __restrict__ ch_idx, float* __restrict__ partials, int nrows, int nt, int nf) {
+    __shared__ float red[32];
+    float all = 0.f, msk = 0.f;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const bool masked = frame_flag[row] != 0;
+        const int mc = ch_idx[row / nt];
+        const size_t base = (size_t)row * nf * 4;
+        for (int f = threadIdx.x; f < nf; f += 256) {
+            const float4 p = load4(pred + base + (size_t)f * 4), x = load4(gt + base + (size_t)f * 4);
+            const float d0 = (p.x - x.x) * (p.x - x.x) + (p.z - x.z) * (p.z - x.z);      // mic 0: re, im
+            const float d1 = (p.y - x.y) * (p.y - x.y) + (p.w - x.w) * (p.w - x.w);      // mic 1
+            all += d0 + d1;
+            if (masked) msk += mc ? d1 : d0;
+        }
+    }
+    const float sa = block_sum(all, red), sm = block_sum(msk, red);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = sa; partials[2 * blockIdx.x + 1] = sm; }
+}
+__global__ void eval_mse_finalize_kernel(const float* __restrict__ partials, int n, float* __restrict__ out2) {
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += (double)partials[2 * i + threadIdx.x];
+        out2[threadIdx.x] = (float)s;
+    }
+}
+
 static int loss_grid(int nrows) {
     const int cap = sm_count() * 8;
     return nrows < cap ? nrows : cap;
@@ -140,6 +169,20 @@ extern "C" int sarssl_masked_loss(const void* pred, int pred_dtype, const float*
         masked_loss_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(pred), patches, frame_flag,
                                                                              ch_idx, out2, static_cast<__nv_bfloat16*>(dpred), nrows, nt, nf,
                                                                              inv_count, counter, partials);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// sums2[0] = sum over all elements of (pred - gt)^2; sums2[1] = the same over masked frame x masked channel only
+extern "C" int sarssl_eval_mse_sums(const float* pred, const float* gt, const uint8_t* frame_flag, const int32_t* ch_idx, float* sums2, int nb, int nt,
+                                    int nf, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(pred && gt && frame_flag && ch_idx && sums2 && workspace && nb > 0 && nt > 0 && nf > 0, "eval_mse_sums: bad arguments");
+    if (workspace_bytes < sarssl_masked_loss_workspace_bytes(nb, nt)) { set_last_error("eval_mse_sums: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    const int nrows = nb * nt, grid = loss_grid(nrows);
+    float* partials = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 256);
+    eval_mse_kernel<<<grid, 256, 0, stream>>>(pred, gt, frame_flag, ch_idx, partials, nrows, nt, nf);
+    SARSSL_LAUNCH_CHECK();
+    eval_mse_finalize_kernel<<<1, 32, 0, stream>>>(partials, grid, sums2);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

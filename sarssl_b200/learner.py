@@ -73,8 +73,6 @@ class Learner(CheckpointMixin, ABC):
 
     def pretest_epoch(self, dataset, return_diff=True, return_eval=False):
         """learner.py:133-167: eval-mode pass (BatchNorm running statistics, no dropout, masks still random)."""
-        if return_eval:
-            raise SarsslError("pretest_epoch(return_eval=True) needs pretrain_evaluate (iSTFT + PESQ, SURVEY.md 8(f) row 3): not built yet")
         self.model.eval()
         log, vis_batch = [], None
         with torch.no_grad():
@@ -84,6 +82,9 @@ class Learner(CheckpointMixin, ABC):
                 log.append(torch.stack([loss_batch, diff_batch]))
         vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]
         if return_diff:
+            if return_eval:      # metrics of the last batch only, like the reference (learner.py:160-162)
+                result = self.pretrain_evaluate(pred_batch=vis_batch["pred"], gt_batch=vis_batch["tar"], mask_batch=vis_batch["mask"])
+                return vals[0], vals[1], vis_batch, result
             return vals[0], vals[1], vis_batch
         return vals[0]
 
@@ -114,3 +115,49 @@ class STFTLearner(Learner):
         if gt_batch is not None:
             raise SarsslError("data_preprocess(gt_batch=...) belongs to the downstream path (SURVEY.md 8(f) row 1), not built yet")
         return data
+
+    def pretrain_evaluate(self, pred_batch, gt_batch, mask_batch):
+        """learner.py:574-618: reconstruct the waveforms of prediction and target with the iSTFT (zero DC
+        bin re-inserted, rectangular synthesis), normalise each by its global maximum, and report the reconstruction errors.
+            pred_batch / gt_batch (nb, nf, nt, 2, 2), mask_batch (nb, nf, nt, 2) with 0 = masked
+        Returns {'sig_pred', 'sig_tar', 'mse', 'mse_mask', 'mse_mask_ch', 'pesq', 'pesq_mask_ch'}.  PESQ comes from torchmetrics in the
+        reference; when that third-party package is not installed the two PESQ entries are NaN."""
+        import ctypes as C
+        from ._lib import check, lib, ptr, stream_ptr
+        L = lib()
+
+        def patch_layout(t):                      # (nb, nf, nt, 2, 2) -> contiguous (nb, nt, nf, 2, 2)
+            v = t.permute(0, 2, 1, 3, 4)
+            return (v if v.is_contiguous() else v.contiguous()).float()
+
+        pred, gt = patch_layout(pred_batch), patch_layout(gt_batch)
+        nb, nt, nf = pred.shape[:3]
+        dev = pred.device
+        # compact masks from the dense one: a frame is masked where some entry is 0; the masked microphone is the one holding zeros
+        zero = mask_batch == 0                                         # (nb, nf, nt, nch)
+        flag = zero.any(dim=3).any(dim=1).to(torch.uint8).contiguous()         # (nb, nt)
+        ch = zero.any(dim=2).any(dim=1).float().argmax(dim=1).to(torch.int32).contiguous()
+        ws = torch.empty(max(L.sarssl_masked_loss_workspace_bytes(nb, nt), 4096), dtype=torch.uint8, device=dev)
+        sums = torch.empty(2, dtype=torch.float32, device=dev)
+        check(L.sarssl_eval_mse_sums(ptr(pred), ptr(gt), ptr(flag), ptr(ch), ptr(sums), nb, nt, nf, ptr(ws), ws.numel(), stream_ptr(dev)), "eval_mse_sums")
+        sigs = []
+        for spec in (pred, gt):
+            sig = torch.empty(nb, (nt + 1) * 256, 2, dtype=torch.float32, device=dev)
+            check(L.sarssl_istft_patches(ptr(spec), ptr(sig), nb, nt, stream_ptr(dev)), "istft_patches")
+            check(L.sarssl_normalize_by_max(ptr(sig), sig.numel(), ptr(ws), ws.numel(), stream_ptr(dev)), "normalize_by_max")
+            sigs.append(sig)
+        nmasked_elems = flag.sum().float() * nf * 2                     # sum(1 - mask_dense): masked frames x bins x re/im
+        result = {"sig_pred": sigs[0], "sig_tar": sigs[1], "mse": sums[0] / pred.numel(), "mse_mask": sums[1] / nmasked_elems,
+                  "mse_mask_ch": sums[1] / (nb * nt * nf * 2)}
+        try:
+            from torchmetrics.functional.audio.pesq import perceptual_evaluation_speech_quality as pesq_fn
+        except Exception:
+            pesq_fn = None
+        pesq = torch.full((nb, 2), float("nan"))
+        if pesq_fn is not None:
+            for b in range(nb):
+                for c in range(2):
+                    pesq[b, c] = pesq_fn(sigs[0][b, :, c].cpu(), sigs[1][b, :, c].cpu(), 16000, "wb")
+        result["pesq"] = pesq
+        result["pesq_mask_ch"] = pesq[torch.arange(nb), ch.cpu().long()]
+        return result

@@ -200,3 +200,29 @@ def test_dropout_statistics_and_train_step():
     assert np.isfinite(first) and np.isfinite(last) and last < first
     le, de, _ = L.pretest_epoch([[sig]])
     assert np.isfinite(le) and de > 0
+
+
+def test_pretrain_evaluate_matches_oracle_math():
+    """Evaluation tail (learner.py:574-618): iSTFT with zero DC, max normalisation, reconstruction errors."""
+    nb, nt = 3, 16
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=5)
+    m = build(nt)
+    L = STFTLearner(m, 512, 0.5, 512, 1, 16000)
+    L.device = DEV
+    random.seed(11)
+    le, de, vis, res = L.pretest_epoch([[sig]], return_diff=True, return_eval=True)
+    pred, gt, mask = vis["pred"].cpu(), vis["tar"].cpu(), vis["mask"].cpu()           # (nb,nf,nt,2,2), (nb,nf,nt,2)
+
+    def to_sig(t):                                                                    # the reference's recipe, on the CPU oracle
+        z = torch.view_as_complex(t.permute(0, 1, 2, 4, 3).contiguous())              # (nb, nf, nt, nch)
+        z = torch.cat((torch.zeros_like(z[:, 0:1]), z), dim=1)
+        s = O.istft(z)
+        return s / s.max()
+
+    assert rel(res["sig_pred"].cpu(), to_sig(pred)) < 1e-4 and rel(res["sig_tar"].cpu(), to_sig(gt)) < 1e-4
+    md = mask[:, :, :, None, :].expand(-1, -1, -1, 2, -1)
+    d = (pred - gt) ** 2
+    assert abs(float(res["mse"]) - float(d.mean())) < 1e-4 * float(d.mean())
+    assert abs(float(res["mse_mask"]) - float((d * (1 - md)).sum() / (1 - md).sum())) < 1e-4 * float(res["mse_mask"])
+    assert abs(float(res["mse_mask_ch"]) - float((d * (1 - md)).sum(4).mean())) < 1e-4 * float(res["mse_mask_ch"])
+    assert res["pesq"].shape == (nb, 2)
