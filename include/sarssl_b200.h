@@ -235,6 +235,11 @@ size_t sarssl_dwconv_wgrad_workspace_bytes(int D, int K);
 int sarssl_dwconv_wgrad(const void* a, const void* dc, float* dweight, int B, int T, int D, int K, int dtype, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream);
 
+/* time-mean pooling of the downstream branch (torch.mean(embed, dim=1), model.py:705) and its gradient:
+ *   pooled[b][d] = mean_t x[b][t][d] (fp32);   dx[b][t][d] = dpooled[b][d] / T      (x / dx rows at stride ldx) */
+int sarssl_mean_pool_fwd(const void* x, long long ldx, float* pooled, int B, int T, int D, int dtype, cudaStream_t stream);
+int sarssl_mean_pool_bwd(const float* dpooled, void* dx, long long ldx, int B, int T, int D, int dtype, cudaStream_t stream);
+
 /* utilities: dtype cast, 4-d permuting copy (weight packing / gradient un-packing), fill */
 int sarssl_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t stream);
 int sarssl_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, const int* dims4_host, const long long* src_strides4_host,

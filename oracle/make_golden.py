@@ -109,6 +109,37 @@ def run_case(name, nb, nt, sig_seed, sd_seed, mask_seed, keep_full):
     print(name, "loss", out["loss"], "diff", out["diff"], "eval", out["eval_loss"])
 
 
+def run_downstream_case(name, nb, nt, embed, sig_seed, sd_seed):
+    """Downstream fine-tuning branch: reference SARSSL(pretrain=False) + STFTLearner(task='TDOA') MSE step."""
+    rm, rl, rops, ru = ref_shim.load_reference()
+    dds = {"spec_spat": 768, "spec": 512, "spat": 256}[embed]
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=sig_seed)
+    labels = (torch.arange(nb, dtype=torch.float32) - nb / 2) * 1e-4                   # TDOA in seconds
+    net = rm.SARSSL(sig_shape=(256, nt, 2, 2), pretrain=False, device="cpu", downstream_embed=embed)
+    net.load_state_dict(O.synthetic_state_dict(sd_seed, pretrain=False, dembed_ds=dds))
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    L = rl.STFTLearner(net, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task="TDOA", ch_mode="M")
+    L.cpu()
+    net.train()
+    x, tar = L.data_preprocess(sig, {"TDOA": labels})
+    pred, emb = net(x)
+    loss = L.loss(pred_batch=pred, gt_batch=tar)
+    loss.backward()
+    out = {"nb": nb, "nt": nt, "sig_seed": sig_seed, "sd_seed": sd_seed, "labels": labels.numpy(), "tar": tar.numpy(), "pred": pred.detach().numpy(),
+           "embed": emb.detach().numpy(), "loss": float(loss), "mae": float(L.evaluate(pred_batch=pred, gt_batch=tar))}
+    for k, p in net.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        g = g.reshape(-1)
+        idx = sample_idx(g.numel(), 64)
+        out["grad_idx/" + k] = idx
+        out["grad_val/" + k] = g.numpy()[idx]
+        out["grad_norm/" + k] = float(g.norm())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "pred", out["pred"].ravel()[:3])
+
+
 def mask_streams():
     """Known-answer vectors for the mask RNG: python `random` (CPython MT19937) under the reference's seeds."""
     out = {}
@@ -138,3 +169,5 @@ if __name__ == "__main__":
     lr_table()
     run_case("tiny_nt16_b3", nb=3, nt=16, sig_seed=5, sd_seed=7, mask_seed=11, keep_full=True)
     run_case("full_nt256_b2", nb=2, nt=256, sig_seed=6, sd_seed=7, mask_seed=400000001, keep_full=False)
+    run_downstream_case("downstream_nt16_b4", nb=4, nt=16, embed="spec_spat", sig_seed=8, sd_seed=9)
+    run_downstream_case("downstream_spat_nt64_b2", nb=2, nt=64, embed="spat", sig_seed=10, sd_seed=9)

@@ -284,6 +284,21 @@ def pretrain_forward(x, sd, pidx, cidx, training=True, dropout_p=0.0, taps=None)
     return loss, diff, vis
 
 
+def downstream_forward(x, sd, embed_use="spec_spat", training=True, dropout_p=0.0):
+    """model.py:667-719 (pretrain=False, head 'mlp', dlabel 1, token 'all'): both encoders on the un-masked input, concatenation (or
+    one of them), mean over time, LayerNorm + Linear.  x (nb, 2, nf, nt, 2) -> (pred (nb, 1), pooled embedding (nb, dembed))."""
+    nb, nmic, nf, nt, _ = x.shape
+    bn = BNState(training)
+    drop = (lambda t: F.dropout(t, dropout_p, True)) if (training and dropout_p > 0) else (lambda t: t)
+    tokens = x.permute(0, 3, 2, 4, 1).reshape(nb, nt, -1)
+    e_spec = embed_encoder(tokens, sd, "spec_encoder", SPEC_LAYERS, NHEAD, bn, drop)
+    e_spat = embed_encoder(tokens, sd, "spat_encoder", SPAT_LAYERS, NHEAD, bn, drop)
+    e = {"spec_spat": torch.cat([e_spec, e_spat], dim=2), "spec": e_spec + 0.0, "spat": e_spat + 0.0}[embed_use]
+    pooled = e.mean(dim=1)
+    pred = _lin(_ln(pooled, sd, "mlp_head.0"), sd, "mlp_head.1")
+    return pred, pooled
+
+
 def masked_loss(pred, vec, pidx, cidx):
     """model.py:585-592,721-747.  pred/vec (nb, nt, nf, 2, nmic).
     loss = mean over (item, masked frame, bin, re/im) of (pred - target)^2 on the masked channel,
@@ -312,7 +327,7 @@ def positional_table(d_model, max_len=10000):
     return pe.unsqueeze(0)
 
 
-def state_dict_spec(nf=256):
+def state_dict_spec(nf=256, pretrain=True, dembed_ds=768):
     """[(key, shape, kind)] for the 214 state_dict entries of SARSSL(pretrain=True).
     kind: 'w' weight matrix / filter, 'b' bias, 'g' norm gain, 'rm' running mean, 'rv' running var,
     'n' num_batches_tracked, 'pe' positional table, 'uv' u/v bias."""
@@ -359,17 +374,21 @@ def state_dict_spec(nf=256):
         stem(enc + ".patch_embed", D)
         for l in range(nl):
             block(f"{enc}.embed.layers.{l}", D, NHEAD)
-    out.extend([("decoder.proj.0.weight", (3 * 4 * nf, 768), "w"), ("decoder.proj.0.bias", (3 * 4 * nf,), "b"),
-                ("decoder.proj.2.weight", (4 * nf, 3 * 4 * nf), "w"), ("decoder.proj.2.bias", (4 * nf,), "b")])
+    if pretrain:
+        out.extend([("decoder.proj.0.weight", (3 * 4 * nf, 768), "w"), ("decoder.proj.0.bias", (3 * 4 * nf,), "b"),
+                    ("decoder.proj.2.weight", (4 * nf, 3 * 4 * nf), "w"), ("decoder.proj.2.bias", (4 * nf,), "b")])
+    else:       # downstream head (model.py:495-500)
+        out.extend([("mlp_head.0.weight", (dembed_ds,), "g"), ("mlp_head.0.bias", (dembed_ds,), "b"),
+                    ("mlp_head.1.weight", (1, dembed_ds), "w"), ("mlp_head.1.bias", (1,), "b")])
     return out
 
 
-def synthetic_state_dict(seed=7, nf=256):
+def synthetic_state_dict(seed=7, nf=256, pretrain=True, dembed_ds=768):
     """Seeded, non-degenerate weights (non-zero biases, non-unit gains) for parity tests.  Generated
     key by key from one torch.Generator so reference, oracle and CUDA path can all be loaded with it."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for key, shape, kind in state_dict_spec(nf):
+    for key, shape, kind in state_dict_spec(nf, pretrain, dembed_ds):
         if kind == "w":
             fan_in = 1
             for s in shape[1:]:

@@ -201,6 +201,23 @@ __global__ void attn_unshift_kernel(const T* __restrict__ dscore, T* __restrict_
     }
 }
 
+// pooled[b][d] = mean_t x[b][t][d] (fp32 out);  dx[b][t][d] = dpooled[b][d] / T        (torch.mean(embed, dim=1), model.py:705)
+template <typename T>
+__global__ void __launch_bounds__(256) mean_pool_fwd_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int Tn, int D) {
+    const int b = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    float s = 0.f;
+    for (int t = 0; t < Tn; ++t) s += to_f32(x[((long long)b * Tn + t) * ldx + d]);
+    pooled[(long long)b * D + d] = s / Tn;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) mean_pool_bwd_kernel(const float* __restrict__ dpooled, T* __restrict__ dx, long long ldx, int Tn, int D) {
+    const int b = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    const T v = from_f32<T>(dpooled[(long long)b * D + d] / Tn);
+    for (int t = blockIdx.z; t < Tn; t += gridDim.z) dx[((long long)b * Tn + t) * ldx + d] = v;
+}
+
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -310,6 +327,21 @@ extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void
                                                                                                 rows, T_, scale, drop_p, seed)));
     SARSSL_LAUNCH_CHECK();
     DISPATCH_T(dtype, (attn_unshift_kernel<T><<<ew_grid(rows * T_), 256, 0, stream>>>(static_cast<const T*>(dattn_inout), static_cast<T*>(dpos), B, H, T_)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_mean_pool_fwd(const void* x, long long ldx, float* pooled, int B, int T_, int D, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(x && pooled && B > 0 && T_ > 0 && D > 0 && B <= 65535, "mean_pool_fwd: bad arguments");
+    DISPATCH_T(dtype, (mean_pool_fwd_kernel<T><<<dim3((D + 255) / 256, B), 256, 0, stream>>>(static_cast<const T*>(x), ldx, pooled, T_, D)));
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_mean_pool_bwd(const float* dpooled, void* dx, long long ldx, int B, int T_, int D, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dpooled && dx && B > 0 && T_ > 0 && D > 0 && B <= 65535, "mean_pool_bwd: bad arguments");
+    const int gz = T_ < 16 ? T_ : 16;
+    DISPATCH_T(dtype, (mean_pool_bwd_kernel<T><<<dim3((D + 255) / 256, B, gz), 256, 0, stream>>>(dpooled, static_cast<T*>(dx), ldx, T_, D)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -13,6 +13,7 @@ namespace sarssl {
 // mode 0: plain [P][4] tensor of type T.  mode 1 / 2: fp32 patches (re0, re1, im0, im1) with the spectral / spatial mask:
 //   spectral: masked frame -> keep only the un-masked microphone; other frames -> keep only the masked microphone
 //   spatial : masked frame -> zeros; other frames -> both microphones
+// mode 3: fp32 patches, no masking (downstream fine-tuning branch)
 template <typename T>
 __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
     if (mode == 0) {
@@ -25,6 +26,7 @@ __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int m
         return *reinterpret_cast<const float4*>(q);
     }
     float4 x = *reinterpret_cast<const float4*>(static_cast<const float*>(in) + p * 4);
+    if (mode == 3) return x;                                    // un-masked fp32 patches (downstream branch, model.py:667-678)
     // (pixel counts stay far below 2^32: 32-bit divisions, a shift when W is a power of two)
     const unsigned up = (unsigned)p, uw = (unsigned)W;
     const unsigned row = ((uw & (uw - 1)) == 0) ? (up >> (31 - __clz((int)uw))) : up / uw;
@@ -319,7 +321,7 @@ using namespace sarssl;
 extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
                                   long long P, int W, int H, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0 && P < 0xFFFFFFFFLL, "stem_expand: bad arguments (P must be in (0, 2^32))");
-    SARSSL_CHECK_ARG(mode == 0 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
+    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
     if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
     else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
     else { set_last_error("stem_expand: bad dtype"); return SARSSL_ERR_ARG; }

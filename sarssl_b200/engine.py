@@ -37,6 +37,7 @@ class Engine:
     def set_dtype(self, dtype):
         self.dtype = dtype
         self.k = KernelSet(self.dev, dtype)
+        self.k32 = self.k if dtype == torch.float32 else KernelSet(self.dev, torch.float32)      # the tiny downstream head runs in fp32
         self._pe_cache = {}
 
     # ------------------------------------------------------------------------------------------------ weights
@@ -248,6 +249,69 @@ class Engine:
                        x2=x2, h3=h3, mean3=mean3, rstd3=rstd3, g=g, ga=ga, cv=cv, sbn=sbn, z=z, dc=dc, x3=x3, x4=x4, mean5=mean5, rstd5=rstd5)
             sv[pre] = rec
         return y
+
+    # ------------------------------------------------------------------------------------------------ downstream branch
+    def forward_downstream(self, patches, embed_use, training, want_grad):
+        """model.py:667-719 (pretrain=False, head 'mlp', dlabel 1): both encoders on the UN-masked input, concatenate, mean over time,
+        LayerNorm + Linear(dembed, 1).  Returns (pred (B, 1) fp32, pooled (B, dembed) fp32, saved)."""
+        k, k32, st = self.k, self.k32, self.store
+        B, T, F = patches.shape[:3]
+        M = B * T
+        self.step_seed += 1
+        p_drop = self.dropout_p if training else 0.0
+        self._prepare_weights(F)
+        sv = {"B": B, "T": T, "F": F, "seed": self.step_seed, "patches": patches, "flag": None, "ch": None, "embed_use": embed_use} if want_grad else None
+        Dc = SPEC_D + SPAT_D
+        cat = k.empty(M, Dc)
+        site = [0]
+        for enc, D, nl, _, col in ENCODERS:                # (the reference runs both encoders whatever `downstream_embed` says, model.py:677-678)
+            e = self._stem_fwd(enc, D, 3, patches, None, None, B, T, F, training, sv)
+            for l in range(nl):
+                last = l == nl - 1
+                e = self._block_fwd(f"{enc}.embed.layers.{l}", D, e, B, T, training, p_drop, site, sv, out=(cat, col, Dc) if last else None)
+        col, Dd = {"spec_spat": (0, Dc), "spec": (0, SPEC_D), "spat": (SPEC_D, SPAT_D)}[embed_use]
+        pooled = torch.empty(B, Dd, dtype=torch.float32, device=self.dev)
+        k.mean_pool_fwd(cat, Dc, pooled, B, T, Dd, x_off=col)
+        hn, mean, rstd = torch.empty_like(pooled), torch.empty(B, dtype=torch.float32, device=self.dev), torch.empty(B, dtype=torch.float32, device=self.dev)
+        k32.layernorm_fwd(pooled, Dd, st.p("mlp_head.0.weight"), st.p("mlp_head.0.bias"), hn, Dd, mean, rstd, B, Dd)
+        pred = torch.empty(B, 1, dtype=torch.float32, device=self.dev)
+        k32.use_tc = False
+        k32.linear(hn, st.p("mlp_head.1.weight"), pred, B, 1, Dd, bias=st.p("mlp_head.1.bias"))
+        if want_grad:
+            sv.update(pooled=pooled, hn=hn, hmean=mean, hrstd=rstd, col=col, Dd=Dd)
+        return pred, pooled, sv
+
+    def backward_downstream(self, sv, dpred, on_ready=None):
+        """dpred (B, 1) fp32 = d loss / d pred."""
+        k, k32, st = self.k, self.k32, self.store
+        B, T, F, col, Dd = sv["B"], sv["T"], sv["F"], sv["col"], sv["Dd"]
+        M, Dc = B * T, SPEC_D + SPAT_D
+        k32.use_tc = False
+        k32.linear_wgrad(dpred, sv["hn"], st.g("mlp_head.1.weight"), B, 1, Dd)
+        # bias gradient = sum_b dpred[b]: a 1 x 1 GEMM over K = B against a stride-0 "ones" operand
+        k32.gemm(dpred, torch.ones(1, 1, device=self.dev), st.g("mlp_head.1.bias").view(1, 1), 1, 1, B, (1, 1), (1, 0), 1, accumulate=True)
+        dhn = torch.empty(B, Dd, dtype=torch.float32, device=self.dev)
+        k32.linear_dgrad(dpred, st.p("mlp_head.1.weight"), dhn, B, 1, Dd)
+        dpool = torch.empty_like(dhn)
+        k32.layernorm_bwd(dhn, Dd, sv["pooled"], Dd, sv["hmean"], sv["hrstd"], st.p("mlp_head.0.weight"), None, dpool, st.g("mlp_head.0.weight"),
+                          st.g("mlp_head.0.bias"), B, Dd)
+        dcat = k.empty(M, Dc)
+        k.mean_pool_bwd(dpool, dcat, Dc, B, T, Dd, dx_off=col)
+        ready = on_ready if on_ready is not None else (lambda name: None)
+        ready("decoder")
+        for enc, D, nl, mode, ecol in ENCODERS:
+            used = ecol >= col and ecol < col + Dd             # encoders outside the pooled slice get no gradient (model.py:693-700)
+            if used:
+                d = None
+                for l in reversed(range(nl)):
+                    last = l == nl - 1
+                    d = self._block_bwd(f"{enc}.embed.layers.{l}", D, sv, B, T, dout=(dcat, ecol, Dc) if last else (d, 0, D))
+                    if enc == "spat_encoder" and l == 1:
+                        ready("spat_blocks_1_2")
+                self._stem_bwd(enc, D, 3, sv, d, B, T, F)
+            elif enc == "spat_encoder":
+                ready("spat_blocks_1_2")
+            ready("spec_encoder" if enc == "spec_encoder" else "spat_stem_block_0")
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self, sv, gscale=None, on_ready=None):

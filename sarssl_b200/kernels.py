@@ -151,6 +151,12 @@ class KernelSet:
         self._ok(self.L.sarssl_dwconv_wgrad(ptr(a), ptr(dc), ptr(dw), B, T, D, K, self.dt, ptr(self.ws), self.ws.numel(), self.stream), "dwconv_wgrad")
         self.launches += 1
 
+    def mean_pool_fwd(self, x, ldx, pooled, B, T, D, x_off=0):
+        self._ok(self.L.sarssl_mean_pool_fwd(_addr(x, x_off), ldx, ptr(pooled), B, T, D, _lib.dtype_code(x), self.stream), "mean_pool_fwd")
+
+    def mean_pool_bwd(self, dpooled, dx, ldx, B, T, D, dx_off=0):
+        self._ok(self.L.sarssl_mean_pool_bwd(ptr(dpooled), _addr(dx, dx_off), ldx, B, T, D, _lib.dtype_code(dx), self.stream), "mean_pool_bwd")
+
     def cast(self, src, dst, n):
         self._ok(self.L.sarssl_cast(ptr(src), _lib.dtype_code(src), ptr(dst), _lib.dtype_code(dst), n, self.stream), "cast")
 

@@ -113,8 +113,70 @@ class STFTLearner(Learner):
             patches = ops.stft_frontend(sig, eps=eps, win_len=self.win_len, hop=int(self.win_len * self.win_shift_ratio), nfft=self.nfft)
             data += [patches.permute(0, 4, 2, 1, 3)]
         if gt_batch is not None:
-            raise SarsslError("data_preprocess(gt_batch=...) belongs to the downstream path (SURVEY.md 8(f) row 1), not built yet")
+            gt = gt_batch[self.task].to(self.device, non_blocking=True)
+            data += [self.get_tar_batch(gt_batch=gt)]
         return data
+
+    # ---- downstream fine-tuning surface
+    def get_tar_batch(self, gt_batch):
+        """learner.py:620-631: (nbatch,) labels -> (nbatch, 1) regression targets (TDOA in samples at 16 kHz)."""
+        if self.task == "TDOA":
+            return gt_batch[:, None] * 16000
+        if self.task in ("DRR", "C50", "T60", "ABS"):
+            return gt_batch[:, None]
+        raise SarsslError(f"Task mode unrecognized: {self.task}")
+
+    def loss(self, pred_batch, gt_batch):
+        """learner.py:633-642: MSE between the (nbatch, 1) prediction and target."""
+        return torch.nn.functional.mse_loss(pred_batch.contiguous(), gt_batch.contiguous().detach().float())
+
+    def evaluate(self, pred_batch, gt_batch):
+        """learner.py:644-653: mean absolute error."""
+        return torch.mean(torch.abs(pred_batch.contiguous().detach() - gt_batch.contiguous().detach()))
+
+    def train_epoch(self, dataset, lr=0.0001, epoch=None, return_metric=False):
+        """learner.py:170-222: one fine-tuning epoch; dataset yields (mic_sig_batch, {task: labels})."""
+        from .optim import FusedAdam
+        self.model.train()
+        optimizer = FusedAdam(self.model, lr=lr)
+        optimizer.zero_grad()
+        sync = getattr(self, "grad_sync", None)
+        losses, metrics = [], []
+        for mic_sig_batch, gt_batch in dataset:
+            in_batch, tar_batch = self.data_preprocess(mic_sig_batch, gt_batch)
+            pred_batch, embed_batch = self.model(in_batch)
+            loss_batch = self.loss(pred_batch=pred_batch, gt_batch=tar_batch)
+            loss_batch.backward()
+            scale = sync.all_reduce() if sync is not None else 1.0
+            optimizer.step(lr, grad_scale=scale, zero_grad=True)
+            losses.append(loss_batch.detach())
+            if return_metric:
+                metrics.append(self.evaluate(pred_batch=pred_batch, gt_batch=tar_batch))
+        loss = float(torch.stack(losses).mean()) if losses else 0.0
+        if return_metric:
+            return loss, (torch.stack(metrics).mean() if metrics else torch.zeros(()))
+        return loss
+
+    def test_epoch(self, dataset, return_metric=False, return_vis=False):
+        """learner.py:224-269."""
+        self.model.eval()
+        losses, metrics, embed, gt = [], [], [], []
+        with torch.no_grad():
+            for mic_sig_batch, gt_batch in dataset:
+                in_batch, tar_batch = self.data_preprocess(mic_sig_batch, gt_batch)
+                pred_batch, embed_batch = self.model(in_batch)
+                losses.append(self.loss(pred_batch=pred_batch, gt_batch=tar_batch))
+                if return_metric:
+                    metrics.append(self.evaluate(pred_batch=pred_batch, gt_batch=tar_batch))
+                if return_vis:
+                    embed.append(embed_batch)
+                    gt.append(tar_batch)
+        out = [float(torch.stack(losses).mean()) if losses else 0.0]
+        if return_metric:
+            out.append(torch.stack(metrics).mean())
+        if return_vis:
+            out.append({"embed": torch.cat(embed, dim=0), "label": torch.cat(gt, dim=0)})
+        return out[0] if len(out) == 1 else tuple(out)
 
     def pretrain_evaluate(self, pred_batch, gt_batch, mask_batch):
         """learner.py:574-618: reconstruct the waveforms of prediction and target with the iSTFT (zero DC

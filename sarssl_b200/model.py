@@ -69,6 +69,27 @@ class _PretrainFn(torch.autograd.Function):
         return None, None, None, None, None, None
 
 
+class _DownstreamFn(torch.autograd.Function):
+    """One autograd node for the downstream branch: (pred, pooled embedding); the loss is formed outside (Learner.loss)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, patches, want):
+        pred, pooled, saved = model._engine().forward_downstream(patches, model.embed_use4ds, training=model.training, want_grad=want)
+        ctx.model, ctx.saved = model, saved
+        ctx.mark_non_differentiable(pooled)
+        return pred, pooled
+
+    @staticmethod
+    def backward(ctx, g_pred, g_pooled):
+        if ctx.saved is None:
+            raise _lib.SarsslError("backward() through a forward that ran without gradient tracking (eval() or no_grad())")
+        ctx.model.store.reattach_grads()
+        sync = getattr(ctx.model, "grad_sync", None)
+        ctx.model.engine.backward_downstream(ctx.saved, g_pred.float().contiguous(), on_ready=sync.bucket_ready if sync is not None else None)
+        ctx.saved = None
+        return None, None, None, None
+
+
 class VisDict(dict):
     """data_vis of model.py:595-599 ('mask', 'pred', 'tar').  'pred' / 'tar' are zero-copy views; the dense 'mask' is only
     materialised when somebody reads it (the reference folds all three every step and uses them once per epoch)."""
@@ -96,9 +117,12 @@ class SARSSL(nn.Module):
                  pretrain_frozen_encoder=False):
         super().__init__()
         nf, nt, nreim, nmic = sig_shape
-        if not pretrain or pretrain_frozen_encoder or use_cls:
-            raise _lib.SarsslError("sarssl_b200.SARSSL implements the pre-training path (pretrain=True, use_cls=False); the downstream branch "
-                                   "(model.py:667-719) is a 'next' row of SURVEY.md 8(f)")
+        if pretrain_frozen_encoder or use_cls:
+            raise _lib.SarsslError("sarssl_b200.SARSSL implements pretrain=True and the downstream branch pretrain=False; use_cls / "
+                                   "pretrain_frozen_encoder (model.py:603-666) are not built")
+        if not pretrain and (downstream_head != "mlp" or downstream_dlabel != 1 or downstream_token != "all" or
+                             downstream_embed not in ("spec_spat", "spec", "spat")):
+            raise _lib.SarsslError("downstream branch: only head 'mlp', dlabel 1, token 'all', embed in {spec_spat, spec, spat} (the shipped defaults)")
         if tuple(patch_shape) != (nf, 1) or patch_mode != "T" or nreim != 2 or nmic != 2:
             raise _lib.SarsslError("only frame patches (patch_shape == (nf, 1), patch_mode 'T') of 2-microphone re/im spectrograms are on the hot path")
         npatch = nt
@@ -107,7 +131,9 @@ class SARSSL(nn.Module):
         self.pretrain, self.pretrain_frozen_encoder, self.use_cls = pretrain, pretrain_frozen_encoder, use_cls
         self.sig_shape, self.nmasked_patch, self.in_ver = tuple(sig_shape), nmasked_patch, "separate"
         self.device = torch.device(device if str(device) != "cpu" else ("cuda" if torch.cuda.is_available() else "cpu"))
-        self.store = ParamStore(self, nf=nf, device=self.device)
+        self.embed_use4ds = downstream_embed
+        dembed_ds = {"spec_spat": 768, "spec": 512, "spat": 256}.get(downstream_embed, 768)
+        self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds)
         # the rest are plain attributes (not sub-modules) so that state_dict() holds exactly the reference's 214 entries
         object.__setattr__(self, "patch_split", PatchSplit(patch_shape=patch_shape, f_first=False))
         object.__setattr__(self, "patch_recover", PatchRecover(output_shape=(nf, nt), patch_shape=patch_shape, f_first=False))
@@ -150,12 +176,16 @@ class SARSSL(nn.Module):
 
     # ---- forward
     def forward(self, x):
-        """x (nb, 2, nf, nt, 2) -> (loss, diff, {'mask': (nb,nf,nt,2), 'pred': (nb,nf,nt,2,2), 'tar': (nb,nf,nt,2,2)})   model.py:519-601"""
+        """pretrain=True : x (nb, 2, nf, nt, 2) -> (loss, diff, {'mask': (nb,nf,nt,2), 'pred': (nb,nf,nt,2,2), 'tar': (nb,nf,nt,2,2)})   model.py:519-601
+        pretrain=False: x -> (pred (nb, 1), time-mean embedding (nb, dembed))                                                       model.py:667-719"""
         self._engine()
         patches = as_patch_layout(x)
         nb, nt, nf = patches.shape[:3]
         if (nf, nt) != tuple(self.sig_shape[:2]):
             raise _lib.SarsslError(f"input is {nf} bins x {nt} frames but the model was built for {self.sig_shape[:2]}")
+        if not self.pretrain:
+            want = torch.is_grad_enabled() and self.training
+            return _DownstreamFn.apply(self._anchor, self, patches, want)
         pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state, dp=self.dp)
         want = torch.is_grad_enabled() and self.training
         loss, diff = _PretrainFn.apply(self._anchor, self, patches, flag, cidx, want)

@@ -15,7 +15,7 @@ import torch.nn as nn
 SPEC_D, SPAT_D, SPEC_LAYERS, SPAT_LAYERS, NHEAD, CNN_CH, DW_K = 512, 256, 1, 3, 4, 64, 31
 
 
-def state_dict_layout(nf=256):
+def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D):
     """[(key, shape, kind)] in the reference's state_dict order.  kind: conv / lin_x (xavier Linear wrapper,
     conformer/modules.py:36-49) / lin_k (default nn.Linear) / bias0 / bias_k / gain / beta / rm / rv / nbt / pe / uv."""
     out = []
@@ -60,9 +60,13 @@ def state_dict_layout(nf=256):
         stem(enc + ".patch_embed", D)
         for l in range(nl):
             block(f"{enc}.embed.layers.{l}", D)
-    dff = 3 * 4 * nf
-    out.extend([("decoder.proj.0.weight", (dff, SPEC_D + SPAT_D), "lin_k"), ("decoder.proj.0.bias", (dff,), "bias_k"),
-                ("decoder.proj.2.weight", (4 * nf, dff), "lin_k"), ("decoder.proj.2.bias", (4 * nf,), "bias_k")])
+    if pretrain:
+        dff = 3 * 4 * nf
+        out.extend([("decoder.proj.0.weight", (dff, SPEC_D + SPAT_D), "lin_k"), ("decoder.proj.0.bias", (dff,), "bias_k"),
+                    ("decoder.proj.2.weight", (4 * nf, dff), "lin_k"), ("decoder.proj.2.bias", (4 * nf,), "bias_k")])
+    else:        # downstream head: nn.Sequential(LayerNorm(dembed_ds), Linear(dembed_ds, 1))   model.py:495-500
+        out.extend([("mlp_head.0.weight", (dembed_ds,), "gain"), ("mlp_head.0.bias", (dembed_ds,), "beta"),
+                    ("mlp_head.1.weight", (1, dembed_ds), "lin_k"), ("mlp_head.1.bias", (1,), "bias_k")])
     return out
 
 
@@ -112,8 +116,8 @@ def _arena_order(layout):
 class ParamStore:
     """Builds the tree under `root`, owns the arenas, and resolves keys to tensors for the engine."""
 
-    def __init__(self, root, nf=256, device="cpu", seed_generator=None):
-        self.layout = state_dict_layout(nf)
+    def __init__(self, root, nf=256, device="cpu", seed_generator=None, pretrain=True, dembed_ds=SPEC_D + SPAT_D):
+        self.layout = state_dict_layout(nf, pretrain, dembed_ds)
         self.shapes = {k: tuple(s) for k, s, _ in self.layout}
         self.kinds = {k: kind for k, _, kind in self.layout}
         self.order = _arena_order(self.layout)

@@ -135,3 +135,30 @@ def test_eval_mode_matches_reference_fixture():
         le, de, _ = O.pretrain_forward(x, sd, pidx, cidx, training=False)
     assert abs(float(le) - float(g["eval_loss"])) <= 1e-5 * float(g["eval_loss"])
     assert abs(float(de) - float(g["eval_diff"])) <= 1e-5 * float(g["eval_diff"])
+
+
+@pytest.mark.parametrize("name,embed", [("downstream_nt16_b4", "spec_spat"), ("downstream_spat_nt64_b2", "spat")])
+def test_downstream_branch_matches_reference_fixture(name, embed):
+    """Downstream fine-tuning branch: oracle vs the reference's SARSSL(pretrain=False) + TDOA MSE step."""
+    g = load(name)
+    nb, nt = int(g["nb"]), int(g["nt"])
+    dds = {"spec_spat": 768, "spec": 512, "spat": 256}[embed]
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"]))
+    sd = O.synthetic_state_dict(int(g["sd_seed"]), pretrain=False, dembed_ds=dds)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k and not k.endswith(".pe"):
+            v.requires_grad_(True)
+    pred, emb = O.downstream_forward(O.preprocess(sig), sd, embed, training=True)
+    tar = torch.from_numpy(g["tar"])
+    assert np.allclose(tar.numpy(), g["labels"][:, None] * 16000)
+    loss = torch.nn.functional.mse_loss(pred, tar)
+    loss.backward()
+    assert np.allclose(pred.detach().numpy(), g["pred"], rtol=1e-4, atol=1e-5) and np.allclose(emb.detach().numpy(), g["embed"], rtol=1e-4, atol=1e-5)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    for k in g.files:
+        if k.startswith("grad_norm/"):
+            key = k[len("grad_norm/"):]
+            gr = sd[key].grad
+            mine = float(gr.norm()) if gr is not None else 0.0
+            assert abs(mine - float(g[k])) <= 1e-3 * float(g[k]) + 1e-6 * gmax, key
