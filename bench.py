@@ -289,6 +289,124 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------
+# downstream fine-tuning step (BASELINE.json configs[3]): --workload finetune
+# --------------------------------------------------------------------------------------------------------------
+FT_NT = 64                                  # TDOA fine-tuning uses 1.04 s clips -> 64 frames (run_downstream.py:71-84)
+FT_NSAMPLE = (FT_NT + 1) * 256
+
+
+def cpu_finetune_clips_per_s(nb, steps, warmup, threads):
+    import torch
+    from oracle import sarssl_oracle as O
+    torch.set_num_threads(threads)
+    sig = O.synthetic_waveforms(nb, FT_NSAMPLE, 2, seed=1234)
+    tar = torch.linspace(-1.0, 1.0, nb)[:, None]
+    sd = O.synthetic_state_dict(7, pretrain=False, dembed_ds=768)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    m = [torch.zeros_like(sd[k]) for k in names]
+    v = [torch.zeros_like(sd[k]) for k in names]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        pred, _ = O.downstream_forward(O.preprocess(sig), sd, "spec_spat", training=True, dropout_p=0.1)
+        loss = torch.nn.functional.mse_loss(pred, tar)
+        loss.backward()
+        with torch.no_grad():
+            O.adam_step([sd[k] for k in names], [sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k]) for k in names], m, v, i + 1, 1e-5)
+        for k in names:
+            sd[k].grad = None
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return nb * len(times) / sum(times)
+
+
+def run_finetune(args):
+    import torch
+    import torch.distributed as dist
+    from sarssl_b200.learner import STFTLearner
+    from sarssl_b200.model import SARSSL
+    from sarssl_b200.optim import FusedAdam
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cores = os.cpu_count() or 1
+            v = cpu_finetune_clips_per_s(8, max(1, min(args.steps, 4)), 1, cores)
+            print(json.dumps({"impl": "reference", "metric": "finetune_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "higher_is_better": True,
+                              "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": "8 clips/step, oracle port, torch CPU fp32"},
+                              "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nb = args.batch if args.batch != 256 else 64                      # configs[3]: batch 512 over 8 GPUs
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model = SARSSL(sig_shape=(NF, FT_NT, 2, 2), pretrain=False, device=dev)
+    model.to(dev)
+    model.set_compute_dtype(dtype)
+    model.train()
+    L = STFTLearner(model, 512, 0.5, 512, 1, 16000, task="TDOA")
+    L.device = dev
+    if world > 1:
+        L.mul_gpu()
+    sync = getattr(L, "grad_sync", None)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    sig = 0.1 * torch.randn(nb, FT_NSAMPLE, 2, device=dev, generator=g)
+    labels = torch.linspace(-5e-5, 5e-5, nb, device=dev)
+    host_sig, host_lab = sig.cpu().pin_memory(), labels.cpu().pin_memory()
+    opt = FusedAdam(model, lr=1e-5)
+
+    def step():
+        x, tar = L.data_preprocess(sig, {"TDOA": labels})
+        pred, _ = model(x)
+        L.loss(pred_batch=pred, gt_batch=tar).backward()
+        opt.step(1e-5, grad_scale=sync.all_reduce() if sync is not None else 1.0)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    ms = timed(step, args.steps)
+    e2e_ms = timed(lambda: L.train_epoch([(host_sig, {"TDOA": host_lab})] * args.steps, lr=1e-5), 1)
+    if rank == 0:
+        line = {"metric": "finetune_clips_per_s", "value": nb * world * args.steps / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"downstream fine-tune step (TDOA head, MSE, Adam), 2-mic, {FT_NSAMPLE} samples (1.04 s), batch {nb}/GPU (BASELINE.json configs[3])",
+                           "per_gpu_batch": nb, "nt": FT_NT, "parallelism": f"dp{world}"},
+                "e2e": {"value": nb * world * args.steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": int(model.engine.k.launches)}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            line["cpu_baseline"] = {"value": cpu_finetune_clips_per_s(8, 2, 1, cores), "unit": "clips/s", "cores": cores, "kind": "port",
+                                    "sample": "8 clips/step x 2 steps, oracle port (torch CPU fp32, dropout on)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -299,8 +417,11 @@ def main():
     ap.add_argument("--frontend-batch", type=int, default=1024)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"], help="pretrain = headline (configs[2]); finetune = configs[3]")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "finetune":
+        run_finetune(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)
