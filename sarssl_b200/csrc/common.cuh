@@ -39,6 +39,10 @@ void set_last_error(const char* fmt, ...);
     } while (0)
 
 int sm_count();                 // cached multiprocessor count of the current device
+// CTAs of `kernel` (threads per CTA, dynamic smem) that are resident on the whole device at once; cached per kernel.  Grid-stride /
+// persistent kernels size their grid with it: a grid slightly above the resident capacity costs a whole extra, mostly idle, wave.
+int resident_ctas_impl(const void* kernel, int threads, size_t smem);
+template <typename K> inline int resident_ctas(K kernel, int threads, size_t smem = 0) { return resident_ctas_impl(reinterpret_cast<const void*>(kernel), threads, smem); }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

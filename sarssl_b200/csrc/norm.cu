@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ d
 }
 
 // number of CTAs for the channel-last BN kernels: every thread must keep a fixed channel set, i.e. (grid * 2048) % C == 0
-static int bn_grid(long long total, int C) {
+static int bn_grid(long long total, int C, int cap_ctas) {
     long long g = (total / 8 + 255) / 256;
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = cap_ctas;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     if (C > 8 && (2048 % C) != 0) {              // C = 512, 768, ...: grid must be a multiple of C / gcd(C, 2048)
@@ -397,7 +397,11 @@ extern "C" int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* 
     SARSSL_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
     SARSSL_CHECK_ARG(cols <= 256 * kLnChunks && cols % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0, "layernorm_bwd: cols=%d must be a multiple of 8, <= %d", cols,
                      256 * kLnChunks);
-    const int grid = capped_grid(rows, 8 * 4, 4);
+    int grid = capped_grid(rows, 8 * 4, 64);
+    {
+        const int cap = dtype == SARSSL_F32 ? resident_ctas(ln_bwd_kernel<float>, 256) : resident_ctas(ln_bwd_kernel<__nv_bfloat16>, 256);
+        if (grid > cap) grid = cap;
+    }
     if (workspace_bytes < (size_t)grid * 2 * cols * sizeof(float)) { set_last_error("layernorm_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     DISPATCH_T(dtype, (ln_bwd_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(dy), lddy, static_cast<const T*>(x), ldx, mean, rstd, gamma,
@@ -413,7 +417,12 @@ extern "C" int sarssl_colsum(const void* x, long long ldx, float* out, int rows,
     SARSSL_CHECK_ARG(x && out && workspace && rows > 0 && cols > 0, "colsum: bad arguments");
     SARSSL_CHECK_ARG(cols % 8 == 0 && ldx % 8 == 0, "colsum: cols and ldx must be multiples of 8");
     const int gx = (cols + 255) / 256;
-    int grid = capped_grid(rows, 64, 4) / gx;
+    int grid = capped_grid(rows, 64, 64);
+    {
+        const int cap = dtype == SARSSL_F32 ? resident_ctas(colsum_kernel<float>, 256) : resident_ctas(colsum_kernel<__nv_bfloat16>, 256);
+        if (grid > cap) grid = cap;
+    }
+    grid /= gx;
     if (grid < 1) grid = 1;
     if (workspace_bytes < (size_t)grid * cols * sizeof(float)) { set_last_error("colsum: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
@@ -431,7 +440,7 @@ extern "C" int sarssl_batchnorm_stats(const void* y, long long rows, int C, cons
     SARSSL_CHECK_ARG(y && gamma && beta && running_mean && running_var && stats && workspace && rows > 0 && C > 0, "batchnorm_stats: bad arguments");
     SARSSL_CHECK_ARG(C == 4 || C % 8 == 0, "batchnorm: C=%d must be 4 or a multiple of 8", C);
     SARSSL_CHECK_ARG((rows * C) % 8 == 0, "batchnorm: rows*C must be a multiple of 8");
-    const int grid = bn_grid(rows * C, C);
+    const int grid = bn_grid(rows * C, C, dtype == SARSSL_F32 ? resident_ctas(bn_reduce_kernel<float, 0>, 256) : resident_ctas(bn_reduce_kernel<__nv_bfloat16, 0>, 256));
     if (workspace_bytes < (size_t)grid * 2 * C * sizeof(float)) { set_last_error("batchnorm_stats: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     if (training) {
@@ -473,7 +482,7 @@ extern "C" int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const flo
                                         long long rows, int C, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(dz && y && stats && dy && dgamma && dbeta && workspace, "batchnorm_act_bwd: null pointer");
     SARSSL_CHECK_ARG((C == 4 || C % 8 == 0) && (rows * C) % 8 == 0, "batchnorm_act_bwd: C=%d must be 4 or a multiple of 8", C);
-    const int grid = bn_grid(rows * C, C);
+    const int grid = bn_grid(rows * C, C, dtype == SARSSL_F32 ? resident_ctas(bn_reduce_kernel<float, 1>, 256) : resident_ctas(bn_reduce_kernel<__nv_bfloat16, 1>, 256));
     if (workspace_bytes < ((size_t)grid * 2 * C + 2 * C) * sizeof(float)) { set_last_error("batchnorm_act_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     float* sums = partials + (size_t)grid * 2 * C;

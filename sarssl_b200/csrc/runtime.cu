@@ -26,6 +26,19 @@ int sm_count() {
     return cached[dev];
 }
 
+int resident_ctas_impl(const void* kernel, int threads, size_t smem) {
+    struct Entry { const void* k; int threads; size_t smem; int n; };
+    static Entry cache[256];
+    static int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kernel && cache[i].threads == threads && cache[i].smem == smem) return cache[i].n;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int n = per_sm * sm_count();
+    if (used < 256) cache[used++] = {kernel, threads, smem, n};
+    return n;
+}
+
 }  // namespace sarssl
 
 extern "C" int sarssl_version(void) { return 100; }   // 0.1.0

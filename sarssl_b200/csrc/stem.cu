@@ -308,9 +308,10 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const T* __restrict_
         for (int j = 0; j < 4; ++j) dst[(size_t)(ty * 4 + i) * 576 + tap * 64 + tx * 4 + j] = acc[i][j];
 }
 
-static int pix_grid(long long P) {
+template <typename K>
+static int pix_grid(K kernel, long long P) {
     long long g = (P + 127) / 128;
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = resident_ctas(kernel, 256);           // exactly one resident wave
     return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
@@ -322,8 +323,8 @@ extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame
                                   long long P, int W, int H, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0 && P < 0xFFFFFFFFLL, "stem_expand: bad arguments (P must be in (0, 2^32))");
     SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
-    if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
-    else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
+    if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(pw_expand_kernel<float>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
+    else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(pw_expand_kernel<__nv_bfloat16>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
     else { set_last_error("stem_expand: bad dtype"); return SARSSL_ERR_ARG; }
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
@@ -332,8 +333,8 @@ extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame
 extern "C" int sarssl_stem_reduce(const void* in, const float* in_scale, const float* in_shift, const float* weight4x64, void* out, long long P,
                                   int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight4x64 && out && P > 0, "stem_reduce: bad arguments");
-    if (dtype == SARSSL_F32) pw_reduce_kernel<float><<<pix_grid(P), 256, 0, stream>>>((const float*)in, in_scale, in_shift, weight4x64, (float*)out, P);
-    else if (dtype == SARSSL_BF16) pw_reduce_kernel<__nv_bfloat16><<<pix_grid(P), 256, 0, stream>>>((const __nv_bfloat16*)in, in_scale, in_shift, weight4x64, (__nv_bfloat16*)out, P);
+    if (dtype == SARSSL_F32) pw_reduce_kernel<float><<<pix_grid(pw_reduce_kernel<float>, P), 256, 0, stream>>>((const float*)in, in_scale, in_shift, weight4x64, (float*)out, P);
+    else if (dtype == SARSSL_BF16) pw_reduce_kernel<__nv_bfloat16><<<pix_grid(pw_reduce_kernel<__nv_bfloat16>, P), 256, 0, stream>>>((const __nv_bfloat16*)in, in_scale, in_shift, weight4x64, (__nv_bfloat16*)out, P);
     else { set_last_error("stem_reduce: bad dtype"); return SARSSL_ERR_ARG; }
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
@@ -350,7 +351,7 @@ extern "C" int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, c
                                     const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
                                     int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_pw_wgrad: bad arguments (P must be in (0, 2^32))");
-    const int grid = pix_grid(P);
+    const int grid = dtype == SARSSL_F32 ? pix_grid(pw_wgrad_kernel<float>, P) : pix_grid(pw_wgrad_kernel<__nv_bfloat16>, P);
     if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     if (dtype == SARSSL_F32) pw_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
