@@ -208,33 +208,52 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
                                                       long long total, int C) {
     __shared__ float sa[256][9], sb[256][9];      // per-thread partials, combined in a fixed order below (deterministic)
     const long long g0 = (long long)blockIdx.x * 256 + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * 256;
+    const long long gs = (long long)gridDim.x * 256, ng = total / 8;
     const int cbase = (C == 4) ? 0 : (int)((g0 * 8) % C);
-    float a[8], b[8], mu[8], rs[8], sc[8], shf[8];
+    // mode 1 accumulates sum(dv) and sum(dv * (y - mean)); rstd is applied once at the end (fewer live registers -> more loads in flight)
+    float a[8], b[8], mu[8], sc[8], shf[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         a[j] = 0.f; b[j] = 0.f;
         const int c = (C == 4) ? (j & 3) : cbase + j;
-        if (MODE == 1) { mu[j] = mean[c]; rs[j] = rstd[c]; sc[j] = scale[c]; shf[j] = shift[c]; }
+        if (MODE == 1) { mu[j] = mean[c]; sc[j] = scale[c]; shf[j] = shift[c]; }
     }
-    for (long long g = g0; g * 8 < total; g += gstride) {
-        float v[8];
-        Vec8<T>::load(y + g * 8, v);
+    auto accumulate = [&](const float (&v)[8], const float (&d)[8]) {
         if (MODE == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a[j] += v[j]; b[j] += v[j] * v[j]; }
         } else {
-            float d[8];
-            Vec8<T>::load(dz + g * 8, d);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float u = v[j] * sc[j] + shf[j];
                 float dv = d[j];
                 if (act == 1) dv = u > 0.f ? dv : 0.f;
                 else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); dv *= sg * (1.0f + u * (1.0f - sg)); }
-                a[j] += dv; b[j] += dv * (v[j] - mu[j]) * rs[j];
+                a[j] += dv; b[j] = fmaf(dv, v[j] - mu[j], b[j]);
             }
         }
+    };
+    constexpr int U = 4;                          // independent 16-byte loads in flight per thread and operand
+    long long g = g0;
+    for (; g + (U - 1) * gs < ng; g += U * gs) {
+        float v[U][8], d[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            Vec8<T>::load(y + (g + u * gs) * 8, v[u]);
+            if (MODE == 1) Vec8<T>::load(dz + (g + u * gs) * 8, d[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(v[u], d[u]);
+    }
+    for (; g < ng; g += gs) {
+        float v[8], d[8];
+        Vec8<T>::load(y + g * 8, v);
+        if (MODE == 1) Vec8<T>::load(dz + g * 8, d);
+        accumulate(v, d);
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] *= rstd[(C == 4) ? (j & 3) : cbase + j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sa[threadIdx.x][j] = a[j]; sb[threadIdx.x][j] = b[j]; }
@@ -299,46 +318,83 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     }
 }
 
-// z = act(y * scale + shift)
+// z = act(y * scale + shift).  Launched with bn_grid: every thread keeps one fixed group of 8 channels, so scale/shift live in registers.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                                        T* __restrict__ z, long long total, int C) {
-    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < total; g += (long long)gridDim.x * 256) {
-        const int cbase = (C == 4) ? 0 : (int)((g * 8) % C);
-        float v[8];
-        Vec8<T>::load(y + g * 8, v);
+    const long long g0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long gs = (long long)gridDim.x * 256, ng = total / 8;
+    const int cbase = (C == 4) ? 0 : (int)((g0 * 8) % C);
+    float sc[8], shf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = (C == 4) ? (j & 3) : cbase + j; sc[j] = scale[c]; shf[j] = shift[c]; }
+    auto apply = [&](float (&v)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = (C == 4) ? (j & 3) : cbase + j;
-            float u = v[j] * scale[c] + shift[c];
+            float u = v[j] * sc[j] + shf[j];
             if (act == 1) u = fmaxf(u, 0.f);
             else if (act == 2) u = __fdividef(u, 1.0f + __expf(-u));
             v[j] = u;
         }
+    };
+    constexpr int U = 4;
+    long long g = g0;
+    for (; g + (U - 1) * gs < ng; g += U * gs) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) Vec8<T>::load(y + (g + u * gs) * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { apply(v[u]); Vec8<T>::store(z + (g + u * gs) * 8, v[u]); }
+    }
+    for (; g < ng; g += gs) {
+        float v[8];
+        Vec8<T>::load(y + g * 8, v);
+        apply(v);
         Vec8<T>::store(z + g * 8, v);
     }
 }
 
-// dy = gamma * rstd * (dv - sum_dv/R - xhat * sum_dv_xhat/R),  dv = dz * act'(bn(y))
+// dy = gamma * rstd * (dv - sum_dv/R - xhat * sum_dv_xhat/R),  dv = dz * act'(bn(y)); per channel this is dy = scale*dv - c0 - c1*y with
+// c1 = scale * rstd * sum_dv_xhat / R and c0 = scale * sum_dv / R - c1 * mean (scale = gamma * rstd).  Same fixed-channel layout as above.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const float* __restrict__ sums, int act, T* __restrict__ dy, long long total, int C, float inv_rows) {
-    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < total; g += (long long)gridDim.x * 256) {
-        const int cbase = (C == 4) ? 0 : (int)((g * 8) % C);
-        float v[8], d[8];
-        Vec8<T>::load(y + g * 8, v);
-        Vec8<T>::load(dz + g * 8, d);
+    const long long g0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long gs = (long long)gridDim.x * 256, ng = total / 8;
+    const int cbase = (C == 4) ? 0 : (int)((g0 * 8) % C);
+    float sc[8], shf[8], c0[8], c1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = (C == 4) ? (j & 3) : cbase + j;
+        sc[j] = scale[c]; shf[j] = shift[c];
+        c1[j] = sc[j] * rstd[c] * sums[C + c] * inv_rows;
+        c0[j] = sc[j] * sums[c] * inv_rows - c1[j] * mean[c];
+    }
+    auto apply = [&](const float (&v)[8], float (&d)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = (C == 4) ? (j & 3) : cbase + j;
-            const float u = v[j] * scale[c] + shift[c];
+            const float u = v[j] * sc[j] + shf[j];
             float dv = d[j];
             if (act == 1) dv = u > 0.f ? dv : 0.f;
             else if (act == 2) { const float sg = 1.0f / (1.0f + __expf(-u)); dv *= sg * (1.0f + u * (1.0f - sg)); }
-            const float xh = (v[j] - mean[c]) * rstd[c];
-            d[j] = scale[c] * (dv - sums[c] * inv_rows - xh * sums[C + c] * inv_rows);
+            d[j] = fmaf(sc[j], dv, -fmaf(c1[j], v[j], c0[j]));
         }
+    };
+    constexpr int U = 4;
+    long long g = g0;
+    for (; g + (U - 1) * gs < ng; g += U * gs) {
+        float v[U][8], d[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { Vec8<T>::load(y + (g + u * gs) * 8, v[u]); Vec8<T>::load(dz + (g + u * gs) * 8, d[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { apply(v[u], d[u]); Vec8<T>::store(dy + (g + u * gs) * 8, d[u]); }
+    }
+    for (; g < ng; g += gs) {
+        float v[8], d[8];
+        Vec8<T>::load(y + g * 8, v);
+        Vec8<T>::load(dz + g * 8, d);
+        apply(v, d);
         Vec8<T>::store(dy + g * 8, d);
     }
 }
@@ -470,7 +526,7 @@ extern "C" int sarssl_batchnorm_act_fwd(const void* y, const float* stats, int a
     SARSSL_CHECK_ARG(y && stats && z && rows > 0 && C > 0, "batchnorm_act_fwd: bad arguments");
     SARSSL_CHECK_ARG((C == 4 || C % 8 == 0) && (rows * C) % 8 == 0, "batchnorm_act_fwd: C=%d must be 4 or a multiple of 8", C);
     const long long total = rows * C;
-    const int grid = capped_grid(total, 2048, 16);
+    const int grid = bn_grid(total, C, dtype == SARSSL_F32 ? resident_ctas(bn_act_fwd_kernel<float>, 256) : resident_ctas(bn_act_fwd_kernel<__nv_bfloat16>, 256));
     DISPATCH_T(dtype, (bn_act_fwd_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(y), stats + 2 * C, stats + 3 * C, act, static_cast<T*>(z),
                                                                      total, C)));
     SARSSL_LAUNCH_CHECK();
@@ -493,7 +549,7 @@ extern "C" int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const flo
     bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, grid, C, sums, dgamma, dbeta);
     SARSSL_LAUNCH_CHECK();
     const long long total = rows * C;
-    const int g2 = capped_grid(total, 2048, 16);
+    const int g2 = bn_grid(total, C, dtype == SARSSL_F32 ? resident_ctas(bn_act_bwd_kernel<float>, 256) : resident_ctas(bn_act_bwd_kernel<__nv_bfloat16>, 256));
     DISPATCH_T(dtype, (bn_act_bwd_kernel<T><<<g2, 256, 0, stream>>>(static_cast<const T*>(dz), static_cast<const T*>(y), mean, rstd, scale, shift, sums,
                                                                    act, static_cast<T*>(dy), total, C, 1.0f / (float)rows)));
     SARSSL_LAUNCH_CHECK();
