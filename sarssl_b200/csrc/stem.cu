@@ -175,6 +175,124 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
     }
 }
 
+// ---- bf16 version of the same sum on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate) -------------------------
+// D[o][n] = sum_p f(wide[p][o]) * B[p][n]: M = 64 wide channels (4 m-tiles), K = pixels, N = 8 = the 4 narrow channels twice:
+// columns 0..3 hold bf16(x), columns 4..7 the rounding residual bf16(x - bf16(x)), so fp32 patch inputs keep 16 mantissa bits.
+// Both operands are pixel-major in memory, i.e. K is the slow index: ldmatrix.trans delivers the fragments.  Every warp owns 16
+// pixels of a 128-pixel tile and a private cp.async ring (no block barrier in the main loop); the BatchNorm+ReLU of the wide
+// operand is applied to the A fragments in registers (fp32 math, rounded to bf16 exactly like the materialised activation).
+constexpr int kWgStages = 4;
+constexpr int kWgWarpStage = 16 * 128 + 16 * 16;                    // wide 16 px x 128 B (16-byte chunks XOR-swizzled by pixel) + narrow 16 px x 16 B
+constexpr int kWgSmem = 8 * kWgStages * kWgWarpStage;               // 73,728 B
+
+__device__ __forceinline__ uint32_t bn_relu_bf16x2(uint32_t r, float sc, float sh) {
+    const float lo = fmaxf(fmaf(__uint_as_float(r << 16), sc, sh), 0.f), hi = fmaxf(fmaf(__uint_as_float(r & 0xffff0000u), sc, sh), 0.f);
+    uint32_t o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
+    return o;
+}
+
+__global__ void __launch_bounds__(256) pw_wgrad_mma_kernel(const __nv_bfloat16* __restrict__ wide, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, const void* __restrict__ narrow, int mode,
+                                                         const uint8_t* __restrict__ flag, const int32_t* __restrict__ ch,
+                                                         float* __restrict__ partials, long long P, int W, int H) {
+    extern __shared__ __align__(128) uint8_t wg_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2;
+    uint8_t* ring = wg_smem + (size_t)warp * kWgStages * kWgWarpStage;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const bool tr = scale != nullptr;
+    float sc[4][2], sh[4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { sc[mt][h] = tr ? scale[16 * mt + g + 8 * h] : 1.f; sh[mt][h] = tr ? shift[16 * mt + g + 8 * h] : 0.f; }
+    float acc[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f; }
+    const long long ntiles = (P + 127) / 128;
+    const long long my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    // stage `it` (tile blockIdx.x + it * gridDim.x): cp.async the warp's 16 x 128 B of `wide`, return its narrow pixel (lanes 0..15) in registers
+    auto issue = [&](long long it, float4& nx) {
+        nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < my_tiles) {
+            const long long p0 = ((long long)blockIdx.x + it * gridDim.x) * 128 + warp * 16;
+            const uint32_t dst = ring_s + (uint32_t)(it % kWgStages) * kWgWarpStage;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int id = lane + 32 * j, px = id >> 3, chunk = id & 7;
+                const bool ok = p0 + px < P;
+                const __nv_bfloat16* src = wide + (ok ? (p0 + px) * 64 + chunk * 8 : 0);
+                const uint32_t d = dst + px * 128 + ((chunk ^ (px & 7)) << 4);
+                const int nbytes = ok ? 16 : 0;                                       // zero-fill beyond the last pixel
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+            }
+            if (lane < 16 && p0 + lane < P) nx = load_narrow<__nv_bfloat16>(narrow, p0 + lane, mode, flag, ch, W, H);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto put_narrow = [&](long long it, const float4& nx) {                            // [px][8] bf16: value, then rounding residual
+        if (lane < 16) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(nx.x, nx.y), h1 = __floats2bfloat162_rn(nx.z, nx.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(nx.x - f0.x, nx.y - f0.y), l1 = __floats2bfloat162_rn(nx.z - f1.x, nx.w - f1.y);
+            uint4 v;
+            v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
+            v.z = *reinterpret_cast<const uint32_t*>(&l0); v.w = *reinterpret_cast<const uint32_t*>(&l1);
+            *reinterpret_cast<uint4*>(ring + (size_t)(it % kWgStages) * kWgWarpStage + 16 * 128 + lane * 16) = v;
+        }
+    };
+
+    float4 nx;
+#pragma unroll 1
+    for (int s = 0; s < kWgStages - 1; ++s) { issue(s, nx); put_narrow(s, nx); }
+#pragma unroll 1
+    for (long long it = 0; it < my_tiles; ++it) {
+        issue(it + kWgStages - 1, nx);                                             // slot (it - 1) % stages: consumed last iteration
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWgStages - 1) : "memory");
+        __syncwarp();
+        const uint32_t st = ring_s + (uint32_t)(it % kWgStages) * kWgWarpStage;
+        uint32_t b0, b1;
+        {
+            const uint32_t addr = st + 16 * 128 + (lane & 15) * 16;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        }
+        const int mi = lane >> 3, r = lane & 7, px = (mi >> 1) * 8 + r;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            uint32_t a0, a1, a2, a3;
+            const uint32_t addr = st + px * 128 + (((2 * mt + (mi & 1)) ^ r) << 4);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+            if (tr) {
+                a0 = bn_relu_bf16x2(a0, sc[mt][0], sh[mt][0]); a2 = bn_relu_bf16x2(a2, sc[mt][0], sh[mt][0]);
+                a1 = bn_relu_bf16x2(a1, sc[mt][1], sh[mt][1]); a3 = bn_relu_bf16x2(a3, sc[mt][1], sh[mt][1]);
+            }
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(acc[mt][0]), "+f"(acc[mt][1]), "+f"(acc[mt][2]), "+f"(acc[mt][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+        __syncwarp();                                                              // every lane is done reading slot it % stages ...
+        put_narrow(it + kWgStages - 1, nx);                                        // ... and slot (it - 1) % stages, refilled here
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // D columns n = 2t, 2t+1 live in lane quad position t: add the residual columns (t + 2) to the value columns, then sum the 8 warps
+    float* red = reinterpret_cast<float*>(wg_smem);                                // [8 warps][64 o][4 c]
+    const int t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float v = acc[mt][q] + __shfl_down_sync(0xffffffffu, acc[mt][q], 2);
+            if (t < 2) red[(warp * 64 + 16 * mt + g + 8 * (q >> 1)) * 4 + 2 * t + (q & 1)] = v;
+        }
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w * 256 + threadIdx.x];
+    partials[(size_t)blockIdx.x * 256 + threadIdx.x] = sum;
+}
+
 __global__ void stem_reduce_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out, int accumulate) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= width) return;
@@ -351,11 +469,19 @@ extern "C" int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, c
                                     const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
                                     int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_pw_wgrad: bad arguments (P must be in (0, 2^32))");
-    const int grid = dtype == SARSSL_F32 ? pix_grid(pw_wgrad_kernel<float>, P) : pix_grid(pw_wgrad_kernel<__nv_bfloat16>, P);
+    int grid;
+    if (dtype == SARSSL_BF16) {
+        static bool attr_set = false;
+        if (!attr_set) { SARSSL_CUDA(cudaFuncSetAttribute(pw_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); attr_set = true; }
+        const long long need = (P + 127) / 128, cap = resident_ctas(pw_wgrad_mma_kernel, 256, kWgSmem);
+        grid = (int)(need < cap ? need : cap);
+    } else {
+        grid = pix_grid(pw_wgrad_kernel<float>, P);
+    }
     if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
     if (dtype == SARSSL_F32) pw_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
-    else if (dtype == SARSSL_BF16) pw_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
+    else if (dtype == SARSSL_BF16) pw_wgrad_mma_kernel<<<grid, 256, kWgSmem, stream>>>((const __nv_bfloat16*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
     else { set_last_error("stem_pw_wgrad: bad dtype"); return SARSSL_ERR_ARG; }
     SARSSL_LAUNCH_CHECK();
     stem_reduce_kernel<<<1, 256, 0, stream>>>(partials, grid, 256, dweight64x4, accumulate);

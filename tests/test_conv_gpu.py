@@ -75,3 +75,48 @@ def test_tc_conv3x3_wgrad_matches_simt(B, H, W):
     k.conv3x3_wgrad_tc(dy, z, out, B, H, W)
     torch.cuda.synchronize()
     assert rel(out, ref) < 1e-4, rel(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,mode", [(2, 16, 256, 0), (3, 5, 130, 0), (1, 3, 37, 0), (2, 16, 256, 1), (2, 16, 256, 2), (2, 7, 64, 3), (16, 64, 256, 1)])
+def test_stem_pointwise_wgrad_vs_torch(dtype, B, H, W, mode):
+    """dW[o][c] = sum_p f(wide[p][o]) * narrow[p][c] (the weight gradient of both 1x1 convs): every narrow-operand mode, with and without
+    the fused BatchNorm+ReLU on the wide operand, ragged pixel counts.  The bf16 version runs on mma.sync with a split (value + residual)
+    narrow operand, so fp32 patches are not rounded."""
+    k = KernelSet(DEV, dtype)
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + mode)
+    P = B * H * W
+    wide = torch.randn(P, 64, generator=g).to(dtype)
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    stats = torch.cat([torch.zeros(128), scale, shift])
+    flag = ch = None
+    if mode == 0:
+        narrow = torch.randn(P, 4, generator=g).to(dtype)
+        eff = narrow.float()
+    else:
+        narrow = torch.randn(P, 4, generator=g)                    # fp32 patches (re0, re1, im0, im1)
+        eff = narrow.clone().view(B, H, W, 4)
+        if mode != 3:
+            flag = (torch.rand(B * H, generator=g) < 0.5).to(torch.uint8)
+            ch = torch.randint(0, 2, (B,), generator=g, dtype=torch.int32)
+            pm = flag.view(B, H).bool()
+            for b in range(B):
+                mc = int(ch[b])
+                for h in range(H):
+                    if mode == 1:
+                        keep = 1 - mc if pm[b, h] else mc
+                        eff[b, h, :, [0, 2] if keep else [1, 3]] = 0.0
+                    elif pm[b, h]:
+                        eff[b, h] = 0.0
+        eff = eff.reshape(P, 4)
+    dev = lambda t: None if t is None else t.to(DEV)
+    for st in (None, stats):
+        z = wide.float() if st is None else torch.relu(wide.float() * scale + shift)
+        if st is not None and dtype == torch.bfloat16:
+            z = z.to(dtype).float()                                 # the kernel rounds the activation like the materialised tensor
+        ref = z.double().t() @ eff.double()
+        dw = torch.zeros(64, 4, device=DEV)
+        k.stem_pw_wgrad(dev(wide), dev(st), dev(narrow), mode, dev(flag), dev(ch), dw, False, P, W, H)
+        assert rel(dw.cpu(), ref) < (2e-5 if dtype == torch.float32 else 1e-4), (st is not None)
+        k.stem_pw_wgrad(dev(wide), dev(st), dev(narrow), mode, dev(flag), dev(ch), dw, True, P, W, H)       # accumulate
+        assert rel(dw.cpu(), 2 * ref) < (2e-5 if dtype == torch.float32 else 1e-4)
