@@ -261,6 +261,18 @@ size_t sarssl_stem_workspace_bytes(void);
 int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, const float* wide_shift, const void* narrow, int mode,
                          const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
                          int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Fused backward of the first stem layer (1x1 conv 4 -> 64, BatchNorm, ReLU; model.py:51-53), bf16 activations only: ONE pass over
+ * dz (gradient w.r.t. the ReLU output) and z (that output) yields dweight64x4 +=, dgamma +=, dbeta +=; no P x 64 tensor is written
+ * (this layer's input gradient is never needed).  stats = (mean, rstd, scale, shift)[64] of its BatchNorm; narrow as stem_expand. */
+int sarssl_stem_head_bwd(const void* dz, const void* z, const float* stats, const void* narrow, int mode, const uint8_t* frame_flag,
+                         const int32_t* ch_idx, const float* weight64x4, float* dgamma, float* dbeta, float* dweight64x4,
+                         long long P, int W, int H, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Fused backward of BatchNorm + ReLU + 1x1 conv 64 -> 4 at the end of the stem (model.py:58-60), bf16 activations only.
+ * y = pre-BatchNorm activation [P][64] with stats (mean, rstd, scale, shift)[64]; dq = gradient w.r.t. the conv output [P][4].
+ * dweight4x64 +=, dgamma +=, dbeta +=, and dy [P][64] (gradient w.r.t. y) is written; the P x 64 gradient of the ReLU output
+ * is recomputed in registers, never stored. */
+int sarssl_stem_tail_bwd(const void* y, const float* stats, const void* dq, const float* weight4x64, float* dgamma, float* dbeta,
+                         float* dweight4x64, void* dy, long long P, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* 3x3 conv 64 -> 64, padding 1, as implicit GEMM; weight_packed [n][tap = (dh+1)*3 + (dw+1)][ci] in `dtype`;
  * BatchNorm+ReLU of the INPUT applied on load when in_scale given (zero padding stays zero). */
 int sarssl_conv3x3(const void* in, const float* in_scale, const float* in_shift, const void* weight_packed, void* out, int B, int H, int W,

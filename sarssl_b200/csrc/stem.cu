@@ -175,15 +175,27 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
     }
 }
 
-// ---- bf16 version of the same sum on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate) -------------------------
-// D[o][n] = sum_p f(wide[p][o]) * B[p][n]: M = 64 wide channels (4 m-tiles), K = pixels, N = 8 = the 4 narrow channels twice:
+// ---- bf16 pixel contractions on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate) -----------------------------
+// D[o][n] = sum_p A[p][o] * B[p][n]: M = 64 wide channels (4 m-tiles), K = pixels, N = 8 = the 4 narrow channels twice:
 // columns 0..3 hold bf16(x), columns 4..7 the rounding residual bf16(x - bf16(x)), so fp32 patch inputs keep 16 mantissa bits.
 // Both operands are pixel-major in memory, i.e. K is the slow index: ldmatrix.trans delivers the fragments.  Every warp owns 16
-// pixels of a 128-pixel tile and a private cp.async ring (no block barrier in the main loop); the BatchNorm+ReLU of the wide
-// operand is applied to the A fragments in registers (fp32 math, rounded to bf16 exactly like the materialised activation).
-constexpr int kWgStages = 4;
-constexpr int kWgWarpStage = 16 * 128 + 16 * 16;                    // wide 16 px x 128 B (16-byte chunks XOR-swizzled by pixel) + narrow 16 px x 16 B
-constexpr int kWgSmem = 8 * kWgStages * kWgWarpStage;               // 73,728 B
+// pixels of a 128-pixel tile and a private cp.async ring (no block barrier in the main loop).  The A fragments are built in
+// registers from the wide tensor(s):
+//   kWgPlain : A = f(wide), f = BatchNorm+ReLU when scale/shift are given (fp32 math, rounded to bf16 like the materialised activation)
+//              -> out[256] = D                                                      (weight gradient of either 1x1 conv)
+//   kWgHead  : A = g = wide * [wide2 > 0]  (gradient through the ReLU that produced wide2); besides G = D it accumulates
+//              S[o] = sum_p g (a ones column), the 8x8 second moments of the narrow operand and its column sums
+//              -> out[392] = G[64][4], S[64], M[8][8], Sx[8]                        (everything the first stem layer's backward needs)
+//   kWgTail  : A0 = m = [scale*wide+shift > 0], A1 = m * wide
+//              -> out[512] = H0[64][4], H1[64][4]                                   (everything the last stem layer's backward needs)
+enum { kWgPlain = 0, kWgHead = 1, kWgTail = 2 };
+template <int MODE> struct WgCfg {
+    static constexpr int kWide = MODE == kWgHead ? 2 : 1;                      // wide tiles per stage
+    static constexpr int kStages = MODE == kWgHead ? 3 : 4;
+    static constexpr int kWarpStage = kWide * 16 * 128 + 16 * 16;              // wide 16 px x 128 B each (16-byte chunks XOR-swizzled by pixel) + narrow 16 px x 16 B
+    static constexpr int kSmem = 8 * kStages * kWarpStage;                     // 73,728 B (plain, tail) / 104,448 B (head)
+    static constexpr int kOut = MODE == kWgPlain ? 256 : (MODE == kWgHead ? 392 : 512);
+};
 
 __device__ __forceinline__ uint32_t bn_relu_bf16x2(uint32_t r, float sc, float sh) {
     const float lo = fmaxf(fmaf(__uint_as_float(r << 16), sc, sh), 0.f), hi = fmaxf(fmaf(__uint_as_float(r & 0xffff0000u), sc, sh), 0.f);
@@ -191,14 +203,32 @@ __device__ __forceinline__ uint32_t bn_relu_bf16x2(uint32_t r, float sc, float s
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo));
     return o;
 }
+// 0xffff in every half of z that holds a positive bf16 (sign clear, magnitude non-zero)
+__device__ __forceinline__ uint32_t positive_halves_bf16x2(uint32_t z) {
+    const uint32_t nz = ((z & 0x7fff7fffu) + 0x7fff7fffu) & ~z & 0x80008000u;
+    return (nz >> 15) * 0xffffu;
+}
+// 0xffff in every half of y with sc * y + sh > 0
+__device__ __forceinline__ uint32_t active_halves_bf16x2(uint32_t y, float sc, float sh) {
+    const float lo = fmaf(__uint_as_float(y << 16), sc, sh), hi = fmaf(__uint_as_float(y & 0xffff0000u), sc, sh);
+    return (lo > 0.f ? 0x0000ffffu : 0u) | (hi > 0.f ? 0xffff0000u : 0u);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-__global__ void __launch_bounds__(256) pw_wgrad_mma_kernel(const __nv_bfloat16* __restrict__ wide, const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, const void* __restrict__ narrow, int mode,
-                                                         const uint8_t* __restrict__ flag, const int32_t* __restrict__ ch,
-                                                         float* __restrict__ partials, long long P, int W, int H) {
+template <int MODE>
+__global__ void __launch_bounds__(256) pw_contract_mma_kernel(const __nv_bfloat16* __restrict__ wide, const __nv_bfloat16* __restrict__ wide2,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            const void* __restrict__ narrow, int mode, const uint8_t* __restrict__ flag,
+                                                            const int32_t* __restrict__ ch, float* __restrict__ partials, long long P, int W, int H) {
+    using Cfg = WgCfg<MODE>;
+    constexpr int S = Cfg::kStages, WS = Cfg::kWarpStage, NOFF = Cfg::kWide * 16 * 128;
     extern __shared__ __align__(128) uint8_t wg_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2;
-    uint8_t* ring = wg_smem + (size_t)warp * kWgStages * kWgWarpStage;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint8_t* ring = wg_smem + (size_t)warp * S * WS;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     const bool tr = scale != nullptr;
     float sc[4][2], sh[4][2];
@@ -206,32 +236,37 @@ __global__ void __launch_bounds__(256) pw_wgrad_mma_kernel(const __nv_bfloat16* 
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) { sc[mt][h] = tr ? scale[16 * mt + g + 8 * h] : 1.f; sh[mt][h] = tr ? shift[16 * mt + g + 8 * h] : 0.f; }
-    float acc[4][4];
+    float acc[4][4], acc2[MODE == kWgPlain ? 1 : 4][4], accM[4], accX[4];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f; }
-    const long long ntiles = (P + 127) / 128;
-    const long long my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) { acc[mt][q] = 0.f; if (MODE != kWgPlain) acc2[mt][q] = 0.f; }
+        accM[q] = accX[q] = 0.f;
+    }
+    const int ntiles = (int)((P + 127) / 128);
+    const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    // stage `it` (tile blockIdx.x + it * gridDim.x): cp.async the warp's 16 x 128 B of `wide`, return its narrow pixel (lanes 0..15) in registers
-    auto issue = [&](long long it, float4& nx) {
+    // stage `it` (tile blockIdx.x + it * gridDim.x): cp.async the warp's 16 x 128 B of each wide tensor, return its narrow pixel (lanes 0..15) in registers
+    auto issue = [&](int it, float4& nx) {
         nx = make_float4(0.f, 0.f, 0.f, 0.f);
         if (it < my_tiles) {
-            const long long p0 = ((long long)blockIdx.x + it * gridDim.x) * 128 + warp * 16;
-            const uint32_t dst = ring_s + (uint32_t)(it % kWgStages) * kWgWarpStage;
+            const long long p0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + warp * 16;
+            const uint32_t dst = ring_s + (uint32_t)(it % S) * WS;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int id = lane + 32 * j, px = id >> 3, chunk = id & 7;
                 const bool ok = p0 + px < P;
-                const __nv_bfloat16* src = wide + (ok ? (p0 + px) * 64 + chunk * 8 : 0);
+                const long long off = ok ? (p0 + px) * 64 + chunk * 8 : 0;
                 const uint32_t d = dst + px * 128 + ((chunk ^ (px & 7)) << 4);
                 const int nbytes = ok ? 16 : 0;                                       // zero-fill beyond the last pixel
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(wide + off), "r"(nbytes) : "memory");
+                if (MODE == kWgHead) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + 16 * 128), "l"(wide2 + off), "r"(nbytes) : "memory");
             }
             if (lane < 16 && p0 + lane < P) nx = load_narrow<__nv_bfloat16>(narrow, p0 + lane, mode, flag, ch, W, H);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto put_narrow = [&](long long it, const float4& nx) {                            // [px][8] bf16: value, then rounding residual
+    auto put_narrow = [&](int it, const float4& nx) {                                  // [px][8] bf16: value, then rounding residual
         if (lane < 16) {
             const __nv_bfloat162 h0 = __floats2bfloat162_rn(nx.x, nx.y), h1 = __floats2bfloat162_rn(nx.z, nx.w);
             const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
@@ -239,23 +274,28 @@ __global__ void __launch_bounds__(256) pw_wgrad_mma_kernel(const __nv_bfloat16* 
             uint4 v;
             v.x = *reinterpret_cast<const uint32_t*>(&h0); v.y = *reinterpret_cast<const uint32_t*>(&h1);
             v.z = *reinterpret_cast<const uint32_t*>(&l0); v.w = *reinterpret_cast<const uint32_t*>(&l1);
-            *reinterpret_cast<uint4*>(ring + (size_t)(it % kWgStages) * kWgWarpStage + 16 * 128 + lane * 16) = v;
+            *reinterpret_cast<uint4*>(ring + (size_t)(it % S) * WS + NOFF + lane * 16) = v;
         }
     };
 
     float4 nx;
 #pragma unroll 1
-    for (int s = 0; s < kWgStages - 1; ++s) { issue(s, nx); put_narrow(s, nx); }
+    for (int s = 0; s < S - 1; ++s) { issue(s, nx); put_narrow(s, nx); }
+    const uint32_t ones = (g == 0) ? 0x3f803f80u : 0u;                                 // B fragment of a matrix whose column 0 is all ones
 #pragma unroll 1
-    for (long long it = 0; it < my_tiles; ++it) {
-        issue(it + kWgStages - 1, nx);                                             // slot (it - 1) % stages: consumed last iteration
-        asm volatile("cp.async.wait_group %0;" ::"n"(kWgStages - 1) : "memory");
+    for (int it = 0; it < my_tiles; ++it) {
+        issue(it + S - 1, nx);                                                         // slot (it - 1) % S: consumed last iteration
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
         __syncwarp();
-        const uint32_t st = ring_s + (uint32_t)(it % kWgStages) * kWgWarpStage;
+        const uint32_t st = ring_s + (uint32_t)(it % S) * WS;
         uint32_t b0, b1;
         {
-            const uint32_t addr = st + 16 * 128 + (lane & 15) * 16;
+            const uint32_t addr = st + NOFF + (lane & 15) * 16;
             asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        }
+        if (MODE == kWgHead) {                                                         // the B fragment of [p][n] is also the A fragment of its transpose (rows 0..7)
+            mma_bf16_16816(accM, b0, 0u, b1, 0u, b0, b1);
+            mma_bf16_16816(accX, b0, 0u, b1, 0u, ones, ones);
         }
         const int mi = lane >> 3, r = lane & 7, px = (mi >> 1) * 8 + r;
 #pragma unroll
@@ -263,34 +303,159 @@ __global__ void __launch_bounds__(256) pw_wgrad_mma_kernel(const __nv_bfloat16* 
             uint32_t a0, a1, a2, a3;
             const uint32_t addr = st + px * 128 + (((2 * mt + (mi & 1)) ^ r) << 4);
             asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
-            if (tr) {
-                a0 = bn_relu_bf16x2(a0, sc[mt][0], sh[mt][0]); a2 = bn_relu_bf16x2(a2, sc[mt][0], sh[mt][0]);
-                a1 = bn_relu_bf16x2(a1, sc[mt][1], sh[mt][1]); a3 = bn_relu_bf16x2(a3, sc[mt][1], sh[mt][1]);
+            if (MODE == kWgPlain) {
+                if (tr) {
+                    a0 = bn_relu_bf16x2(a0, sc[mt][0], sh[mt][0]); a2 = bn_relu_bf16x2(a2, sc[mt][0], sh[mt][0]);
+                    a1 = bn_relu_bf16x2(a1, sc[mt][1], sh[mt][1]); a3 = bn_relu_bf16x2(a3, sc[mt][1], sh[mt][1]);
+                }
+                mma_bf16_16816(acc[mt], a0, a1, a2, a3, b0, b1);
+            } else if (MODE == kWgHead) {
+                uint32_t z0, z1, z2, z3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(z0), "=r"(z1), "=r"(z2), "=r"(z3) : "r"(addr + 16 * 128));
+                a0 &= positive_halves_bf16x2(z0); a1 &= positive_halves_bf16x2(z1); a2 &= positive_halves_bf16x2(z2); a3 &= positive_halves_bf16x2(z3);
+                mma_bf16_16816(acc[mt], a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(acc2[mt], a0, a1, a2, a3, ones, ones);
+            } else {
+                const uint32_t m0 = active_halves_bf16x2(a0, sc[mt][0], sh[mt][0]), m2 = active_halves_bf16x2(a2, sc[mt][0], sh[mt][0]);
+                const uint32_t m1 = active_halves_bf16x2(a1, sc[mt][1], sh[mt][1]), m3 = active_halves_bf16x2(a3, sc[mt][1], sh[mt][1]);
+                mma_bf16_16816(acc[mt], m0 & 0x3f803f80u, m1 & 0x3f803f80u, m2 & 0x3f803f80u, m3 & 0x3f803f80u, b0, b1);
+                mma_bf16_16816(acc2[mt], a0 & m0, a1 & m1, a2 & m2, a3 & m3, b0, b1);
             }
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                         : "+f"(acc[mt][0]), "+f"(acc[mt][1]), "+f"(acc[mt][2]), "+f"(acc[mt][3])
-                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
         }
-        __syncwarp();                                                              // every lane is done reading slot it % stages ...
-        put_narrow(it + kWgStages - 1, nx);                                        // ... and slot (it - 1) % stages, refilled here
+        __syncwarp();                                                                  // every lane is done reading slot it % S ...
+        put_narrow(it + S - 1, nx);                                                    // ... and slot (it - 1) % S, refilled here
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // D columns n = 2t, 2t+1 live in lane quad position t: add the residual columns (t + 2) to the value columns, then sum the 8 warps
-    float* red = reinterpret_cast<float*>(wg_smem);                                // [8 warps][64 o][4 c]
-    const int t = lane & 3;
+    constexpr int NOUT = Cfg::kOut;
+    float* red = reinterpret_cast<float*>(wg_smem) + warp * NOUT;                      // [8 warps][NOUT]
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            const int o = 16 * mt + g + 8 * (q >> 1), c = 2 * t + (q & 1);
             const float v = acc[mt][q] + __shfl_down_sync(0xffffffffu, acc[mt][q], 2);
-            if (t < 2) red[(warp * 64 + 16 * mt + g + 8 * (q >> 1)) * 4 + 2 * t + (q & 1)] = v;
+            if (t < 2) red[o * 4 + c] = v;
+            if (MODE == kWgTail) {
+                const float v2 = acc2[mt][q] + __shfl_down_sync(0xffffffffu, acc2[mt][q], 2);
+                if (t < 2) red[256 + o * 4 + c] = v2;
+            }
+            if (MODE == kWgHead && t == 0 && (q & 1) == 0) red[256 + o] = acc2[mt][q];
         }
+    if (MODE == kWgHead) {
+        red[320 + g * 8 + 2 * t] = accM[0]; red[320 + g * 8 + 2 * t + 1] = accM[1];
+        if (t == 0) red[384 + g] = accX[0];
+    }
     __syncthreads();
-    float sum = 0.f;
+    for (int i = threadIdx.x; i < NOUT; i += 256) {
+        float sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += red[w * 256 + threadIdx.x];
-    partials[(size_t)blockIdx.x * 256 + threadIdx.x] = sum;
+        for (int w = 0; w < 8; ++w) sum += reinterpret_cast<const float*>(wg_smem)[w * NOUT + i];
+        partials[(size_t)blockIdx.x * NOUT + i] = sum;
+    }
+}
+
+template <int MODE>
+static int launch_pw_contract(const void* wide, const void* wide2, const float* scale, const float* shift, const void* narrow, int mode,
+                              const uint8_t* flag, const int32_t* ch, float* partials, size_t partial_floats, long long P, int W, int H,
+                              cudaStream_t stream, int* grid_out) {
+    using Cfg = WgCfg<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) { SARSSL_CUDA(cudaFuncSetAttribute(pw_contract_mma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr_set = true; }
+    const long long need = (P + 127) / 128, cap = resident_ctas(pw_contract_mma_kernel<MODE>, 256, Cfg::kSmem);
+    const int grid = (int)(need < cap ? need : cap);
+    if (partial_floats < (size_t)grid * Cfg::kOut) { set_last_error("stem pixel contraction: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    pw_contract_mma_kernel<MODE><<<grid, 256, Cfg::kSmem, stream>>>(static_cast<const __nv_bfloat16*>(wide), static_cast<const __nv_bfloat16*>(wide2), scale, shift,
+                                                                     narrow, mode, flag, ch, partials, P, W, H);
+    SARSSL_LAUNCH_CHECK();
+    *grid_out = grid;
+    return SARSSL_OK;
+}
+
+// ---- fused backward of the first stem layer (1x1 conv 4 -> 64, BatchNorm, ReLU): one pass over (dz, z) -----------------------------
+// With y = W x, g = dz * [z > 0] and the BatchNorm backward dy = sc*g - c0 - c1*y (see bn_act_bwd_kernel) the weight gradient is
+//   dW[o][c] = sum_p dy[p][o] x[p][c] = sc[o] G[o][c] - c0[o] Sx[c] - c1[o] (W Mxx)[o][c],
+// and sum_p g*y = sum_c W[o][c] G[o][c]: nothing of size P x 64 is written (the input gradient of this layer is never needed).
+// sums [392] = G[64][4], S[64], M[8][8], Sx[8] (value | residual halves still separate).  One block of 256 threads = (o, c).
+__global__ void stem_head_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ w64x4, const float* __restrict__ stats,
+                                              double inv_rows, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw64x4) {
+    const int o = threadIdx.x >> 2, c = threadIdx.x & 3;
+    const double mean = stats[o], rstd = stats[64 + o], sc = stats[128 + o];
+    double Sgy = 0.0, WM = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        Sgy += (double)w64x4[o * 4 + k] * (double)sums[o * 4 + k];
+        const double mxx = (double)sums[320 + k * 8 + c] + (double)sums[320 + k * 8 + c + 4] + (double)sums[320 + (k + 4) * 8 + c] + (double)sums[320 + (k + 4) * 8 + c + 4];
+        WM += (double)w64x4[o * 4 + k] * mxx;
+    }
+    const double S = sums[256 + o], Sx = (double)sums[384 + c] + (double)sums[384 + c + 4];
+    const double s2 = rstd * (Sgy - mean * S);
+    const double c1 = sc * rstd * s2 * inv_rows, c0 = sc * S * inv_rows - c1 * mean;
+    dw64x4[o * 4 + c] += (float)(sc * (double)sums[o * 4 + c] - c0 * Sx - c1 * WM);
+    if (c == 0) { dgamma[o] += (float)s2; dbeta[o] += (float)S; }
+}
+
+// ---- fused backward of the last stem layer pair (BatchNorm, ReLU, 1x1 conv 64 -> 4) -------------------------------------------------
+// Upstream gradient dq [P][4] (narrow).  dz[p][o] = sum_c W[c][o] dq[p][c] is never materialised: with m = [sc*y+sh > 0],
+//   H0[o][c] = sum_p m dq,  H1[o][c] = sum_p m y dq   give   dW[c][o] = sc H1 + sh H0   (z = m (sc y + sh)),
+//   sum_p g = sum_c W[c][o] H0[o][c],  sum_p g y = sum_c W[c][o] H1[o][c]                (g = m dz),
+// and a second pass writes dy = sc*g - c0 - c1*y recomputing dz from dq in registers.
+__global__ void stem_tail_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ w4x64, const float* __restrict__ stats,
+                                              double inv_rows, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw4x64,
+                                              float* __restrict__ coef) {
+    const int o = threadIdx.x >> 2, c = threadIdx.x & 3;
+    const double mean = stats[o], rstd = stats[64 + o], sc = stats[128 + o], sh = stats[192 + o];
+    dw4x64[c * 64 + o] += (float)(sc * (double)sums[256 + o * 4 + c] + sh * (double)sums[o * 4 + c]);
+    if (c == 0) {
+        double S = 0.0, Sgy = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { S += (double)w4x64[k * 64 + o] * (double)sums[o * 4 + k]; Sgy += (double)w4x64[k * 64 + o] * (double)sums[256 + o * 4 + k]; }
+        const double s2 = rstd * (Sgy - mean * S);
+        const double c1 = sc * rstd * s2 * inv_rows;
+        dgamma[o] += (float)s2; dbeta[o] += (float)S;
+        coef[o] = (float)(sc * S * inv_rows - c1 * mean);        // c0
+        coef[64 + o] = (float)c1;
+    }
+}
+
+// dy[p][o] = sc[o] * [sc*y+sh > 0] * (sum_c W[c][o] dq[p][c]) - c0[o] - c1[o] * y[p][o].  8 threads per pixel, 8 channels each.
+__global__ void __launch_bounds__(256, 2) stem_tail_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dq,
+                                                                const float* __restrict__ w4x64, const float* __restrict__ stats,
+                                                                const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, long long P) {
+    const int sub = threadIdx.x & 7;
+    float wr[8][4], sc[8], sh[8], c0[8], c1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int o = sub * 8 + j;
+        sc[j] = stats[128 + o]; sh[j] = stats[192 + o]; c0[j] = coef[o]; c1[j] = coef[64 + o];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[j][c] = w4x64[c * 64 + o] * sc[j];               // sc folded into the weights
+    }
+    for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
+        float4 x[4];
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u < P) {
+                x[u] = load_narrow<__nv_bfloat16>(dq, p0 + u, 0, nullptr, nullptr, 0, 0);
+                Vec8<__nv_bfloat16>::load(y + (p0 + u) * 64 + sub * 8, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u >= P) break;
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float yv = v[u][j];
+                const float dzs = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
+                const float gs = fmaf(yv, sc[j], sh[j]) > 0.f ? dzs : 0.f;
+                o8[j] = gs - fmaf(c1[j], yv, c0[j]);
+            }
+            Vec8<__nv_bfloat16>::store(dy + (p0 + u) * 64 + sub * 8, o8);
+        }
+    }
 }
 
 __global__ void stem_reduce_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out, int accumulate) {
@@ -469,22 +634,64 @@ extern "C" int sarssl_stem_pw_wgrad(const void* wide, const float* wide_scale, c
                                     const uint8_t* frame_flag, const int32_t* ch_idx, float* dweight64x4, int accumulate, long long P, int W, int H,
                                     int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(wide && narrow && dweight64x4 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_pw_wgrad: bad arguments (P must be in (0, 2^32))");
-    int grid;
-    if (dtype == SARSSL_BF16) {
-        static bool attr_set = false;
-        if (!attr_set) { SARSSL_CUDA(cudaFuncSetAttribute(pw_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); attr_set = true; }
-        const long long need = (P + 127) / 128, cap = resident_ctas(pw_wgrad_mma_kernel, 256, kWgSmem);
-        grid = (int)(need < cap ? need : cap);
-    } else {
-        grid = pix_grid(pw_wgrad_kernel<float>, P);
-    }
-    if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
-    if (dtype == SARSSL_F32) pw_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
-    else if (dtype == SARSSL_BF16) pw_wgrad_mma_kernel<<<grid, 256, kWgSmem, stream>>>((const __nv_bfloat16*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
-    else { set_last_error("stem_pw_wgrad: bad dtype"); return SARSSL_ERR_ARG; }
-    SARSSL_LAUNCH_CHECK();
+    int grid = 0;
+    if (dtype == SARSSL_BF16) {
+        const int rc = launch_pw_contract<kWgPlain>(wide, nullptr, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials,
+                                                    workspace_bytes / sizeof(float), P, W, H, stream, &grid);
+        if (rc != SARSSL_OK) return rc;
+    } else if (dtype == SARSSL_F32) {
+        grid = pix_grid(pw_wgrad_kernel<float>, P);
+        if (workspace_bytes < (size_t)grid * 256 * sizeof(float)) { set_last_error("stem_pw_wgrad: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+        pw_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)wide, wide_scale, wide_shift, narrow, mode, frame_flag, ch_idx, partials, P, W, H);
+        SARSSL_LAUNCH_CHECK();
+    } else { set_last_error("stem_pw_wgrad: bad dtype"); return SARSSL_ERR_ARG; }
     stem_reduce_kernel<<<1, 256, 0, stream>>>(partials, grid, 256, dweight64x4, accumulate);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// Backward of the first stem layer in one pass (bf16 activations only): see stem_head_bwd_finalize_kernel.
+// dz = gradient w.r.t. the layer's ReLU output z [P][64]; stats = (mean, rstd, scale, shift) of its BatchNorm; narrow = the layer input.
+extern "C" int sarssl_stem_head_bwd(const void* dz, const void* z, const float* stats, const void* narrow, int mode, const uint8_t* frame_flag,
+                                    const int32_t* ch_idx, const float* weight64x4, float* dgamma, float* dbeta, float* dweight64x4,
+                                    long long P, int W, int H, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(dz && z && stats && narrow && weight64x4 && dgamma && dbeta && dweight64x4 && workspace && P > 0 && P < 0xFFFFFFFFLL,
+                     "stem_head_bwd: bad arguments (P must be in (0, 2^32))");
+    SARSSL_CHECK_ARG(dtype == SARSSL_BF16, "stem_head_bwd: bf16 activations only");
+    float* partials = static_cast<float*>(workspace);
+    int grid = 0;
+    const size_t floats = workspace_bytes / sizeof(float);
+    if (floats < 512) { set_last_error("stem_head_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    const int rc = launch_pw_contract<kWgHead>(dz, z, nullptr, nullptr, narrow, mode, frame_flag, ch_idx, partials + 512, floats - 512, P, W, H, stream, &grid);
+    if (rc != SARSSL_OK) return rc;
+    stem_reduce_kernel<<<2, 256, 0, stream>>>(partials + 512, grid, WgCfg<kWgHead>::kOut, partials, 0);
+    SARSSL_LAUNCH_CHECK();
+    stem_head_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partials, weight64x4, stats, 1.0 / (double)P, dgamma, dbeta, dweight64x4);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+// Backward of BatchNorm + ReLU + 1x1 conv (64 -> 4) at the end of the stem (bf16 activations only): see stem_tail_bwd_finalize_kernel.
+// y = pre-BatchNorm activation [P][64], stats = its (mean, rstd, scale, shift), dq = gradient w.r.t. the conv output [P][4]; writes dy [P][64].
+extern "C" int sarssl_stem_tail_bwd(const void* y, const float* stats, const void* dq, const float* weight4x64, float* dgamma, float* dbeta,
+                                    float* dweight4x64, void* dy, long long P, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(y && stats && dq && weight4x64 && dgamma && dbeta && dweight4x64 && dy && workspace && P > 0 && P < 0xFFFFFFFFLL,
+                     "stem_tail_bwd: bad arguments (P must be in (0, 2^32))");
+    SARSSL_CHECK_ARG(dtype == SARSSL_BF16, "stem_tail_bwd: bf16 activations only");
+    float* partials = static_cast<float*>(workspace);           // [0, 512) reduced sums, [512, 640) c0 | c1, then the per-CTA partials
+    int grid = 0;
+    const size_t floats = workspace_bytes / sizeof(float);
+    if (floats < 640) { set_last_error("stem_tail_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    const int rc = launch_pw_contract<kWgTail>(y, nullptr, stats + 128, stats + 192, dq, 0, nullptr, nullptr, partials + 640, floats - 640, P, 0, 0, stream, &grid);
+    if (rc != SARSSL_OK) return rc;
+    stem_reduce_kernel<<<2, 256, 0, stream>>>(partials + 640, grid, WgCfg<kWgTail>::kOut, partials, 0);
+    SARSSL_LAUNCH_CHECK();
+    stem_tail_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partials, weight4x64, stats, 1.0 / (double)P, dgamma, dbeta, dweight4x64, partials + 512);
+    SARSSL_LAUNCH_CHECK();
+    const int g2 = pix_grid(stem_tail_bwd_apply_kernel, P);
+    stem_tail_bwd_apply_kernel<<<g2, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dq), weight4x64, stats,
+                                                      partials + 512, static_cast<__nv_bfloat16*>(dy), P);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -452,14 +452,17 @@ class Engine:
         dz4 = k.empty(M, 4 * F)
         k.linear_dgrad(de, self.W[f"{pe}.12.packed"], dz4, M, D, 4 * F)
         k.bn_act_bwd(dz4, r["y4"], r["s4"], ACT_RELU, dz4, st.g(f"{pe}.10.weight"), st.g(f"{pe}.10.bias"), P, 4)        # dz4 -> dy4
-        # 1x1 conv 64 -> 4
-        tmp = torch.empty(CNN_CH, 4, dtype=torch.float32, device=self.dev)
-        k.stem_pw_wgrad(r["y3"], r["s3"], dz4, 0, None, None, tmp, False, P, F, T)
-        k.permute4(tmp, st.g(f"{pe}.9.weight"), (4, CNN_CH, 1, 1), (1, 4, 0, 0), accumulate=True)
+        # 1x1 conv 64 -> 4 and the BatchNorm + ReLU in front of it
         dz = k.empty(P, CNN_CH)
-        k.stem_expand(dz4, 0, None, None, self.W[f"{pe}.9.T"], dz, P, F, T)
+        if k.conv_tc:            # one fused path: the P x 64 gradient of the ReLU output is never stored
+            k.stem_tail_bwd(r["y3"], r["s3"], dz4, st.p(f"{pe}.9.weight"), st.g(f"{pe}.7.weight"), st.g(f"{pe}.7.bias"), st.g(f"{pe}.9.weight"), dz, P)
+        else:
+            tmp = torch.empty(CNN_CH, 4, dtype=torch.float32, device=self.dev)
+            k.stem_pw_wgrad(r["y3"], r["s3"], dz4, 0, None, None, tmp, False, P, F, T)
+            k.permute4(tmp, st.g(f"{pe}.9.weight"), (4, CNN_CH, 1, 1), (1, 4, 0, 0), accumulate=True)
+            k.stem_expand(dz4, 0, None, None, self.W[f"{pe}.9.T"], dz, P, F, T)
+            k.bn_act_bwd(dz, r["y3"], r["s3"], ACT_RELU, dz, st.g(f"{pe}.7.weight"), st.g(f"{pe}.7.bias"), P, CNN_CH)       # -> dy3
         del dz4
-        k.bn_act_bwd(dz, r["y3"], r["s3"], ACT_RELU, dz, st.g(f"{pe}.7.weight"), st.g(f"{pe}.7.bias"), P, CNN_CH)       # -> dy3
         dz_prev = k.empty(P, CNN_CH)
         for i, y_in, s_in, y_bn, bn_key, z_in in ((6, r["y2"], r["s2"], r["y2"], f"{pe}.4", r["z2"]), (3, r["y1"], r["s1"], r["y1"], f"{pe}.1", r["z1"])):
             dwpk = torch.empty(CNN_CH, 9, CNN_CH, dtype=torch.float32, device=self.dev)
@@ -472,7 +475,12 @@ class Engine:
                 k.conv3x3_tc(dz, self.W[f"{pe}.{i}.bwd"], dz_prev, B, T, F)
             else:
                 k.conv3x3(dz, None, self.W[f"{pe}.{i}.bwd"], dz_prev, B, T, F)
-            k.bn_act_bwd(dz_prev, y_bn, s_in, ACT_RELU, dz_prev, st.g(bn_key + ".weight"), st.g(bn_key + ".bias"), P, CNN_CH)
+            if not (k.conv_tc and i == 3):
+                k.bn_act_bwd(dz_prev, y_bn, s_in, ACT_RELU, dz_prev, st.g(bn_key + ".weight"), st.g(bn_key + ".bias"), P, CNN_CH)
             dz, dz_prev = dz_prev, dz
         # 1x1 conv 4 -> 64 (no input gradient needed)
-        k.stem_pw_wgrad(dz, None, sv["patches"], mode, sv["flag"], sv["ch"], st.g(f"{pe}.0.weight").view(CNN_CH, 4), True, P, F, T)
+        if k.conv_tc:            # BatchNorm + ReLU + weight gradient from one pass over (dz1, z1)
+            k.stem_head_bwd(dz, r["z1"], r["s1"], sv["patches"], mode, sv["flag"], sv["ch"], st.p(f"{pe}.0.weight"), st.g(f"{pe}.1.weight"),
+                            st.g(f"{pe}.1.bias"), st.g(f"{pe}.0.weight"), P, F, T)
+        else:
+            k.stem_pw_wgrad(dz, None, sv["patches"], mode, sv["flag"], sv["ch"], st.g(f"{pe}.0.weight").view(CNN_CH, 4), True, P, F, T)

@@ -186,6 +186,20 @@ class KernelSet:
                                              ptr(self.ws), self.ws.numel(), self.stream), "stem_pw_wgrad")
         self.launches += 1
 
+    def stem_head_bwd(self, dz, z, stats, narrow, mode, flag, ch, w64x4, dgamma, dbeta, dw64x4, P, W, H):
+        """Backward of conv1x1(4->64)+BN+ReLU in one pass over (dz, z); accumulates into dgamma, dbeta, dw64x4."""
+        self._ok(self.L.sarssl_stem_head_bwd(ptr(dz), ptr(z), ptr(stats), ptr(narrow), mode, ptr(flag), ptr(ch), ptr(w64x4), ptr(dgamma), ptr(dbeta),
+                                             ptr(dw64x4), P, W, H, self.dt, ptr(self.ws), self.ws.numel(), self.stream), "stem_head_bwd")
+        self.launches += 3
+        self.tc_launches += 1
+
+    def stem_tail_bwd(self, y, stats, dq, w4x64, dgamma, dbeta, dw4x64, dy, P):
+        """Backward of BN+ReLU+conv1x1(64->4): accumulates dgamma, dbeta, dw4x64 and writes dy (gradient w.r.t. the pre-BN activation)."""
+        self._ok(self.L.sarssl_stem_tail_bwd(ptr(y), ptr(stats), ptr(dq), ptr(w4x64), ptr(dgamma), ptr(dbeta), ptr(dw4x64), ptr(dy), P, self.dt,
+                                             ptr(self.ws), self.ws.numel(), self.stream), "stem_tail_bwd")
+        self.launches += 4
+        self.tc_launches += 1
+
     @property
     def conv_tc(self):
         return self.use_tc and self.dtype == torch.bfloat16

@@ -47,6 +47,13 @@ def main():
         ("stem_pw_wgrad (bn+relu(wide), narrow)", lambda: k.stem_pw_wgrad(wide[0], stats, narrow, 0, None, None, dw, False, P, F, T), W + N),
         ("stem_pw_wgrad (wide, narrow)", lambda: k.stem_pw_wgrad(wide[0], None, narrow, 0, None, None, dw, False, P, F, T), W + N),
     ]
+    z = torch.relu(wide[1].float()).to(torch.bfloat16)
+    patches = torch.randn(P, 4, device=dev, generator=g)
+    dgam, dbet, dw2 = torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.zeros(4, 64, device=dev)
+    cases += [
+        ("stem_head_bwd (dz, z, fp32 patches)", lambda: k.stem_head_bwd(wide[2], z, stats, patches, 3, None, None, w64x4, dgam, dbet, dw, P, F, T), 2 * W + 2 * N),
+        ("stem_tail_bwd (y, dq -> dy)", lambda: k.stem_tail_bwd(wide[0], stats, narrow, w4x64, dgam, dbet, dw2, wide[1], P), 3 * W + 2 * N),
+    ]
     for name, fn, nbytes in cases:
         if args.only and args.only not in name:
             continue

@@ -120,3 +120,72 @@ def test_stem_pointwise_wgrad_vs_torch(dtype, B, H, W, mode):
         assert rel(dw.cpu(), ref) < (2e-5 if dtype == torch.float32 else 1e-4), (st is not None)
         k.stem_pw_wgrad(dev(wide), dev(st), dev(narrow), mode, dev(flag), dev(ch), dw, True, P, W, H)       # accumulate
         assert rel(dw.cpu(), 2 * ref) < (2e-5 if dtype == torch.float32 else 1e-4)
+
+
+def _bn_stats64(y, gamma, beta, eps=1e-5):
+    mean, var = y.double().mean(0), y.double().var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    scale = gamma.double() * rstd
+    return torch.cat([mean, rstd, scale, beta.double() - mean * scale]).float()
+
+
+@pytest.mark.parametrize("B,H,W,mode", [(2, 16, 256, 1), (2, 16, 256, 2), (3, 5, 130, 3), (1, 3, 37, 3), (8, 64, 256, 1)])
+def test_stem_head_backward_fused_vs_autograd(B, H, W, mode):
+    """conv1x1(4->64) + BatchNorm(batch statistics) + ReLU backward from ONE pass over (dz, z): dW, dgamma, dbeta vs torch autograd."""
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator().manual_seed(B * 100 + H + mode)
+    P = B * H * W
+    x = torch.randn(P, 4, generator=g) + 0.3
+    flag = ch = None
+    eff = x.clone().view(B, H, W, 4)
+    if mode != 3:
+        flag = (torch.rand(B * H, generator=g) < 0.5).to(torch.uint8)
+        ch = torch.randint(0, 2, (B,), generator=g, dtype=torch.int32)
+        pm = flag.view(B, H).bool()
+        for b in range(B):
+            mc = int(ch[b])
+            for h in range(H):
+                if mode == 1:
+                    keep = 1 - mc if pm[b, h] else mc
+                    eff[b, h, :, [0, 2] if keep else [1, 3]] = 0.0
+                elif pm[b, h]:
+                    eff[b, h] = 0.0
+    eff = eff.reshape(P, 4)
+    w = (torch.randn(64, 4, generator=g) * 0.5).requires_grad_(True)
+    gamma = (torch.rand(64, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(64, generator=g) * 0.2).requires_grad_(True)
+    dz = torch.randn(P, 64, generator=g).bfloat16()
+    y = eff @ w.t()
+    z = torch.relu(F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5))
+    z.backward(dz.float())
+    stats = _bn_stats64(y.detach(), gamma.detach(), beta.detach())
+    dw, dg, db = torch.zeros(64, 4, device=DEV), torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+    dev = lambda t: None if t is None else t.to(DEV)
+    for rep in (1, 2):                                                       # the second call accumulates
+        k.stem_head_bwd(dev(dz), dev(z.detach().bfloat16()), dev(stats), dev(x), mode, dev(flag), dev(ch), dev(w.detach()), dg, db, dw, P, W, H)
+        assert rel(dw.cpu(), rep * w.grad) < 2e-3, rel(dw.cpu(), rep * w.grad)
+        assert rel(dg.cpu(), rep * gamma.grad) < 2e-3 and rel(db.cpu(), rep * beta.grad) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 256), (3, 5, 130), (1, 3, 37), (8, 64, 256)])
+def test_stem_tail_backward_fused_vs_autograd(B, H, W):
+    """BatchNorm + ReLU + conv1x1(64->4) backward without materialising the P x 64 ReLU gradient: dy, dW, dgamma, dbeta vs torch autograd."""
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator().manual_seed(B * 100 + H)
+    P = B * H * W
+    y16 = (torch.randn(P, 64, generator=g) * 1.5 + 0.2).bfloat16()
+    y = y16.float().requires_grad_(True)
+    w = (torch.randn(4, 64, generator=g) * 0.2).requires_grad_(True)
+    gamma = (torch.rand(64, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(64, generator=g) * 0.2).requires_grad_(True)
+    dq = torch.randn(P, 4, generator=g).bfloat16()
+    q = torch.relu(F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5)) @ w.t()
+    q.backward(dq.float())
+    stats = _bn_stats64(y.detach(), gamma.detach(), beta.detach())
+    dw, dg, db = torch.zeros(4, 64, device=DEV), torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+    dy = torch.empty(P, 64, device=DEV, dtype=torch.bfloat16)
+    for rep in (1, 2):
+        k.stem_tail_bwd(y16.to(DEV), stats.to(DEV), dq.to(DEV), w.detach().to(DEV), dg, db, dw, dy, P)
+        assert rel(dy.float().cpu(), y.grad) < 6e-3, rel(dy.float().cpu(), y.grad)
+        assert rel(dw.cpu(), rep * w.grad) < 1e-3, rel(dw.cpu(), rep * w.grad)
+        assert rel(dg.cpu(), rep * gamma.grad) < 1e-3 and rel(db.cpu(), rep * beta.grad) < 1e-3
