@@ -208,10 +208,24 @@ __device__ __forceinline__ uint32_t positive_halves_bf16x2(uint32_t z) {
     const uint32_t nz = ((z & 0x7fff7fffu) + 0x7fff7fffu) & ~z & 0x80008000u;
     return (nz >> 15) * 0xffffu;
 }
-// 0xffff in every half of y with sc * y + sh > 0
-__device__ __forceinline__ uint32_t active_halves_bf16x2(uint32_t y, float sc, float sh) {
-    const float lo = fmaf(__uint_as_float(y << 16), sc, sh), hi = fmaf(__uint_as_float(y & 0xffff0000u), sc, sh);
-    return (lo > 0.f ? 0x0000ffffu : 0u) | (hi > 0.f ? 0xffff0000u : 0u);
+// [sc*y + sh > 0] for a bf16 y as one packed compare: (y ^ flip) > thr with flip = sign bit when sc < 0 and thr = the largest bf16 <=
+// (-sh/sc) * sign(sc) (y is exactly a bf16, so comparing against the rounded-down threshold is the same predicate).  Returned packed
+// twice (both halves of an A-fragment register belong to the same channel): .x = flip, .y = thr.
+__device__ __forceinline__ uint2 relu_gate_bf16x2(float sc, float sh) {
+    uint32_t flip = 0u;
+    float thr;
+    if (sc == 0.f) thr = sh > 0.f ? -3.0e38f : 3.0e38f;
+    else { thr = -sh / sc; if (sc < 0.f) { thr = -thr; flip = 0x8000u; } }
+    uint32_t b = __float_as_uint(thr);
+    if (thr >= 0.f) b &= 0xffff0000u;                                  // towards zero = down
+    else if (b & 0xffffu) b = (b & 0xffff0000u) + 0x10000u;            // negative: away from zero = down
+    b >>= 16;
+    return make_uint2(flip | (flip << 16), b | (b << 16));
+}
+// 0xffff in every half of y that passes the gate
+__device__ __forceinline__ uint32_t active_halves_bf16x2(uint32_t y, uint2 gate) {
+    const uint32_t v = y ^ gate.x;
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), *reinterpret_cast<const __nv_bfloat162*>(&gate.y));
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -236,6 +250,11 @@ __global__ void __launch_bounds__(256) pw_contract_mma_kernel(const __nv_bfloat1
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) { sc[mt][h] = tr ? scale[16 * mt + g + 8 * h] : 1.f; sh[mt][h] = tr ? shift[16 * mt + g + 8 * h] : 0.f; }
+    uint2 gate[4][2];
+    if (MODE == kWgTail) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) { gate[mt][0] = relu_gate_bf16x2(sc[mt][0], sh[mt][0]); gate[mt][1] = relu_gate_bf16x2(sc[mt][1], sh[mt][1]); }
+    }
     float acc[4][4], acc2[MODE == kWgPlain ? 1 : 4][4], accM[4], accX[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -316,8 +335,8 @@ __global__ void __launch_bounds__(256) pw_contract_mma_kernel(const __nv_bfloat1
                 mma_bf16_16816(acc[mt], a0, a1, a2, a3, b0, b1);
                 mma_bf16_16816(acc2[mt], a0, a1, a2, a3, ones, ones);
             } else {
-                const uint32_t m0 = active_halves_bf16x2(a0, sc[mt][0], sh[mt][0]), m2 = active_halves_bf16x2(a2, sc[mt][0], sh[mt][0]);
-                const uint32_t m1 = active_halves_bf16x2(a1, sc[mt][1], sh[mt][1]), m3 = active_halves_bf16x2(a3, sc[mt][1], sh[mt][1]);
+                const uint32_t m0 = active_halves_bf16x2(a0, gate[mt][0]), m2 = active_halves_bf16x2(a2, gate[mt][0]);
+                const uint32_t m1 = active_halves_bf16x2(a1, gate[mt][1]), m3 = active_halves_bf16x2(a3, gate[mt][1]);
                 mma_bf16_16816(acc[mt], m0 & 0x3f803f80u, m1 & 0x3f803f80u, m2 & 0x3f803f80u, m3 & 0x3f803f80u, b0, b1);
                 mma_bf16_16816(acc2[mt], a0 & m0, a1 & m1, a2 & m2, a3 & m3, b0, b1);
             }
@@ -420,41 +439,44 @@ __global__ void stem_tail_bwd_finalize_kernel(const float* __restrict__ sums, co
 }
 
 // dy[p][o] = sc[o] * [sc*y+sh > 0] * (sum_c W[c][o] dq[p][c]) - c0[o] - c1[o] * y[p][o].  8 threads per pixel, 8 channels each.
-__global__ void __launch_bounds__(256, 2) stem_tail_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dq,
+// The 8 per-channel constants stay in shared memory ([j][sub] order: the 8 sub-groups of a warp read 128 contiguous bytes), read
+// once per 4 pixels, so the kernel keeps enough CTAs resident to cover the HBM latency.
+__global__ void __launch_bounds__(256, 3) stem_tail_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dq,
                                                                 const float* __restrict__ w4x64, const float* __restrict__ stats,
                                                                 const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, long long P) {
-    const int sub = threadIdx.x & 7;
-    float wr[8][4], sc[8], sh[8], c0[8], c1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int o = sub * 8 + j;
-        sc[j] = stats[128 + o]; sh[j] = stats[192 + o]; c0[j] = coef[o]; c1[j] = coef[64 + o];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) wr[j][c] = w4x64[c * 64 + o] * sc[j];               // sc folded into the weights
+    __shared__ float4 cw[64], cb[64];                   // (sc*W[0..3][o]) and (sc, sh, c0, c1) at index j*8 + sub, o = sub*8 + j
+    if (threadIdx.x < 64) {
+        const int o = threadIdx.x, i = (o & 7) * 8 + (o >> 3);
+        const float sc = stats[128 + o];
+        cw[i] = make_float4(w4x64[o] * sc, w4x64[64 + o] * sc, w4x64[128 + o] * sc, w4x64[192 + o] * sc);
+        cb[i] = make_float4(sc, stats[192 + o], coef[o], coef[64 + o]);
     }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
     for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
         float4 x[4];
         float v[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (p0 + u < P) {
-                x[u] = load_narrow<__nv_bfloat16>(dq, p0 + u, 0, nullptr, nullptr, 0, 0);
-                Vec8<__nv_bfloat16>::load(y + (p0 + u) * 64 + sub * 8, v[u]);
-            }
+            const long long p = p0 + u < P ? p0 + u : P - 1;          // clamp: the tail pixels are loaded, not stored
+            x[u] = load_narrow<__nv_bfloat16>(dq, p, 0, nullptr, nullptr, 0, 0);
+            Vec8<__nv_bfloat16>::load(y + p * 64 + sub * 8, v[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (p0 + u >= P) break;
-            float o8[8];
+        for (int j = 0; j < 8; ++j) {
+            asm volatile("" ::: "memory");                                // keep the constant loads where they are used (register pressure)
+            const float4 w = cw[j * 8 + sub], b = cb[j * 8 + sub];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int u = 0; u < 4; ++u) {
                 const float yv = v[u][j];
-                const float dzs = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
-                const float gs = fmaf(yv, sc[j], sh[j]) > 0.f ? dzs : 0.f;
-                o8[j] = gs - fmaf(c1[j], yv, c0[j]);
+                const float dzs = w.x * x[u].x + w.y * x[u].y + w.z * x[u].z + w.w * x[u].w;
+                const float gs = fmaf(yv, b.x, b.y) > 0.f ? dzs : 0.f;
+                v[u][j] = gs - fmaf(b.w, yv, b.z);
             }
-            Vec8<__nv_bfloat16>::store(dy + (p0 + u) * 64 + sub * 8, o8);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (p0 + u < P) Vec8<__nv_bfloat16>::store(dy + (p0 + u) * 64 + sub * 8, v[u]);
     }
 }
 
