@@ -253,6 +253,13 @@ int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t stream);
  * spatial input masking of model.py:541 / :563 is applied on load (frame_flag (B,H) uint8, ch_idx (B) int32). */
 int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
                        long long P, int W, int H, int dtype, cudaStream_t stream);
+/* conv 4 -> 64 + BatchNorm + ReLU in one pass: out = relu(scale * conv(in) + shift).  The batch statistics of the conv output are
+ * known beforehand: the conv is linear in 4 channels, so sarssl_stem_input_stats derives sum(y), sum(y^2) from the input's first and
+ * second moments (one pass over the [P][4] input); feed sums2x64 to sarssl_batchnorm_finalize with nparts = 1. */
+int sarssl_stem_expand_bn_relu(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4,
+                               const float* scale, const float* shift, void* out, long long P, int W, int H, int dtype, cudaStream_t stream);
+int sarssl_stem_input_stats(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, float* sums2x64,
+                            long long P, int W, int H, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* 1x1 conv 64 -> 4 with optional BatchNorm+ReLU of the input applied on load (in_scale/in_shift nullable) */
 int sarssl_stem_reduce(const void* in, const float* in_scale, const float* in_shift, const float* weight4x64, void* out, long long P,
                        int dtype, cudaStream_t stream);

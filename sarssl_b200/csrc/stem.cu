@@ -40,19 +40,24 @@ __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int m
 }
 
 // out[p][o] = sum_c W[o][c] * in[p][c],  o < 64.  8 threads per pixel, 8 channels each.
+// With scale/shift (the BatchNorm of the conv output, batch statistics known beforehand from sarssl_stem_input_stats) the kernel
+// writes relu(scale * (W x) + shift) directly: the pre-BatchNorm tensor is never stored.
 template <typename T>
 __global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__ in, int mode, const uint8_t* __restrict__ flag,
-                                                      const int32_t* __restrict__ ch, const float* __restrict__ Wt, T* __restrict__ out,
-                                                      long long P, int W, int H) {
+                                                      const int32_t* __restrict__ ch, const float* __restrict__ Wt, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, T* __restrict__ out, long long P, int W, int H) {
     __shared__ float ws[64][4];
-    if (threadIdx.x < 256) ws[threadIdx.x >> 2][threadIdx.x & 3] = Wt[threadIdx.x];
+    if (threadIdx.x < 256) ws[threadIdx.x >> 2][threadIdx.x & 3] = Wt[threadIdx.x] * (scale ? scale[threadIdx.x >> 2] : 1.f);
     __syncthreads();
     const int sub = threadIdx.x & 7;
-    float wr[8][4];
+    const bool bn = scale != nullptr;
+    float wr[8][4], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 8; ++j) {
+        sh[j] = bn ? shift[sub * 8 + j] : 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) wr[j][c] = ws[sub * 8 + j][c];
+    }
     // 4 pixels per thread per iteration (independent loads in flight)
     for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
         float4 x[4];
@@ -63,7 +68,10 @@ __global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__
             if (p0 + u >= P) break;
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
+            for (int j = 0; j < 8; ++j) {
+                o[j] = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
+                if (bn) o[j] = fmaxf(o[j] + sh[j], 0.f);
+            }
             Vec8<T>::store(out + (p0 + u) * 64 + sub * 8, o);
         }
     }
@@ -480,6 +488,52 @@ __global__ void __launch_bounds__(256, 3) stem_tail_bwd_apply_kernel(const __nv_
     }
 }
 
+// ---- batch statistics of y = W x without forming y: y is linear in the 4 input channels, so sum_p y and sum_p y^2 follow from the
+// column sums Sx[4] and second moments Mxx[4][4] of the (masked) input.  partials [cta][14] = Sx, then the upper triangle of Mxx.
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_moments_kernel(const void* __restrict__ in, int mode, const uint8_t* __restrict__ flag,
+                                                           const int32_t* __restrict__ ch, float* __restrict__ partials, long long P, int W, int H) {
+    float a[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) a[i] = 0.f;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+        const float4 x = load_narrow<T>(in, p, mode, flag, ch, W, H);
+        a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w;
+        a[4] = fmaf(x.x, x.x, a[4]); a[5] = fmaf(x.x, x.y, a[5]); a[6] = fmaf(x.x, x.z, a[6]); a[7] = fmaf(x.x, x.w, a[7]);
+        a[8] = fmaf(x.y, x.y, a[8]); a[9] = fmaf(x.y, x.z, a[9]); a[10] = fmaf(x.y, x.w, a[10]);
+        a[11] = fmaf(x.z, x.z, a[11]); a[12] = fmaf(x.z, x.w, a[12]); a[13] = fmaf(x.w, x.w, a[13]);
+    }
+    __shared__ float red[8][14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        const float v = warp_sum(a[i]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 14) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * 14 + threadIdx.x] = t;
+    }
+}
+
+// one block of 64 threads (o): out[0][o] = sum_p y[p][o], out[1][o] = sum_p y[p][o]^2  (the [1][2][64] partial-sum layout of batchnorm_finalize)
+__global__ void narrow_moments_finalize_kernel(const float* __restrict__ partials, int nparts, const float* __restrict__ w64x4, float* __restrict__ out) {
+    __shared__ double m[14];
+    if (threadIdx.x < 14) {
+        double t = 0.0;
+        for (int p = 0; p < nparts; ++p) t += (double)partials[(size_t)p * 14 + threadIdx.x];
+        m[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int o = threadIdx.x;
+    const double w0 = w64x4[o * 4], w1 = w64x4[o * 4 + 1], w2 = w64x4[o * 4 + 2], w3 = w64x4[o * 4 + 3];
+    out[o] = (float)(w0 * m[0] + w1 * m[1] + w2 * m[2] + w3 * m[3]);
+    out[64 + o] = (float)(w0 * w0 * m[4] + w1 * w1 * m[8] + w2 * w2 * m[11] + w3 * w3 * m[13] +
+                          2.0 * (w0 * w1 * m[5] + w0 * w2 * m[6] + w0 * w3 * m[7] + w1 * w2 * m[9] + w1 * w3 * m[10] + w2 * w3 * m[12]));
+}
+
 __global__ void stem_reduce_kernel(const float* __restrict__ partials, int nparts, int width, float* __restrict__ out, int accumulate) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= width) return;
@@ -624,13 +678,44 @@ static int pix_grid(K kernel, long long P) {
 
 using namespace sarssl;
 
-extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
-                                  long long P, int W, int H, int dtype, cudaStream_t stream) {
+static int stem_expand_impl(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, const float* scale,
+                            const float* shift, void* out, long long P, int W, int H, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0 && P < 0xFFFFFFFFLL, "stem_expand: bad arguments (P must be in (0, 2^32))");
     SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
-    if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(pw_expand_kernel<float>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (float*)out, P, W, H);
-    else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(pw_expand_kernel<__nv_bfloat16>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, (__nv_bfloat16*)out, P, W, H);
+    if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(pw_expand_kernel<float>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, scale, shift, (float*)out, P, W, H);
+    else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(pw_expand_kernel<__nv_bfloat16>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, scale, shift, (__nv_bfloat16*)out, P, W, H);
     else { set_last_error("stem_expand: bad dtype"); return SARSSL_ERR_ARG; }
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
+                                  long long P, int W, int H, int dtype, cudaStream_t stream) {
+    return stem_expand_impl(in, mode, frame_flag, ch_idx, weight64x4, nullptr, nullptr, out, P, W, H, dtype, stream);
+}
+
+// out = relu(scale * conv1x1(in) + shift): conv + BatchNorm + ReLU in one pass (the BatchNorm statistics come from sarssl_stem_input_stats)
+extern "C" int sarssl_stem_expand_bn_relu(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4,
+                                          const float* scale, const float* shift, void* out, long long P, int W, int H, int dtype, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(scale && shift, "stem_expand_bn_relu: scale / shift missing");
+    return stem_expand_impl(in, mode, frame_flag, ch_idx, weight64x4, scale, shift, out, P, W, H, dtype, stream);
+}
+
+// sums[0][o] = sum_p y[p][o], sums[1][o] = sum_p y[p][o]^2 of y = conv1x1(in) (64 outputs) from the input's first and second moments
+extern "C" int sarssl_stem_input_stats(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, float* sums2x64,
+                                       long long P, int W, int H, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SARSSL_CHECK_ARG(in && weight64x4 && sums2x64 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_input_stats: bad arguments (P must be in (0, 2^32))");
+    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_input_stats: mode %d needs masks", mode);
+    SARSSL_CHECK_ARG(dtype == SARSSL_F32 || dtype == SARSSL_BF16, "stem_input_stats: bad dtype");
+    long long g = (P + 255) / 256;
+    const long long cap = dtype == SARSSL_F32 ? resident_ctas(narrow_moments_kernel<float>, 256) : resident_ctas(narrow_moments_kernel<__nv_bfloat16>, 256);
+    const int grid = (int)(g < cap ? g : cap);
+    if (workspace_bytes < (size_t)grid * 14 * sizeof(float)) { set_last_error("stem_input_stats: workspace too small"); return SARSSL_ERR_WORKSPACE; }
+    float* partials = static_cast<float*>(workspace);
+    if (dtype == SARSSL_F32) narrow_moments_kernel<float><<<grid, 256, 0, stream>>>(in, mode, frame_flag, ch_idx, partials, P, W, H);
+    else narrow_moments_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(in, mode, frame_flag, ch_idx, partials, P, W, H);
+    SARSSL_LAUNCH_CHECK();
+    narrow_moments_finalize_kernel<<<1, 64, 0, stream>>>(partials, grid, weight64x4, sums2x64);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -136,15 +136,21 @@ class Engine:
         k, st = self.k, self.store
         pe = enc + ".patch_embed"
         M, P = B * T, B * T * F
-        y1 = k.empty(P, CNN_CH)
-        k.stem_expand(patches, mode, flag, ch, st.p(f"{pe}.0.weight"), y1, P, F, T)
-        s1 = self._bn(f"{pe}.1", y1, P, CNN_CH, training)
-        y2, y3, z1, z2 = k.empty(P, CNN_CH), k.empty(P, CNN_CH), None, None
-        if k.conv_tc:            # tensor-core path: TMA feeds the MMA directly, so BatchNorm+ReLU is materialised once (bf16) first
+        y1, y2, y3, z1, z2 = None, k.empty(P, CNN_CH), k.empty(P, CNN_CH), None, None
+        if k.conv_tc:
+            # tensor-core path: TMA feeds the MMA directly, so BatchNorm+ReLU outputs are materialised (bf16).  The first layer is linear
+            # in 4 channels: its BatchNorm statistics come from the input's moments and conv+BN+ReLU is one pass; y1 is never stored.
             z1 = k.empty(P, CNN_CH)
-            k.bn_act_fwd(y1, s1, ACT_RELU, z1, P, CNN_CH)
+            if training:
+                s1 = k.stem_input_bn_stats(patches, mode, flag, ch, st.p(f"{pe}.0.weight"), P, F, T, self._bn_args(f"{pe}.1"))
+            else:
+                s1 = self._bn(f"{pe}.1", z1, P, CNN_CH, False)          # running statistics; the tensor argument is not read
+            k.stem_expand_bn_relu(patches, mode, flag, ch, st.p(f"{pe}.0.weight"), s1, z1, P, F, T)
             s2 = k.conv3x3_tc(z1, self.W[f"{pe}.3.fwd"], y2, B, T, F, bn=self._bn_args(f"{pe}.4") if training else None)    # BN statistics fused in the epilogue
         else:                    # CUDA-core path applies BatchNorm+ReLU while loading the operand tile
+            y1 = k.empty(P, CNN_CH)
+            k.stem_expand(patches, mode, flag, ch, st.p(f"{pe}.0.weight"), y1, P, F, T)
+            s1 = self._bn(f"{pe}.1", y1, P, CNN_CH, training)
             k.conv3x3(y1, s1, self.W[f"{pe}.3.fwd"], y2, B, T, F)
             s2 = None
         if s2 is None:

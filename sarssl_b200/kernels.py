@@ -174,6 +174,21 @@ class KernelSet:
     def stem_expand(self, x, mode, flag, ch, w64x4, out, P, W, H):
         self._ok(self.L.sarssl_stem_expand(ptr(x), mode, ptr(flag), ptr(ch), ptr(w64x4), ptr(out), P, W, H, self.dt, self.stream), "stem_expand")
 
+    def stem_expand_bn_relu(self, x, mode, flag, ch, w64x4, stats, out, P, W, H):
+        self._ok(self.L.sarssl_stem_expand_bn_relu(ptr(x), mode, ptr(flag), ptr(ch), ptr(w64x4), _addr(stats, 2 * 64), _addr(stats, 3 * 64), ptr(out), P, W, H,
+                                                   self.dt, self.stream), "stem_expand_bn_relu")
+
+    def stem_input_bn_stats(self, x, mode, flag, ch, w64x4, P, W, H, bn):
+        """Batch statistics (and running-stat update) of BatchNorm(conv1x1(x)) from the moments of x; bn = (gamma, beta, rmean, rvar, nbt)."""
+        sums = torch.empty(2 * 64, dtype=torch.float32, device=self.dev)
+        self._ok(self.L.sarssl_stem_input_stats(ptr(x), mode, ptr(flag), ptr(ch), ptr(w64x4), ptr(sums), P, W, H, self.dt, ptr(self.ws), self.ws.numel(),
+                                                self.stream), "stem_input_stats")
+        stats = torch.empty(4 * 64, dtype=torch.float32, device=self.dev)
+        self._ok(self.L.sarssl_batchnorm_finalize(ptr(sums), 1, P, 64, ptr(bn[0]), ptr(bn[1]), 1e-5, 0.1, ptr(bn[2]), ptr(bn[3]), ptr(bn[4]),
+                                                  ptr(stats), self.stream), "batchnorm_finalize")
+        self.launches += 2
+        return stats
+
     def stem_reduce(self, x, stats, w4x64, out, P):
         sc = _addr(stats, 2 * 64) if stats is not None else None
         sh = _addr(stats, 3 * 64) if stats is not None else None

@@ -189,3 +189,32 @@ def test_stem_tail_backward_fused_vs_autograd(B, H, W):
         assert rel(dy.float().cpu(), y.grad) < 6e-3, rel(dy.float().cpu(), y.grad)
         assert rel(dw.cpu(), rep * w.grad) < 1e-3, rel(dw.cpu(), rep * w.grad)
         assert rel(dg.cpu(), rep * gamma.grad) < 1e-3 and rel(db.cpu(), rep * beta.grad) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,mode", [(2, 16, 256, 1), (2, 16, 256, 2), (3, 5, 130, 3), (1, 3, 37, 3)])
+def test_stem_first_layer_stats_from_input_moments(dtype, B, H, W, mode):
+    """BatchNorm statistics of conv1x1(x) from the moments of x == statistics of the materialised conv output (fp32 tensor), including the
+    running-stat update; conv+BN+ReLU in one pass == the three separate kernels."""
+    k, k32 = KernelSet(DEV, dtype), KernelSet(DEV, torch.float32)
+    g = torch.Generator().manual_seed(B * 100 + H + mode)
+    P = B * H * W
+    x = (torch.randn(P, 4, generator=g) + 0.4).to(DEV)
+    flag = ch = None
+    if mode != 3:
+        flag = (torch.rand(B * H, generator=g) < 0.5).to(torch.uint8).to(DEV)
+        ch = torch.randint(0, 2, (B,), generator=g, dtype=torch.int32).to(DEV)
+    w = (torch.randn(64, 4, generator=g) * 0.5).to(DEV)
+    gamma, beta = (torch.rand(64, generator=g) + 0.5).to(DEV), (torch.randn(64, generator=g) * 0.2).to(DEV)
+    bn_a = (gamma, beta, torch.zeros(64, device=DEV), torch.ones(64, device=DEV), torch.zeros(1, dtype=torch.long, device=DEV))
+    bn_b = (gamma, beta, torch.zeros(64, device=DEV), torch.ones(64, device=DEV), torch.zeros(1, dtype=torch.long, device=DEV))
+    y = torch.empty(P, 64, device=DEV)
+    k32.stem_expand(x, mode, flag, ch, w, y, P, W, H)
+    ref = k32.bn_stats(y, P, 64, *bn_a, True)
+    got = k.stem_input_bn_stats(x, mode, flag, ch, w, P, W, H, bn_b)
+    assert rel(got[:64].cpu(), ref[:64].cpu()) < 1e-5 and rel(got[64:].cpu(), ref[64:].cpu()) < 1e-4
+    assert rel(bn_b[2].cpu(), bn_a[2].cpu()) < 1e-5 and rel(bn_b[3].cpu(), bn_a[3].cpu()) < 1e-5 and int(bn_b[4]) == 1
+    z_ref = torch.relu(y * ref[128:192] + ref[192:256])
+    z = torch.empty(P, 64, device=DEV, dtype=dtype)
+    k.stem_expand_bn_relu(x, mode, flag, ch, w, ref, z, P, W, H)
+    assert rel(z.float().cpu(), z_ref.cpu()) < (1e-5 if dtype == torch.float32 else 4e-3)
