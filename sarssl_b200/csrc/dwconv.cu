@@ -6,49 +6,83 @@
 // Tiles of 64 time steps x 64 channels are staged in shared memory with their halo; threads run along channels so
 // global accesses are coalesced and shared-memory accesses conflict-free.
 #include "common.cuh"
+#include "vec.cuh"
 
 namespace sarssl {
 
-constexpr int kDwT = 64, kDwD = 64, kDwMaxK = 31;
+constexpr int kDwT = 64, kDwD = 64, kDwMaxK = 31, kDwRows = kDwT + kDwMaxK - 1, kDwPer = kDwT / 4;
 
+// rows [t0 - pad, t0 - pad + nrows) x channels [d0, d0 + 64) of `in` -> tile (fp32), zero outside the sequence / channel range.
+// 16-byte loads when D % 8 == 0.
+template <typename T>
+__device__ __forceinline__ void dw_stage(const T* __restrict__ in, float (*tile)[kDwD], int nrows, int b, int t_first, int d0, int Tn, int D) {
+    if ((D & 7) == 0) {
+        for (int c = threadIdx.x; c < nrows * 8; c += 256) {
+            const int r = c >> 3, ch = (c & 7) * 8, t = t_first + r, d = d0 + ch;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (t >= 0 && t < Tn && d < D) Vec8<T>::load(in + ((long long)b * Tn + t) * D + d, v);
+            *reinterpret_cast<float4*>(&tile[r][ch]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(&tile[r][ch + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else {
+        const int dl = threadIdx.x & 63, d = d0 + dl;
+        for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
+            const int t = t_first + r;
+            tile[r][dl] = (d < D && t >= 0 && t < Tn) ? to_f32(in[((long long)b * Tn + t) * D + d]) : 0.f;
+        }
+    }
+}
+
+// Thread (channel dl, time group tg) produces 16 consecutive outputs of its channel: the 31 taps live in registers and every staged
+// input is read from shared memory once per thread (46 loads for 496 FMAs; the kernel is FMA-, not shared-memory-bound).
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, T* __restrict__ out, int B, int Tn, int D,
                                                    int K, int flip) {
-    __shared__ float tile[kDwT + kDwMaxK - 1][kDwD];
-    __shared__ float ws[kDwMaxK][kDwD];
+    __shared__ __align__(16) float tile[kDwRows][kDwD];
     const int pad = (K - 1) / 2;
     const int d0 = blockIdx.x * kDwD, t0 = blockIdx.y * kDwT, b = blockIdx.z;
     const int dl = threadIdx.x & 63, tg = threadIdx.x >> 6;
     const int d = d0 + dl;
-    for (int k = tg; k < K; k += 4) ws[k][dl] = d < D ? w[(long long)d * K + (flip ? K - 1 - k : k)] : 0.f;
-    for (int r = tg; r < kDwT + K - 1; r += 4) {
-        const int t = t0 + r - pad;
-        tile[r][dl] = (d < D && t >= 0 && t < Tn) ? to_f32(in[((long long)b * Tn + t) * D + d]) : 0.f;
-    }
+    dw_stage<T>(in, tile, kDwRows, b, t0 - pad, d0, Tn, D);          // all 94 rows (finite data or zeros) whatever K is
+    float wr[kDwMaxK];
+#pragma unroll
+    for (int k = 0; k < kDwMaxK; ++k) wr[k] = (k < K && d < D) ? w[(long long)d * K + (flip ? K - 1 - k : k)] : 0.f;
     __syncthreads();
     if (d >= D) return;
-    for (int tt = tg; tt < kDwT; tt += 4) {
-        const int t = t0 + tt;
-        if (t >= Tn) break;
-        float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc = fmaf(ws[k][dl], tile[tt + k][dl], acc);
-        out[((long long)b * Tn + t) * D + d] = from_f32<T>(acc);
+    const int tb = tg * kDwPer;
+    float acc[kDwPer];
+#pragma unroll
+    for (int o = 0; o < kDwPer; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kDwPer + kDwMaxK - 1; ++r) {
+        const float x = tile[tb + r][dl];
+#pragma unroll
+        for (int o = 0; o < kDwPer; ++o)
+            if (r - o >= 0 && r - o < kDwMaxK) acc[o] = fmaf(wr[r - o], x, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < kDwPer; ++o) {
+        const int t = t0 + tb + o;
+        if (t < Tn) out[((long long)b * Tn + t) * D + d] = from_f32<T>(acc[o]);
     }
 }
 
-// grid (D/64, nchunks); CTA loops over (b, t-tile) pairs chunk-strided; partials [nchunks][D][K]
+// grid (D/64, nchunks); CTA loops over (b, t-tile) pairs chunk-strided; partials [nchunks][D][K].  Same register blocking as the
+// forward kernel with the roles swapped: 16 output gradients in registers, inputs streamed once, 31 tap accumulators.
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__ a, const T* __restrict__ dc, float* __restrict__ partials, int B,
                                                          int Tn, int D, int K) {
     // 40 KB: staged tiles; re-used for the cross-thread reduction at the end (4*31*64 floats fit)
-    __shared__ float buf[(kDwT + kDwMaxK - 1 + kDwT) * kDwD];
+    __shared__ __align__(16) float buf[(kDwRows + kDwT) * kDwD];
     float (*ta)[kDwD] = reinterpret_cast<float (*)[kDwD]>(buf);
-    float (*tdc)[kDwD] = reinterpret_cast<float (*)[kDwD]>(buf + (kDwT + kDwMaxK - 1) * kDwD);
+    float (*tdc)[kDwD] = reinterpret_cast<float (*)[kDwD]>(buf + kDwRows * kDwD);
     float (*red)[kDwMaxK][kDwD] = reinterpret_cast<float (*)[kDwMaxK][kDwD]>(buf);
     const int pad = (K - 1) / 2;
     const int d0 = blockIdx.x * kDwD;
     const int dl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-    const int d = d0 + dl;
+    const int d = d0 + dl, tb = tg * kDwPer;
     float acc[kDwMaxK];
 #pragma unroll
     for (int k = 0; k < kDwMaxK; ++k) acc[k] = 0.f;
@@ -57,20 +91,18 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__
     for (long long wk = blockIdx.y; wk < nwork; wk += gridDim.y) {
         const int b = (int)(wk / ntile), t0 = (int)(wk % ntile) * kDwT;
         __syncthreads();
-        for (int r = tg; r < kDwT + K - 1; r += 4) {
-            const int t = t0 + r - pad;
-            ta[r][dl] = (d < D && t >= 0 && t < Tn) ? to_f32(a[((long long)b * Tn + t) * D + d]) : 0.f;
-        }
-        for (int r = tg; r < kDwT; r += 4) {
-            const int t = t0 + r;
-            tdc[r][dl] = (d < D && t < Tn) ? to_f32(dc[((long long)b * Tn + t) * D + d]) : 0.f;
-        }
+        dw_stage<T>(a, ta, kDwRows, b, t0 - pad, d0, Tn, D);
+        dw_stage<T>(dc, tdc, kDwT, b, t0, d0, Tn, D);
         __syncthreads();
-        for (int tt = tg * (kDwT / 4); tt < (tg + 1) * (kDwT / 4); ++tt) {
-            const float g = tdc[tt][dl];
+        float g[kDwPer];
 #pragma unroll
-            for (int k = 0; k < kDwMaxK; ++k)
-                if (k < K) acc[k] = fmaf(g, ta[tt + k][dl], acc[k]);
+        for (int o = 0; o < kDwPer; ++o) g[o] = tdc[tb + o][dl];
+#pragma unroll
+        for (int r = 0; r < kDwPer + kDwMaxK - 1; ++r) {
+            const float x = ta[tb + r][dl];
+#pragma unroll
+            for (int o = 0; o < kDwPer; ++o)
+                if (r - o >= 0 && r - o < kDwMaxK) acc[r - o] = fmaf(g[o], x, acc[r - o]);
         }
     }
     __syncthreads();

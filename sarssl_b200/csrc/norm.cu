@@ -58,67 +58,80 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, lo
 }
 
 // ---------------------------------------------------------------- LayerNorm backward
-// dx = add + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  partial dgamma/dbeta per CTA
-template <typename T>
+// dx = add + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  partial dgamma/dbeta per CTA.
+// One warp per row; NCH = 256-column chunks per row (compile time, so a 256-wide model does not pay the registers of a 1024-wide
+// one) and R rows in flight per warp: all loads of the R rows are issued before the first reduction (the kernel is latency-bound).
+template <typename T, int NCH, int R>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                    const float* __restrict__ gamma, const T* __restrict__ add, T* __restrict__ dx,
                                                    float* __restrict__ partials, int rows, int cols) {
     __shared__ float sh[8][2][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float dg[kLnChunks][8], db[kLnChunks][8], gm[kLnChunks][8];
+    float dg[NCH][8], db[NCH][8], gm[NCH][8];
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = c * 256 + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; gm[c][j] = 0.f; }
         if (col < cols) load8f(gamma + col, gm[c]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { dg[c][j] = 0.f; db[c][j] = 0.f; }
     }
-    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-        const T* dyr = dy + (long long)row * lddy;
-        const T* xr = x + (long long)row * ldx;
-        const float mu = mean[row], rs = rstd[row];
-        float g[kLnChunks][8], xh[kLnChunks][8];
-        float s1 = 0.f, s2 = 0.f;
+    const int rstride = gridDim.x * 8;
+    for (int row0 = blockIdx.x * 8 + warp; row0 < rows; row0 += rstride * R) {
+        float d[R][NCH][8], xv[R][NCH][8], av[R][NCH][8];
+        float mu[R], rs[R];
 #pragma unroll
-        for (int c = 0; c < kLnChunks; ++c) {
-            const int col = c * 256 + lane * 8;
-            if (col < cols) {
-                float d[8], xv[8];
-                Vec8<T>::load(dyr + col, d);
-                Vec8<T>::load(xr + col, xv);
+        for (int q = 0; q < R; ++q) {
+            const int row = row0 + q * rstride;
+            const bool ok = row < rows;
+            mu[q] = ok ? mean[row] : 0.f; rs[q] = ok ? rstd[row] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    xh[c][j] = (xv[j] - mu) * rs;
-                    g[c][j] = d[j] * gm[c][j];
-                    dg[c][j] += d[j] * xh[c][j];
-                    db[c][j] += d[j];
-                    s1 += g[c][j];
-                    s2 += g[c][j] * xh[c][j];
+            for (int c = 0; c < NCH; ++c) {
+                const int col = c * 256 + lane * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { d[q][c][j] = 0.f; xv[q][c][j] = 0.f; av[q][c][j] = 0.f; }
+                if (ok && col < cols) {
+                    Vec8<T>::load(dy + (long long)row * lddy + col, d[q][c]);
+                    Vec8<T>::load(x + (long long)row * ldx + col, xv[q][c]);
+                    if (add) Vec8<T>::load(add + (long long)row * cols + col, av[q][c]);
                 }
             }
         }
-        s1 = warp_sum(s1) / cols;
-        s2 = warp_sum(s2) / cols;
 #pragma unroll
-        for (int c = 0; c < kLnChunks; ++c) {
-            const int col = c * 256 + lane * 8;
-            if (col < cols) {
-                float o[8];
+        for (int q = 0; q < R; ++q) {
+            const int row = row0 + q * rstride;
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
-                if (add) {
-                    float av[8];
-                    Vec8<T>::load(add + (long long)row * cols + col, av);
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += av[j];
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xv[q][c][j] - mu[q]) * rs[q];
+                    const float g = d[q][c][j] * gm[c][j];
+                    dg[c][j] = fmaf(d[q][c][j], xh, dg[c][j]);
+                    db[c][j] += d[q][c][j];
+                    s1 += g;
+                    s2 = fmaf(g, xh, s2);
+                    xv[q][c][j] = xh; d[q][c][j] = g;
                 }
-                Vec8<T>::store(dx + (long long)row * cols + col, o);
+            s1 = warp_sum(s1) / cols;
+            s2 = warp_sum(s2) / cols;
+            if (row < rows) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int col = c * 256 + lane * 8;
+                    if (col < cols) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = av[q][c][j] + rs[q] * (d[q][c][j] - s1 - xv[q][c][j] * s2);
+                        Vec8<T>::store(dx + (long long)row * cols + col, o);
+                    }
+                }
             }
         }
     }
     // reduce the 8 warps' dgamma/dbeta, one 256-column chunk at a time
-    for (int c = 0; c < kLnChunks; ++c) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
         if (c * 256 >= cols) break;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sh[warp][0][lane * 8 + j] = dg[c][j]; sh[warp][1][lane * 8 + j] = db[c][j]; }
@@ -453,17 +466,24 @@ extern "C" int sarssl_layernorm_bwd(const void* dy, long long lddy, const void* 
     SARSSL_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
     SARSSL_CHECK_ARG(cols <= 256 * kLnChunks && cols % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0, "layernorm_bwd: cols=%d must be a multiple of 8, <= %d", cols,
                      256 * kLnChunks);
-    int grid = capped_grid(rows, 8 * 4, 64);
-    {
-        const int cap = dtype == SARSSL_F32 ? resident_ctas(ln_bwd_kernel<float>, 256) : resident_ctas(ln_bwd_kernel<__nv_bfloat16>, 256);
-        if (grid > cap) grid = cap;
-    }
-    if (workspace_bytes < (size_t)grid * 2 * cols * sizeof(float)) { set_last_error("layernorm_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
-    DISPATCH_T(dtype, (ln_bwd_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(dy), lddy, static_cast<const T*>(x), ldx, mean, rstd, gamma,
-                                                               static_cast<const T*>(add), static_cast<T*>(dx), partials, rows, cols)));
+#define LN_BWD_LAUNCH(NCH, R)                                                                                                                    \
+    do {                                                                                                                                         \
+        int grid = capped_grid(rows, 8 * R, 64);                                                                                                 \
+        const int cap = dtype == SARSSL_F32 ? resident_ctas(ln_bwd_kernel<float, NCH, R>, 256) : resident_ctas(ln_bwd_kernel<__nv_bfloat16, NCH, R>, 256); \
+        if (grid > cap) grid = cap;                                                                                                              \
+        if (workspace_bytes < (size_t)grid * 2 * cols * sizeof(float)) { set_last_error("layernorm_bwd: workspace too small"); return SARSSL_ERR_WORKSPACE; } \
+        DISPATCH_T(dtype, (ln_bwd_kernel<T, NCH, R><<<grid, 256, 0, stream>>>(static_cast<const T*>(dy), lddy, static_cast<const T*>(x), ldx, mean, rstd, gamma, \
+                                                                            static_cast<const T*>(add), static_cast<T*>(dx), partials, rows, cols)));    \
+        nparts = grid;                                                                                                                           \
+    } while (0)
+    int nparts = 0;
+    if (cols <= 256) LN_BWD_LAUNCH(1, 2);
+    else if (cols <= 512) LN_BWD_LAUNCH(2, 1);
+    else LN_BWD_LAUNCH(4, 1);
+#undef LN_BWD_LAUNCH
     SARSSL_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(2 * cols + 31) / 32, 256, 0, stream>>>(partials, grid, 2 * cols, dgamma, dbeta, cols, 1);
+    reduce_partials_kernel<<<(2 * cols + 31) / 32, 256, 0, stream>>>(partials, nparts, 2 * cols, dgamma, dbeta, cols, 1);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
