@@ -39,11 +39,30 @@ __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int m
     return x;
 }
 
+// The mask of modes 1 / 2 depends only on the pixel's image row (frame): bit c set = channel c is zeroed.
+__device__ __forceinline__ unsigned narrow_zero_bits(long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
+    if (mode != 1 && mode != 2) return 0u;
+    const unsigned up = (unsigned)p, uw = (unsigned)W;
+    const unsigned row = ((uw & (uw - 1)) == 0) ? (up >> (31 - __clz((int)uw))) : up / uw;
+    const bool pm = flag[row] != 0;
+    if (mode == 2) return pm ? 0xFu : 0u;
+    const int mc = ch[row / (unsigned)H];
+    const int keep = pm ? 1 - mc : mc;
+    return keep == 0 ? 0xAu : 0x5u;                            // keep microphone 0: zero (re1, im1) = channels 1, 3
+}
+__device__ __forceinline__ float4 apply_zero_bits(float4 x, unsigned z) {
+    if (z & 1u) x.x = 0.f;
+    if (z & 2u) x.y = 0.f;
+    if (z & 4u) x.z = 0.f;
+    if (z & 8u) x.w = 0.f;
+    return x;
+}
+
 // out[p][o] = sum_c W[o][c] * in[p][c],  o < 64.  8 threads per pixel, 8 channels each.
 // With scale/shift (the BatchNorm of the conv output, batch statistics known beforehand from sarssl_stem_input_stats) the kernel
 // writes relu(scale * (W x) + shift) directly: the pre-BatchNorm tensor is never stored.
 template <typename T>
-__global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__ in, int mode, const uint8_t* __restrict__ flag,
+__global__ void __launch_bounds__(256, 3) pw_expand_kernel(const void* __restrict__ in, int mode, const uint8_t* __restrict__ flag,
                                                       const int32_t* __restrict__ ch, const float* __restrict__ Wt, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, T* __restrict__ out, long long P, int W, int H) {
     __shared__ float ws[64][4];
@@ -61,8 +80,16 @@ __global__ void __launch_bounds__(256) pw_expand_kernel(const void* __restrict__
     // 4 pixels per thread per iteration (independent loads in flight)
     for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
         float4 x[4];
+        if ((W & 3) == 0) {                // the 4 consecutive pixels share an image row: one mask lookup (p0 % 4 == 0)
+            const unsigned zb = narrow_zero_bits(p0, mode, flag, ch, W, H);
+            const int lm = (mode == 1 || mode == 2) ? 3 : mode;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = (p0 + u < P) ? load_narrow<T>(in, p0 + u, mode, flag, ch, W, H) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 4; ++u)
+                x[u] = (p0 + u < P) ? apply_zero_bits(load_narrow<T>(in, p0 + u, lm, nullptr, nullptr, W, H), zb) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = (p0 + u < P) ? load_narrow<T>(in, p0 + u, mode, flag, ch, W, H) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (p0 + u >= P) break;
