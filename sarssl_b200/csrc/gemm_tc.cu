@@ -492,8 +492,8 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     // split-K: weight gradients (fp32 accumulate, plain epilogue) have few output tiles and a very long K
     const int num_kb = (a->K + TBK - 1) / TBK;
     int splitk = 1;
-    if (e.accumulate && !e.c_is_bf16 && !a->pre_out && !a->resid && !a->bias && a->act == 0 && a->drop_p == 0.f && nbatch == 1) {
-        const long long tiles = (long long)((a->N + BN - 1) / BN) * ((a->M + TBM - 1) / TBM);
+    if (e.accumulate && !e.c_is_bf16 && !a->pre_out && !a->resid && !a->bias && a->act == 0 && a->drop_p == 0.f) {
+        const long long tiles = (long long)((a->N + BN - 1) / BN) * ((a->M + TBM - 1) / TBM) * nbatch;
         const long long want = ((tiles <= 16 ? 3LL : 4LL) * sm_count() + tiles - 1) / tiles;     // 3-4 work items per SM balance best (measured)
         splitk = (int)(want < 1 ? 1 : want);
         if (splitk > num_kb / 4) splitk = num_kb / 4 > 0 ? num_kb / 4 : 1;       // at least 4 k-blocks per slice

@@ -428,9 +428,15 @@ class Engine:
         # dK[b, j, h, :] = sum_i dscore[b, h, i, j] * (q + u)[b, i, h, :]
         k.gemm(dattn, rec["qu"], dqkv, T, dh_, T, (1, T), (1, D), 3 * D, c_off=D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * D, dh_), sCb=(T * 3 * D, dh_))
         k.gemm(dpos, rec["pp"], dqv, T, dh_, T, (T, 1), (1, D), D, batch=(B, H), sAb=(T * T, B * T * T), sBb=(0, dh_), sCb=(T * D, dh_))
-        dpp = k.empty(T, D)
-        # dPproj[k, h*dh + d] = sum_{b,i} dpos[h][b][i][k] * (q + v)[b, i, h, d]   (one GEMM per head over all B*T rows)
-        k.gemm(dpos, rec["qv"], dpp, T, dh_, B * T, (1, T), (1, D), D, batch=(1, H), sAb=(0, B * T * T), sBb=(0, dh_), sCb=(0, dh_))
+        # dPproj[k, h*dh + d] = sum_{b,i} dpos[h][b][i][k] * (q + v)[b, i, h, d]   (one GEMM per head over all B*T rows; only H x 2 output
+        # tiles with K = B*T, so it accumulates in fp32 through split-K)
+        dpp32 = torch.zeros(T, D, dtype=torch.float32, device=self.dev)
+        k.gemm(dpos, rec["qv"], dpp32, T, dh_, B * T, (1, T), (1, D), D, batch=(1, H), sAb=(0, B * T * T), sBb=(0, dh_), sCb=(0, dh_), accumulate=True)
+        if self.dtype == torch.float32:
+            dpp = dpp32
+        else:
+            dpp = k.empty(T, D)
+            k.cast(dpp32, dpp, T * D)
         k.colsum(dqu, D, st.g(a + ".u_bias").view(D), M, D)
         k.colsum(dqv, D, st.g(a + ".v_bias").view(D), M, D)
         k.add2(dqu, D, dqv, D, dqkv, 3 * D, M, D)
