@@ -48,6 +48,61 @@ class Learner(CheckpointMixin, ABC):
         from .parallel import GradientSync
         self.grad_sync = GradientSync.create(self.model)
 
+    def device_batches(self, dataset):
+        """Input pipeline step in front of the path (the reference leaves it to DataLoader + a blocking `.to(device)` inside
+        data_preprocess, learner.py:530): host tensors of batch i+1 are copied to the device on a side stream while batch i is
+        being computed, so the H2D transfer (134 MB for 256 clips) never sits on the compute stream.  Items keep their structure
+        (list / tuple / dict of tensors); pinned host tensors copy asynchronously, pageable ones still overlap with the device work
+        already queued.  Device tensors pass through untouched."""
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            yield from dataset
+            return
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = self._copy_stream
+
+        def move(obj, moved):
+            if torch.is_tensor(obj):
+                if obj.device.type == "cuda":
+                    return obj
+                t = obj.to(dev, non_blocking=True)
+                moved.append(t)
+                return t
+            if isinstance(obj, dict):
+                return {k: move(v, moved) for k, v in obj.items()}
+            if isinstance(obj, (list, tuple)):
+                return type(obj)(move(v, moved) for v in obj)
+            return obj
+
+        def stage(item):
+            moved = []
+            with torch.cuda.stream(copy_stream):
+                out = move(item, moved)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return out, moved, ev
+
+        it = iter(dataset)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = stage(next(it))            # enqueue the next copy before handing out the current batch
+            except StopIteration:
+                nxt = None
+            out, moved, ev = cur
+            compute = torch.cuda.current_stream(dev)
+            compute.wait_event(ev)
+            for t in moved:
+                t.record_stream(compute)         # allocated on the copy stream, consumed on the compute stream
+            yield out
+
     def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True):
         """learner.py:76-131: one epoch of pre-training.  A fresh Adam (moments reset) per epoch like the reference; loss / diff
         of every step are kept on the device and read back once at the end of the epoch (the reference syncs 3x per step)."""
@@ -57,7 +112,7 @@ class Learner(CheckpointMixin, ABC):
         optimizer.zero_grad()
         sync = getattr(self, "grad_sync", None)
         log, vis_batch = [], None
-        for batch_idx, (mic_sig_batch,) in enumerate(dataset):
+        for batch_idx, (mic_sig_batch,) in enumerate(self.device_batches(dataset)):
             in_batch, = self.data_preprocess(mic_sig_batch, None)
             loss_batch, diff_batch, vis_batch = self.model(in_batch)
             loss_batch.backward()
@@ -76,7 +131,7 @@ class Learner(CheckpointMixin, ABC):
         self.model.eval()
         log, vis_batch = [], None
         with torch.no_grad():
-            for data in dataset:
+            for data in self.device_batches(dataset):
                 in_batch, = self.data_preprocess(data[0], None)
                 loss_batch, diff_batch, vis_batch = self.model(in_batch)
                 log.append(torch.stack([loss_batch, diff_batch]))
@@ -142,7 +197,7 @@ class STFTLearner(Learner):
         optimizer.zero_grad()
         sync = getattr(self, "grad_sync", None)
         losses, metrics = [], []
-        for mic_sig_batch, gt_batch in dataset:
+        for mic_sig_batch, gt_batch in self.device_batches(dataset):
             in_batch, tar_batch = self.data_preprocess(mic_sig_batch, gt_batch)
             pred_batch, embed_batch = self.model(in_batch)
             loss_batch = self.loss(pred_batch=pred_batch, gt_batch=tar_batch)
@@ -162,7 +217,7 @@ class STFTLearner(Learner):
         self.model.eval()
         losses, metrics, embed, gt = [], [], [], []
         with torch.no_grad():
-            for mic_sig_batch, gt_batch in dataset:
+            for mic_sig_batch, gt_batch in self.device_batches(dataset):
                 in_batch, tar_batch = self.data_preprocess(mic_sig_batch, gt_batch)
                 pred_batch, embed_batch = self.model(in_batch)
                 losses.append(self.loss(pred_batch=pred_batch, gt_batch=tar_batch))
