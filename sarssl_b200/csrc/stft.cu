@@ -157,6 +157,119 @@ __global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const flo
     }
 }
 
+// ---------------- pipelined fused kernel -------------------------------------------------------------------------------------
+// Same work split as stft_frontend_fused_kernel (item = kPF consecutive frames of one clip, one frame per 64-lane group), but the
+// three latencies that kernel exposes are overlapped inside the CTA:
+//   * the bulk-TMA load of item n+1 is in flight while item n is transformed            (double-buffered input);
+//   * the per-clip rendezvous and the scaled store of item n-1 happen after item n has been transformed and published, so the
+//     other CTAs working on that clip had a whole transform's time to arrive          (double-buffered un-scaled output).
+// Items are assigned statically, item(n) = blockIdx.x + n * gridDim.x, with gridDim.x >= items per clip: a CTA owns at most one
+// item of any clip, items n-1 and n+1 lie in different clips, and a CTA only ever waits for a clip after publishing everything it
+// has transformed - with all CTAs resident the rendezvous cannot dead-lock (induction over the clip index).
+constexpr int kPF = 4;
+struct PipeSmem {
+    float2 in[2][(kPF + 1) * kHop];               // 2 x 10 KB  staged samples (ch0, ch1)
+    float4 out[2][kPF * kHop];                    // 2 x 16 KB  un-scaled bins 1..256, (re0, re1, im0, im1)
+    float scratch[kGroups][kFftScratchFloats];    // 18 KB
+    float red[32];
+    uint64_t bar[2];
+    float scale;
+};
+
+__global__ void __launch_bounds__(kThreads) stft_frontend_pipe_kernel(const float* __restrict__ sig, float4* __restrict__ out,
+                                                                    float* partials, unsigned* counters, int nb,
+                                                                    long long nsample, int nt, int ipc, float eps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
+    const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
+    FftLane lane;
+    lane.init(l);
+    float* sre = sm.scratch[g];
+    float* sim = sre + kFftPlane;
+    const long long nitems = (long long)nb * ipc;
+    auto issue_load = [&](long long item, int buf) {          // thread 0 only
+        const int b = (int)(item / ipc), fb = (int)(item - (long long)b * ipc);
+        const int f0 = fb * kPF, nfr = min(kPF, nt - f0);
+        const uint32_t bytes = (uint32_t)(nfr + 1) * kHop * sizeof(float2);
+        mbar_expect_tx(&sm.bar[buf], bytes);
+        tma_bulk_g2s(sm.in[buf], sig + ((size_t)b * nsample + (size_t)f0 * kHop) * 2, bytes, &sm.bar[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_fence_init();
+        if (blockIdx.x < nitems) issue_load(blockIdx.x, 0);
+    }
+    __syncthreads();
+    uint32_t phases = 0;                                      // bit buf = parity to wait for on bar[buf]
+    int pb = -1, pfb = 0, pnfr = 0;                            // the published, not yet stored item (clip, item in clip, frames)
+    for (int n = 0;; ++n) {
+        const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
+        const int buf = n & 1;
+        const bool valid = item < nitems;
+        int b = 0, fb = 0, nfr = 0;
+        if (valid) {
+            if (tid == 0 && item + gridDim.x < nitems) issue_load(item + gridDim.x, buf ^ 1);      // in[buf ^ 1] was last read two barriers ago
+            b = (int)(item / ipc); fb = (int)(item - (long long)b * ipc);
+            nfr = min(kPF, nt - fb * kPF);
+            mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
+            float part = 0.f;
+            if (g < nfr) {
+                float2 v[8];
+                fft_frame(sm.in[buf] + g * kHop, lane, sre, sim, l, g, v);
+                float4* orow = sm.out[buf] + g * kHop;
+#pragma unroll
+                for (int k3 = 0; k3 < 4; ++k3) {
+                    const float4 o = split_bin(v, sre, sim, l, k3);
+                    part += sqrtf(o.x * o.x + o.z * o.z);
+                    const int k = l + 64 * k3;
+                    if (k >= 1) orow[k - 1] = o;
+                }
+                if (l == 0) {
+                    const float4 o = split_bin(v, sre, sim, 0, 4);
+                    part += sqrtf(o.x * o.x + o.z * o.z);
+                    orow[255] = o;
+                }
+            }
+            const float total = block_sum(part, sm.red);
+            if (tid == 0) {
+                partials[(size_t)b * ipc + fb] = total;
+                __threadfence();
+                atomicAdd(&counters[2 + b], 1u);
+            }
+        }
+        if (pb >= 0) {                                        // finish the previous item: rendezvous, scale, store
+            if (tid == 0) {
+                unsigned spins = 0;
+                while (ld_acquire_u32(&counters[2 + pb]) < (unsigned)ipc) {
+                    __nanosleep(32);
+                    if (++spins > (1u << 24)) { atomicExch(&counters[1], 1u); break; }      // never expected; report instead of hanging
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {                                   // fixed-order (deterministic) sum of the clip's partials
+                float s = 0.f;
+                for (int i = tid; i < ipc; i += 32) s += __ldcg(&partials[(size_t)pb * ipc + i]);
+                s = warp_sum(s);
+                if (tid == 0) sm.scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
+            }
+            __syncthreads();
+            const float scale = sm.scale;
+            float4* dst = out + ((size_t)pb * nt + (size_t)pfb * kPF) * kHop;
+            const float4* src = sm.out[buf ^ 1];
+            for (int i = tid; i < pnfr * kHop; i += kThreads) {
+                float4 o = src[i];
+                o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+                st_stream_f4(dst + i, o);
+            }
+        }
+        __syncthreads();
+        if (!valid) break;
+        pb = b; pfb = fb; pnfr = nfr;
+    }
+}
+
 // ---------------- second-generation fused kernel: independent warps, one transform each (fft512w.cuh) ----------------
 // Every warp of the persistent grid is its own worker: frame f = warp_global_id + round * total_warps of the (clip-major) frame list.
 // Per frame: bulk-TMA its 512 samples (double buffered: the next frame's samples are in flight while this one is transformed),
@@ -398,9 +511,30 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     float* scale = reinterpret_cast<float*>(ws + off);
     off += ((size_t)nb * sizeof(float) + 255) / 256 * 256;
 
-    // force_generic: 0 = fused kernel with 64-lane FFT groups (default, fastest measured), 1 = generic three-kernel path,
+    // force_generic: 0 / 4 = fused kernel with 64-lane FFT groups (default, fastest measured), 1 = generic three-kernel path,
+    // 3 = the fused kernel with load / rendezvous / store pipelined inside the CTA (same speed: the kernel is bound by the FFT's
+    // group barriers and shared-memory round trips, not by the exposed latencies),
     // 2 = experimental warp-worker kernel (one warp per transform, no block barriers; measured slower: the per-clip rendezvous
     // keeps its independent warps in lock step - profiles/r01_stft_variants.txt)
+    if (force_generic == 3) {      // pipelined kernel (its own frames-per-item granularity); measured equal to the default, profiles/r01_stft_variants.txt
+        static int max_ctas_v3 = -1;
+        if (max_ctas_v3 < 0) {
+            SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+            int n = 0;
+            SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_pipe_kernel, kThreads, sizeof(PipeSmem)));
+            max_ctas_v3 = n;
+        }
+        const int ipc3 = (nt + kPF - 1) / kPF;
+        const long long resident3 = (long long)max_ctas_v3 * sm_count(), items3 = (long long)nb * ipc3;
+        if (nch == 2 && (nsample % 2 == 0) && resident3 >= ipc3) {
+            SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
+            const int grid = (int)(items3 < resident3 ? items3 : resident3);
+            stft_frontend_pipe_kernel<<<grid, kThreads, sizeof(PipeSmem), stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt,
+                                                                                   ipc3, eps);
+            SARSSL_LAUNCH_CHECK();
+            return SARSSL_OK;
+        }
+    }
     static int max_ctas_v1 = -1, max_ctas_v2 = -1;
     const bool v1 = force_generic != 2;
     const size_t smem = v1 ? sizeof(FusedSmem) : sizeof(WarpWorkerSmem);
