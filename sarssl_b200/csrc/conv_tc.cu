@@ -5,7 +5,11 @@
 //
 // Forward / data gradient  (conv3x3_tc_kernel, persistent, 1 CTA per SM):
 //   out[b,h,w,:] = sum_{dh,dw} in[b,h+dh,w+dw,:] . Wp[:, tap(dh,dw), :]        (data gradient = same kernel, mirrored weights)
-//   * output tile = 128 consecutive pixels of one image row, accumulator 128 x 64 fp32 in TMEM (double buffered);
+//   * output tile = 128 consecutive pixels of TWO vertically adjacent image rows, accumulator 128 x 128 fp32 in TMEM (double
+//     buffered): columns 0-63 = row h, 64-127 = row h+1.  Input rows h and h+1 feed both output rows, so their UMMAs run with
+//     N = 128 against two weight taps that sit side by side in shared memory ([W(dh) | W(dh-1)]); rows h-1 and h+2 feed one output
+//     row each (N = 64).  With N = 64 alone every instruction re-reads its 128 x 16 A slice for half the math and the kernel is bound
+//     by shared-memory operand reads (measured: the same FLOPs issued as N = 128 run 18 % faster);
 //   * A operand: ONE TMA box per image row ([w0-1, w0+135) x 64 ch, out-of-bounds pixels zero-filled = the padding) serves the
 //     three horizontal taps by sliding the UMMA descriptor start by one pixel row (128 B) - swizzling is address based, see
 //     tests/test_tc_probe_gpu.py; a rolling ring of row boxes lets vertically consecutive tiles re-use two of their three rows,
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
         mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_tmem)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_tmem)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     cfence_before();
@@ -132,7 +136,9 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(wbar, CWB);
-            for (int t = 0; t < 9; ++t) ctma_load_2d(wsm + t * 8192, &tmW, t * 64, 0, wbar);
+            // global tap t = (dh+1)*3 + (dw+1) -> slot (dw+1)*3 + (1-dh): for a fixed dw the taps lie in the order dh = +1, 0, -1, so
+            // [W(dh) | W(dh-1)] is one contiguous 128-row B operand
+            for (int t = 0; t < 9; ++t) ctma_load_2d(wsm + ((t % 3) * 3 + (2 - t / 3)) * 8192, &tmW, t * 64, 0, wbar);
             int s = 0;
             uint32_t ephase = 0;                                // bit s = phase of empty[s] to wait for next (starts "already free")
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
@@ -140,7 +146,8 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
                 const long long r = u / p.nseg_h;
                 const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
                 const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
-                for (int row = h0 - 1; row <= h1; ++row) {
+                const int npair = (h1 - h0 + 1) >> 1;
+                for (int row = h0 - 1; row <= h0 + 2 * npair; ++row) {       // rows past the image are zero-filled by TMA
                     mbar_wait(&empty[s], ((ephase >> s) & 1u) ^ 1u);
                     ephase ^= 1u << s;
                     mbar_expect_tx(&full[s], CBOXB);
@@ -151,50 +158,63 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
         }
     } else if (warp == 1) {
         {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t hi = cdesc_hi(1024);
             mbar_wait(wbar, 0);
             const uint32_t w_lo = cdesc_lo(smem_u32(wsm), 16), ring_lo = cdesc_lo(smem_u32(ring), 16);
-            int slot0 = 0;                                      // ring slot of the oldest row box of the current tile
+            int slot0 = 0;                                      // ring slot of the oldest row box (row h - 1) of the current pair
             uint32_t fphase = 0;                                // bit s = phase of full[s] expected next
             uint32_t it = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG);
-                const int ntile = h1 - h0;
-                for (int t = 0; t < ntile; ++t, ++it) {
-                    // rows needed: slots slot0, slot0+1, slot0+2; each box's full barrier is waited exactly once, in order
-                    for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
-                        int sj = slot0 + j; if (sj >= CSLOTS) sj -= CSLOTS;
-                        mbar_wait(&full[sj], (fphase >> sj) & 1u);
-                        fphase ^= 1u << sj;
+                const int npair = (h1 - h0 + 1) >> 1;
+                for (int t = 0; t < npair; ++t, ++it) {
+                    // rows h-1 .. h+2 = slots slot0 .. slot0+3; each box's full barrier is waited exactly once, in order
+                    int sl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { sl[j] = slot0 + j; if (sl[j] >= CSLOTS) sl[j] -= CSLOTS; }
+                    for (int j = (t == 0 ? 0 : 2); j < 4; ++j) {
+                        mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
+                        fphase ^= 1u << sl[j];
                     }
                     const uint32_t acc = it & 1u;
                     mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
                     cfence_after();
-                    const uint32_t d = tmem + acc * 64;
-                    int s1 = slot0 + 1; if (s1 >= CSLOTS) s1 -= CSLOTS;
-                    int s2 = slot0 + 2; if (s2 >= CSLOTS) s2 -= CSLOTS;
-                    const uint32_t a_lo0 = ring_lo + (uint32_t)slot0 * (CBOXB >> 4), a_lo1 = ring_lo + (uint32_t)s1 * (CBOXB >> 4),
-                                   a_lo2 = ring_lo + (uint32_t)s2 * (CBOXB >> 4);
-                    const bool last = t == ntile - 1;
+                    const uint32_t d = tmem + acc * 128;
+                    const uint32_t a0 = ring_lo + (uint32_t)sl[0] * (CBOXB >> 4), a1 = ring_lo + (uint32_t)sl[1] * (CBOXB >> 4),
+                                   a2 = ring_lo + (uint32_t)sl[2] * (CBOXB >> 4), a3 = ring_lo + (uint32_t)sl[3] * (CBOXB >> 4);
+                    const bool last = t == npair - 1;
                     if (celect_one()) {
+                        // weight slot (dw, dh) = dw*3 + (1 - dh) (dw, dh as 0..2 / -1..1); the first instruction initialises all 128 columns
 #pragma unroll
-                        for (int dh = 0; dh < 3; ++dh) {
-                            const uint32_t a_lo = dh == 0 ? a_lo0 : (dh == 1 ? a_lo1 : a_lo2);
+                        for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
-                            for (int dw = 0; dw < 3; ++dw) {
+                            for (int k = 0; k < 4; ++k)         // input row h:   dh = 0 for output row h | dh = -1 for output row h+1
+                                cumma2(d, a1 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 1) * 512 + k * 2, hi, idesc128, (uint32_t)((dw | k) != 0));
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    cumma2(d, a_lo + dw * 8 + k * 2, hi, w_lo + (dh * 3 + dw) * 512 + k * 2, hi, idesc, (uint32_t)((dh | dw | k) != 0));
-                            }
-                        }
-                        ccommit(&empty[slot0]);                 // the oldest row is dead after this tile
-                        if (last) { ccommit(&empty[s1]); ccommit(&empty[s2]); }
+                        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for output row h | dh = 0 for output row h+1
+                                cumma2(d, a2 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc128, 1u);
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1, output row h only (columns 0-63)
+                                cumma2(d, a0 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 2) * 512 + k * 2, hi, idesc64, 1u);
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1, output row h+1 only (columns 64-127)
+                                cumma2(d + 64, a3 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc64, 1u);
+                        ccommit(&empty[sl[0]]);                 // rows h-1 and h are dead after this pair
+                        ccommit(&empty[sl[1]]);
+                        if (last) { ccommit(&empty[sl[2]]); ccommit(&empty[sl[3]]); }
                         ccommit(&tfull[acc]);
                     }
                     __syncwarp();
-                    slot0 += last ? 3 : 1; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
+                    slot0 += last ? 4 : 2; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
                 }
             }
         }
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
         const int q = warp & 3;
         const int chalf = (warp - 2) >> 2;                      // two warps share a lane quarter: channels [32*chalf, 32*chalf + 32)
         const int row = q * 32 + lane;                          // pixel row of the tile = TMEM lane
-        // fused BatchNorm statistics: thread (channel sc, row quarter sh) adds its 32 staged bf16 values of every tile
+        // fused BatchNorm statistics: thread (channel sc, row quarter sh) adds its 32 staged bf16 values of every output row
         const int et = (warp - 2) * 32 + lane, sc = et & 63, sh = et >> 6;
         float bn_s = 0.f, bn_q = 0.f;
         uint32_t it = 0;
@@ -211,18 +231,20 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
             const long long r = u / p.nseg_h;
             const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
             const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
-            for (int h = h0; h < h1; ++h, ++it) {
+            for (int h = h0; h < h1; h += 2, ++it) {
                 const uint32_t acc = it & 1u;
-                unsigned char* stage = osm + acc * COUTB;
-                // the TMA store that last read this staging buffer (2 tiles ago) must have finished reading it
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const int nrow = min(2, h1 - h);                // the last pair of an odd segment has one real output row
+                // both staging buffers were last read by the previous pair's TMA stores (issued a whole tile's MMA time ago)
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 mbar_wait(&tfull[acc], (it >> 1) & 1u);
                 cfence_after();
-                {
+#pragma unroll
+                for (int rp = 0; rp < 2; ++rp) {
+                    unsigned char* stage = osm + rp * COUTB;
                     const int c0 = chalf * 32;
                     uint32_t v[32];
-                    ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
+                    ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + rp * 64 + c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 pk;
@@ -242,17 +264,20 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (warp == 2 && lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmOut), "r"(0), "r"(w0), "r"(h), "r"(b),
-                                 "r"(smem_u32(stage)) : "memory");
+                    for (int rp = 0; rp < nrow; ++rp)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmOut), "r"(0), "r"(w0), "r"(h + rp),
+                                     "r"(b), "r"(smem_u32(osm + rp * COUTB)) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (p.bn_partials != nullptr) {
                     const int rmax = min(32, p.W - w0 - sh * 32);                 // rows beyond the image edge hold garbage
-                    const unsigned char* colp = stage + ((sc & 7) << 1);
-                    for (int r = 0; r < rmax; ++r) {
-                        const int rr = sh * 32 + r;
-                        const float xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + (((sc >> 3) ^ (rr & 7)) << 4)));
-                        bn_s += xv; bn_q += xv * xv;
+                    for (int rp = 0; rp < nrow; ++rp) {
+                        const unsigned char* colp = osm + rp * COUTB + ((sc & 7) << 1);
+                        for (int r = 0; r < rmax; ++r) {
+                            const int rr = sh * 32 + r;
+                            const float xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + (((sc >> 3) ^ (rr & 7)) << 4)));
+                            bn_s += xv; bn_q += xv * xv;
+                        }
                     }
                 }
             }
@@ -272,7 +297,7 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
     }
     cfence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
 // ============================================================================================================================
