@@ -19,9 +19,10 @@
 //
 // Weight gradient  (conv3x3_wgrad_tc_kernel, persistent, split over pixels):
 //   dWp[o, tap, ci] = sum_pixels dy[p, o] * in[p + tap, ci]; the contraction runs over pixels, so both operands are MN-major;
-//   the whole 576 x 64 result lives in TMEM (6 accumulators of 128 x 64: two taps of the same image row per UMMA), each k-block
-//   (64 pixels) loads one dy box and re-uses the rolling ring of input row boxes; per-CTA partial sums are reduced in a fixed
-//   order by a second kernel.
+//   the whole 576 x 64 result lives in TMEM (6 accumulators of 128 x 64: two taps of the same image row per UMMA).  Output rows are
+//   processed in pairs: the dy boxes of rows h and h+1 sit side by side in shared memory, so the input rows that feed both (h, h+1)
+//   run as N = 128 instructions into two neighbouring accumulators ([dh | dh-1]); rows h-1 and h+2 feed one tap row each (N = 64).
+//   The rolling ring of input row boxes is re-used across pairs; per-CTA partial sums are reduced in a fixed order by a second kernel.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -359,27 +360,34 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                 const long long r = u / p.nseg_h;
                 const int wt = (int)(r % p.tiles_w), b = (int)(r / p.tiles_w);
                 const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG), w0 = wt * GK;
-                // interleave: input rows h0-1, h0 first, then for each output row h: input row h+1 and dy row h
-                for (int row = h0 - 1; row <= h1; ++row) {
+                const int npair = (h1 - h0 + 1) >> 1;
+                // input rows h0-1 .. h0+2*npair (rows outside the image are zero-filled); the two dy rows of a pair follow its last input row.
+                // A trailing half pair still loads its (unused) second dy row and fourth input row so that the slot accounting is uniform.
+                for (int row = h0 - 1; row <= h0 + 2 * npair; ++row) {
                     mbar_wait(&empty[s], ((ephase >> s) & 1u) ^ 1u);
                     ephase ^= 1u << s;
                     mbar_expect_tx(&full[s], GBOXR * 128);
                     ctma_load_4d(ring + s * GBOXB, &tmIn, 0, w0 - 1, row, b, &full[s]);
                     if (++s == GSLOTS) s = 0;
-                    if (row >= h0 + 1) {                        // dy row (row - 1) is needed together with input row `row`
-                        mbar_wait(&dempty[sd], ((dephase >> sd) & 1u) ^ 1u);
-                        dephase ^= 1u << sd;
-                        mbar_expect_tx(&dfull[sd], 8192);
-                        ctma_load_4d(dyr + sd * 8192, &tmDy, 0, w0, row - 1, b, &dfull[sd]);
-                        if (++sd == GDY) sd = 0;
+                    const int rel = row - h0;                   // after input row h+2 of the pair (h, h+1): dy rows h, h+1
+                    if (rel >= 2 && (rel & 1) == 0) {
+#pragma unroll 1
+                        for (int rp = 0; rp < 2; ++rp) {
+                            mbar_wait(&dempty[sd], ((dephase >> sd) & 1u) ^ 1u);
+                            dephase ^= 1u << sd;
+                            mbar_expect_tx(&dfull[sd], 8192);
+                            ctma_load_4d(dyr + sd * 8192, &tmDy, 0, w0, row - 2 + rp, b, &dfull[sd]);
+                            if (++sd == GDY) sd = 0;
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         {
-            // A (input taps) MN-major M = 128: two 64-channel groups LBO apart; B (dy) MN-major N = 64
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            // A (input taps) MN-major M = 128: two 64-channel groups LBO (one pixel row) apart; B (dy) MN-major, N = 64 or two rows N = 128
+            constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t hi = cdesc_hi(1024);
             const uint32_t ring_lo = cdesc_lo(smem_u32(ring), 128), dy_lo0 = cdesc_lo(smem_u32(dyr), 8192);
             int slot0 = 0, sd = 0;
@@ -387,43 +395,65 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
                 const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG);
-                const int ntile = h1 - h0;
-                for (int t = 0; t < ntile; ++t) {
-                    for (int j = (t == 0 ? 0 : 2); j < 3; ++j) {
-                        int sj = slot0 + j; if (sj >= GSLOTS) sj -= GSLOTS;
-                        mbar_wait(&full[sj], (fphase >> sj) & 1u);
-                        fphase ^= 1u << sj;
+                const int npair = (h1 - h0 + 1) >> 1;
+                for (int t = 0; t < npair; ++t) {
+                    int sl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { sl[j] = slot0 + j; if (sl[j] >= GSLOTS) sl[j] -= GSLOTS; }
+                    for (int j = (t == 0 ? 0 : 2); j < 4; ++j) {
+                        mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
+                        fphase ^= 1u << sl[j];
                     }
-                    mbar_wait(&dfull[sd], (dphase >> sd) & 1u);
-                    dphase ^= 1u << sd;
+                    for (int rp = 0; rp < 2; ++rp) {            // dy rows h, h+1 = slots sd, sd+1 (sd is even: never wraps inside a pair)
+                        mbar_wait(&dfull[sd + rp], (dphase >> (sd + rp)) & 1u);
+                        dphase ^= 1u << (sd + rp);
+                    }
                     cfence_after();
                     const uint32_t dy_lo = dy_lo0 + (uint32_t)sd * (8192 >> 4);
                     const uint32_t accf = any ? 1u : 0u;
-                    int s1 = slot0 + 1; if (s1 >= GSLOTS) s1 -= GSLOTS;
-                    int s2 = slot0 + 2; if (s2 >= GSLOTS) s2 -= GSLOTS;
-                    const uint32_t a_lo0 = ring_lo + (uint32_t)slot0 * (GBOXB >> 4), a_lo1 = ring_lo + (uint32_t)s1 * (GBOXB >> 4),
-                                   a_lo2 = ring_lo + (uint32_t)s2 * (GBOXB >> 4);
-                    const bool last = t == ntile - 1;
+                    const uint32_t a0 = ring_lo + (uint32_t)sl[0] * (GBOXB >> 4), a1 = ring_lo + (uint32_t)sl[1] * (GBOXB >> 4),
+                                   a2 = ring_lo + (uint32_t)sl[2] * (GBOXB >> 4), a3 = ring_lo + (uint32_t)sl[3] * (GBOXB >> 4);
+                    const bool last = t == npair - 1;
+                    const bool full_pair = h0 + 2 * t + 1 < h1;  // a trailing half pair has only output row h
+                    // accumulator (tap group G, dh) lives at columns G*192 + (1-dh)*64: [dh=+1 | dh=0 | dh=-1], so an N = 128 instruction whose B is
+                    // [dy(h) | dy(h+1)] lands on (dh, dh-1).  The first instructions ever issued initialise every column exactly once.
                     if (celect_one()) {
 #pragma unroll
-                        for (int dh = 0; dh < 3; ++dh) {
-                            const uint32_t a_lo = dh == 0 ? a_lo0 : (dh == 1 ? a_lo1 : a_lo2);
+                        for (int G = 0; G < 2; ++G) {            // G = 0: taps dw = -1, 0;  G = 1: tap dw = +1 (upper 64 lanes unused)
+                            const uint32_t d = tmem + G * 192, ao = G * 16;
+                            if (full_pair) {
 #pragma unroll
-                            for (int half = 0; half < 2; ++half) {              // taps (dw = -1, 0) together, then (dw = +1, -)
-                                const uint32_t d = tmem + (dh * 2 + half) * 64;
+                                for (int k = 0; k < 4; ++k)     // input row h+1: dh = +1 for dy(h), dh = 0 for dy(h+1)
+                                    cumma2(d, a2 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc128, k == 0 ? accf : 1u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    cumma2(d, a_lo + half * 16 + k * 128, hi, dy_lo + k * 128, hi, idesc, k == 0 ? accf : 1u);
+                                for (int k = 0; k < 4; ++k)     // input row h-1: dh = -1 for dy(h)
+                                    cumma2(d + 128, a0 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc64, k == 0 ? accf : 1u);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)     // input row h:   dh = 0 for dy(h), dh = -1 for dy(h+1)
+                                    cumma2(d + 64, a1 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)     // input row h+2: dh = +1 for dy(h+1)
+                                    cumma2(d, a3 + ao + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
+                            } else {
+#pragma unroll
+                                for (int dh = 0; dh < 3; ++dh) {                  // single output row: input rows h-1, h, h+1 against dy(h)
+                                    const uint32_t a = dh == 0 ? a0 : (dh == 1 ? a1 : a2);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        cumma2(d + (2 - dh) * 64, a + ao + k * 128, hi, dy_lo + k * 128, hi, idesc64, k == 0 ? accf : 1u);
+                                }
                             }
                         }
-                        ccommit(&empty[slot0]);
-                        if (last) { ccommit(&empty[s1]); ccommit(&empty[s2]); }
+                        ccommit(&empty[sl[0]]);
+                        ccommit(&empty[sl[1]]);
+                        if (last) { ccommit(&empty[sl[2]]); ccommit(&empty[sl[3]]); }
                         ccommit(&dempty[sd]);
+                        ccommit(&dempty[sd + 1]);
                     }
                     __syncwarp();
                     any = true;
-                    slot0 += last ? 3 : 1; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
-                    if (++sd == GDY) sd = 0;
+                    slot0 += last ? 4 : 2; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
+                    sd += 2; if (sd >= GDY) sd = 0;
                 }
             }
             if (celect_one()) ccommit(done);
@@ -439,11 +469,12 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
             mbar_wait(done, 0);
             cfence_after();
         }
-        // TMEM lane l of accumulator g: l < 64 -> tap 3*(g/2) + 2*(g%2), ci = l;  l >= 64 (g even only) -> next tap, ci = l - 64
+        // accumulator g = G*3 + (1-dh) at columns g*64: lanes l < 64 -> tap (dh, dw = 2G-1), ci = l;  l >= 64 (G = 0 only) -> tap (dh, dw = 0), ci = l - 64
         for (int g = 0; g < 6; ++g) {
             const int l = q * 32 + lane;
-            const int tap = 3 * (g >> 1) + 2 * (g & 1) + (l >> 6);
-            const bool valid = (l < 64) || ((g & 1) == 0);
+            const int G = g / 3, dhi = 2 - (g % 3);              // dhi = dh + 1
+            const int tap = dhi * 3 + 2 * G + (l >> 6);
+            const bool valid = (l < 64) || (G == 0);
             const int ci = l & 63;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
