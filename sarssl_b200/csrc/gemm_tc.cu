@@ -115,7 +115,7 @@ struct TcSmem {
 // A_MN / B_MN: operand is MN-major (rows of the global matrix run along the contraction dimension), used by weight gradients.
 // NS = pipeline stages: 3 for long K; 2 for K <= 512 (4-8 k-blocks), which lets three CTAs share an SM so that more epilogue warps
 // are in flight - those GEMMs are epilogue / store bound.
-template <int BN, bool A_MN, bool B_MN, int NS>
+template <int BN, bool A_MN, bool B_MN, int NS, int EPI = 0>
 __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpi p) {
     extern __shared__ unsigned char smem_raw[];
@@ -217,12 +217,24 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             }
         }
     } else {
+        // EPI != 0: the epilogue variant is fixed at compile time (bit 6 = fast marker, bit 0 bias, bits 1-2 activation, bit 3 second
+        // (pre-activation) output, bit 4 dropout, bit 5 residual; bf16 C through the TMA store, alpha = 1, no split-K): the flag tests
+        // below fold away and each instantiation is straight-line code.  EPI == 0 keeps every test at run time.
+        constexpr bool FAST = EPI != 0;
+        const bool f_tma = FAST ? true : (p.tma_store != 0);
+        const bool f_vec = FAST ? true : (p.vec_ok != 0);
+        const bool f_bf16 = FAST ? true : (p.c_is_bf16 != 0);
+        const bool f_bias = FAST ? ((EPI & 1) != 0) : (p.bias != nullptr);
+        const int f_act = FAST ? ((EPI >> 1) & 3) : p.act;
+        const bool f_pre = FAST ? ((EPI & 8) != 0) : (p.pre != nullptr);
+        const bool f_resid = FAST ? ((EPI & 32) != 0) : (p.resid != nullptr);
+        const float f_alpha = FAST ? 1.0f : p.alpha;
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const int cpart = (warp - 2) >> 2;              // warps sharing a lane quarter interleave the tile's 32-column chunks
-        const bool drop = p.drop_p > 0.f;
+        const bool drop = FAST ? ((EPI & 16) != 0) : (p.drop_p > 0.f);
         const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-        const bool atomic = p.splitk > 1;
+        const bool atomic = FAST ? false : (p.splitk > 1);
         uint32_t it = 0;
         for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
             int zz, m0, n0;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             const int zb = zz / p.splitk;
             const int z1 = zb / p.nb2, z2 = zb - z1 * p.nb2;
             const uint32_t acc = it & 1u;
-            if (p.tma_store) {                          // the previous tile's TMA store must have finished reading the staging buffers
+            if (f_tma) {                          // the previous tile's TMA store must have finished reading the staging buffers
                 if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
             }
@@ -243,22 +255,22 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
                 const int nb = n0 + c0;
-                if (!p.tma_store && (m >= p.M || nb >= p.N)) continue;
-                if (p.tma_store && nb >= p.N) continue;              // (N % 32 == 0 on this path: whole chunks only)
+                if (!f_tma && (m >= p.M || nb >= p.N)) continue;
+                if (f_tma && nb >= p.N) continue;              // (N % 32 == 0 on this path: whole chunks only)
                 const long long off = zoff + (long long)m * p.ldc + nb;
                 const long long roff = zoff + (long long)m * p.ldr + nb;
-                if (p.vec_ok && nb + 32 <= p.N) {
+                if (f_vec && (FAST || nb + 32 <= p.N)) {
                     // ---------------- vector path: 32 consecutive columns of one row
                     float v[32];
                     const bool row_ok = m < p.M;                     // rows past M only exist to fill the staged tile; TMA clips them
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 bz = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[j] = __uint_as_float(r[j]) * p.alpha + bz.x; v[j + 1] = __uint_as_float(r[j + 1]) * p.alpha + bz.y;
-                        v[j + 2] = __uint_as_float(r[j + 2]) * p.alpha + bz.z; v[j + 3] = __uint_as_float(r[j + 3]) * p.alpha + bz.w;
+                        float4 bz = f_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j] = __uint_as_float(r[j]) * f_alpha + bz.x; v[j + 1] = __uint_as_float(r[j + 1]) * f_alpha + bz.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) * f_alpha + bz.z; v[j + 3] = __uint_as_float(r[j + 3]) * f_alpha + bz.w;
                     }
-                    if (p.pre) {
-                        if (p.c_is_bf16) {
+                    if (f_pre) {
+                        if (f_bf16) {
                             unsigned char* sbox = stP + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
                             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
 #pragma unroll
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                                 __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
                                 const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
                                                             *reinterpret_cast<uint32_t*>(&t3));
-                                if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
+                                if (f_tma) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
                                 else dst[j >> 3] = pk;
                             }
                         } else {
@@ -276,10 +288,10 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                             for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
-                    if (p.act == 1) {
+                    if (f_act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (p.act == 2) {
+                    } else if (f_act == 2) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
                     }
@@ -291,8 +303,8 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                             v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
                         }
                     }
-                    if (p.resid && row_ok) {
-                        if (p.c_is_bf16) {
+                    if (f_resid && row_ok) {
+                        if (f_bf16) {
                             const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + roff);
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -310,11 +322,11 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                                 v[j] = u.x + p.beta * v[j]; v[j + 1] = u.y + p.beta * v[j + 1]; v[j + 2] = u.z + p.beta * v[j + 2]; v[j + 3] = u.w + p.beta * v[j + 3];
                             }
                         }
-                    } else if (p.beta != 1.0f && !p.resid) {
+                    } else if (!f_resid && p.beta != 1.0f) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= p.beta;
                     }
-                    if (p.c_is_bf16) {
+                    if (f_bf16) {
                         unsigned char* sbox = stC + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
                         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
 #pragma unroll
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                             __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
                             const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
                                                         *reinterpret_cast<uint32_t*>(&t3));
-                            if (p.tma_store) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
+                            if (f_tma) *reinterpret_cast<uint4*>(sbox + (((((c0 & 63) + j) >> 3) ^ ((q * 32 + lane) & 7)) << 4)) = pk;
                             else dst[j >> 3] = pk;
                         }
                     } else {
@@ -346,24 +358,24 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     }
                     continue;
                 }
-                // ---------------- scalar path (ragged N or unaligned C)
-#pragma unroll 1
+                // ---------------- scalar path (ragged N or unaligned C); fully unrolled: a run-time index would push r[] into local memory
+#pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = nb + j;
-                    if (n >= p.N) break;
-                    float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? p.bias[n] : 0.f);
-                    if (p.pre) {
-                        if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.pre)[off + j] = __float2bfloat16_rn(v);
+                    if (n >= p.N) continue;
+                    float v = __uint_as_float(r[j]) * f_alpha + (f_bias ? p.bias[n] : 0.f);
+                    if (f_pre) {
+                        if (f_bf16) static_cast<__nv_bfloat16*>(p.pre)[off + j] = __float2bfloat16_rn(v);
                         else static_cast<float*>(p.pre)[off + j] = v;
                     }
-                    if (p.act == 1) v = fmaxf(v, 0.f);
-                    else if (p.act == 2) v = __fdividef(v, 1.0f + __expf(-v));
+                    if (f_act == 1) v = fmaxf(v, 0.f);
+                    else if (f_act == 2) v = __fdividef(v, 1.0f + __expf(-v));
                     if (drop) v = keep_mask(p.drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
-                    if (p.resid) {
-                        const float rv = p.c_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
+                    if (f_resid) {
+                        const float rv = f_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
                         v = rv + p.beta * v;
                     } else v *= p.beta;
-                    if (p.c_is_bf16) static_cast<__nv_bfloat16*>(p.C)[off + j] = __float2bfloat16_rn(v);
+                    if (f_bf16) static_cast<__nv_bfloat16*>(p.C)[off + j] = __float2bfloat16_rn(v);
                     else {
                         float* cp = static_cast<float*>(p.C) + off + j;
                         if (atomic) atomicAdd(cp, v);
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (p.tma_store) {
+            if (f_tma) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (warp == 2 && lane == 0) {
@@ -384,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                         if (n0 + 64 * j < p.N) {
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmC), "r"(n0 + 64 * j), "r"(m0),
                                          "r"(z2), "r"(z1), "r"(smem_u32(stC + j * (TBM * 128))) : "memory");
-                            if (p.pre)
+                            if (f_pre)
                                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmPre), "r"(n0 + 64 * j),
                                              "r"(m0), "r"(z2), "r"(z1), "r"(smem_u32(stP + j * (TBM * 128))) : "memory");
                         }
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                 }
             }
         }
-        if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (f_tma && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -436,16 +448,16 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return SARSSL_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int NS>
+template <int BN, bool A_MN, bool B_MN, int NS, int EPI = 0>
 static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, cudaStream_t stream) {
     static bool configured = false;
     const int smem = TcSmem<BN, NS>::kBytes;
     if (!configured) {
-        SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, NS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const int grid = (int)(e.ntiles < sm_count() ? e.ntiles : sm_count());
-    gemm_tc_kernel<BN, A_MN, B_MN, NS><<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, mp, e);
+    gemm_tc_kernel<BN, A_MN, B_MN, NS, EPI><<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, mp, e);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
@@ -518,6 +530,24 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
                   : make_map(&ma, a->A, a->K, a->M, lda, 64, TBK, a->nb1, a->sAb1, a->nb2, a->sAb2))) return rc;
     if ((rc = b_k ? make_map(&mb, a->B, a->N, a->K, ldb, TBK, BN, a->nb1, a->sBb1, a->nb2, a->sBb2)
                   : make_map(&mb, a->B, a->K, a->N, ldb, 64, TBK, a->nb1, a->sBb1, a->nb2, a->sBb2))) return rc;
+    // compile-time epilogue variants for the layer types of the model (everything else runs the generic epilogue)
+    if (!bn64 && e.tma_store && e.splitk == 1 && a->alpha == 1.0f && !a->accumulate) {
+        const int flags = 64 | (a->bias ? 1 : 0) | ((a->act & 3) << 1) | (a->pre_out ? 8 : 0) | (a->drop_p > 0.f ? 16 : 0) | (a->resid ? 32 : 0);
+        const bool beta_ok = a->resid || a->beta == 1.0f;
+        if (beta_ok && a_k && b_k) {
+            switch (flags) {
+                case 64: return launch_tc_ns<128, false, false, 4, 64>(ma, mb, mc, mp, e, stream);                       // plain
+                case 64 | 1: return launch_tc_ns<128, false, false, 4, 64 | 1>(ma, mb, mc, mp, e, stream);               // bias
+                case 64 | 1 | 2: return launch_tc_ns<128, false, false, 4, 64 | 1 | 2>(ma, mb, mc, mp, e, stream);       // bias + ReLU
+                case 64 | 1 | 4 | 8 | 16: return launch_tc_ns<128, false, false, 4, 64 | 1 | 4 | 8 | 16>(ma, mb, mc, mp, e, stream);   // bias + Swish + pre + dropout (FFN 1)
+                case 64 | 1 | 4 | 8: return launch_tc_ns<128, false, false, 4, 64 | 1 | 4 | 8>(ma, mb, mc, mp, e, stream);             // the same in eval mode
+                case 64 | 1 | 16 | 32: return launch_tc_ns<128, false, false, 4, 64 | 1 | 16 | 32>(ma, mb, mc, mp, e, stream);         // bias + dropout + residual
+                case 64 | 1 | 32: return launch_tc_ns<128, false, false, 4, 64 | 1 | 32>(ma, mb, mc, mp, e, stream);                   // the same in eval mode
+                default: break;
+            }
+        }
+        if (beta_ok && a_k && b_mn && flags == 64) return launch_tc_ns<128, false, true, 4, 64>(ma, mb, mc, mp, e, stream);    // data gradients
+    }
     if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, false>(ma, mb, mc, mp, e, stream);
     if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, true>(ma, mb, mc, mp, e, stream);
     if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, true, false>(ma, mb, mc, mp, e, stream);
