@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
                     int sl[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { sl[j] = slot0 + j; if (sl[j] >= CSLOTS) sl[j] -= CSLOTS; }
-                    for (int j = (t == 0 ? 0 : 2); j < 4; ++j) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {               // (unrolled: a run-time index would push sl[] into local memory)
+                        if (j < 2 && t != 0) continue;
                         mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
                         fphase ^= 1u << sl[j];
                     }
@@ -400,10 +402,13 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                     int sl[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { sl[j] = slot0 + j; if (sl[j] >= GSLOTS) sl[j] -= GSLOTS; }
-                    for (int j = (t == 0 ? 0 : 2); j < 4; ++j) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {               // (unrolled: a run-time index would push sl[] into local memory)
+                        if (j < 2 && t != 0) continue;
                         mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
                         fphase ^= 1u << sl[j];
                     }
+#pragma unroll
                     for (int rp = 0; rp < 2; ++rp) {            // dy rows h, h+1 = slots sd, sd+1 (sd is even: never wraps inside a pair)
                         mbar_wait(&dfull[sd + rp], (dphase >> (sd + rp)) & 1u);
                         dphase ^= 1u << (sd + rp);
