@@ -269,8 +269,8 @@ def run_ours(args):
                 "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 conv 64->64 implicit GEMM, forward)" if dtype == torch.bfloat16 else "conv3x3_kernel (CUDA cores, fp32)", "achieved": conv_tflops,
                              "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"],
                              # dram__bytes_read + dram__bytes_write of one launch, ncu --set full (profiles/r01b_conv3x3_tc_kernel.txt, 64 clips):
-                             # 1054.7 MB vs 1073.7 MB algorithmic (read + write one bf16 64-channel map) -> no redundant HBM traffic
-                             "traffic": 1054.7e6 * cb / 64.0, "traffic_source": "ncu --set full, 64-clip launch, scaled by clips per launch",
+                             # 1056.6 MB vs 1073.7 MB algorithmic (read + write one bf16 64-channel map) -> no redundant HBM traffic
+                             "traffic": 1056.6e6 * cb / 64.0, "traffic_source": "ncu --set full (profiles/r01h_conv3x3_tc_kernels.txt), 64-clip launch, scaled by clips per launch",
                              "peak_source": pk["source"], "kernel_ms": conv_ms, "algorithmic_flops_per_launch": cb * CONV3_FLOP_PER_CLIP,
                              "clips_per_launch": cb},
                 "frontend": {"workload": f"stft_frontend + masked_recon_loss fwd+bwd, batch {fb} (BASELINE.json configs[1])",
