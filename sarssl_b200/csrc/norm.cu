@@ -180,7 +180,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // ---------------------------------------------------------------- column sums: partial[cta][cols]
 // CTA = 256 threads = 32 column groups (8 columns each, one 16-byte load) x 8 row lanes; grid.x tiles the columns by 256,
 // grid.y strides the rows.
-template <typename T>
+// ATOMIC: the CTA's column sums are added straight into `partials` (= the fp32 output, [cols]) with red.global.add - no second
+// kernel; the summation order then varies from run to run, like the split-K weight gradients these bias gradients sit next to.
+template <typename T, bool ATOMIC>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ partials, int rows, int cols) {
     __shared__ float sh[8][256];
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
-        partials[(size_t)blockIdx.y * cols + c] = s;
+        if (ATOMIC) atomicAdd(partials + c, s);
+        else partials[(size_t)blockIdx.y * cols + c] = s;
     }
 }
 
@@ -495,14 +498,19 @@ extern "C" int sarssl_colsum(const void* x, long long ldx, float* out, int rows,
     const int gx = (cols + 255) / 256;
     int grid = capped_grid(rows, 64, 64);
     {
-        const int cap = dtype == SARSSL_F32 ? resident_ctas(colsum_kernel<float>, 256) : resident_ctas(colsum_kernel<__nv_bfloat16>, 256);
+        const int cap = dtype == SARSSL_F32 ? resident_ctas(colsum_kernel<float, false>, 256) : resident_ctas(colsum_kernel<__nv_bfloat16, false>, 256);
         if (grid > cap) grid = cap;
     }
     grid /= gx;
     if (grid < 1) grid = 1;
+    if (accumulate && dtype == SARSSL_BF16) {       // bf16 training path: one launch, partial sums added with red.global.add (see colsum_kernel)
+        colsum_kernel<__nv_bfloat16, true><<<dim3(gx, grid), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, out, rows, cols);
+        SARSSL_LAUNCH_CHECK();
+        return SARSSL_OK;
+    }
     if (workspace_bytes < (size_t)grid * cols * sizeof(float)) { set_last_error("colsum: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     float* partials = static_cast<float*>(workspace);
-    DISPATCH_T(dtype, (colsum_kernel<T><<<dim3(gx, grid), 256, 0, stream>>>(static_cast<const T*>(x), ldx, partials, rows, cols)));
+    DISPATCH_T(dtype, (colsum_kernel<T, false><<<dim3(gx, grid), 256, 0, stream>>>(static_cast<const T*>(x), ldx, partials, rows, cols)));
     SARSSL_LAUNCH_CHECK();
     reduce_partials_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partials, grid, cols, out, out, cols, accumulate);
     SARSSL_LAUNCH_CHECK();
