@@ -247,6 +247,14 @@ int sarssl_permute4(const void* src, int src_dtype, void* dst, int dst_dtype, co
 int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Input pipeline in front of the path (next row 4)                      dataset.py:142-178 (soundfile.read)
+ * Host functions: RIFF/WAVE decode (PCM 8/16/24/32, float 32/64) to float32 [nsample][nch], scaled like libsndfile.
+ * ---------------------------------------------------------------------------------------------------------- */
+int sarssl_wav_info(const char* path, int* fs, int* nch, long long* nsample);
+/* frames [first, first + count) -> out_host[count][nch]; frames past the end are zero-filled, *nread = real frames */
+int sarssl_wav_read_f32(const char* path, long long first, long long count, float* out_host, long long* nread);
+
+/* ------------------------------------------------------------------------------------------------------------
  * A6  CNN patch-embedding stem on channel-last images [B][H = frame][W = bin][C]      model.py:50-64,203-208
  * ---------------------------------------------------------------------------------------------------------- */
 /* 1x1 conv 4 -> 64.  mode 0: `in` is [P][4] of `dtype`; mode 1 / 2: `in` is the fp32 patch tensor and the spectral /
