@@ -226,3 +226,30 @@ def test_pretrain_evaluate_matches_oracle_math():
     assert abs(float(res["mse_mask"]) - float((d * (1 - md)).sum() / (1 - md).sum())) < 1e-4 * float(res["mse_mask"])
     assert abs(float(res["mse_mask_ch"]) - float((d * (1 - md)).sum(4).mean())) < 1e-4 * float(res["mse_mask_ch"])
     assert res["pesq"].shape == (nb, 2)
+
+
+def test_long_clip_nt1024_config5():
+    """BASELINE.json configs[4] shape (16.4 s clips, nt = 1024): the attention / score kernels leave their T <= 256 fast paths.
+    fp32 forward vs the CPU oracle (1e-4), then a bf16 forward + backward: loss within 2e-2 of fp32, finite gradients."""
+    nb, nt = 1, 1024
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=21)
+    m = build(nt)
+    L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    x, = L.data_preprocess(sig.to(DEV))
+    random.seed(3)
+    with torch.no_grad():
+        loss32, diff32, vis = m(x)
+    sd = O.synthetic_state_dict(7)
+    random.seed(3)
+    pidx, cidx = O.draw_masks(nb, nt, nt // 2, 2)
+    with torch.no_grad():
+        rl, rd, rvis = O.pretrain_forward(O.preprocess(sig), sd, pidx, cidx, training=True)
+    assert rel(vis["pred"].cpu(), rvis["pred"]) < 1e-4
+    assert abs(float(loss32) - float(rl)) < 1e-4 * float(rl) and abs(float(diff32) - float(rd)) < 1e-4 * float(rd)
+    mb = build(nt, dtype=torch.bfloat16)
+    random.seed(3)
+    loss16, _, _ = mb(x)
+    loss16.backward()
+    assert abs(float(loss16) - float(rl)) < 2e-2 * float(rl)
+    for k, p in mb.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
