@@ -9,6 +9,29 @@
 
 namespace sarssl {
 
+// packed fp32 pairs (one issue slot, two FMAs).  Same FLOP rate as scalar FFMA (measured: scripts/micro/ffma2_rate.cu), but half the
+// issue slots - what the pixel kernels below are short of.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ---- input loader shared by the narrow (4-channel) kernels ---------------------------------------------------------
 // mode 0: plain [P][4] tensor of type T.  mode 1 / 2: fp32 patches (re0, re1, im0, im1) with the spectral / spatial mask:
 //   spectral: masked frame -> keep only the un-masked microphone; other frames -> keep only the masked microphone
@@ -122,6 +145,10 @@ __global__ void __launch_bounds__(256) pw_reduce_kernel(const T* __restrict__ in
 #pragma unroll
         for (int c = 0; c < 4; ++c) wr[c][j] = ws[c][sub * 8 + j];
     }
+    // weights packed for fma.rn.f32x2: (W[0][j], W[1][j]) and (W[2][j], W[3][j]) - one issue slot feeds two accumulators
+    unsigned long long w01[8], w23[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w01[j] = pack_f32x2(wr[0][j], wr[1][j]); w23[j] = pack_f32x2(wr[2][j], wr[3][j]); }
     const long long per_iter = (long long)gridDim.x * 128;
     const long long iters = (P + per_iter - 1) / per_iter;
     for (long long it = 0; it < iters; ++it) {
@@ -135,24 +162,40 @@ __global__ void __launch_bounds__(256) pw_reduce_kernel(const T* __restrict__ in
                 for (int j = 0; j < 8; ++j) qv[u][j] = 0.f;
             }
         }
+        // acc[u*2 + h] = this thread's 8-channel share of outputs (2h, 2h+1) of pixel u
+        unsigned long long acc[8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            unsigned long long a01 = 0ull, a23 = 0ull;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float v = qv[u][j];
-                if (tr) v = fmaxf(v * scr[j] + shr[j], 0.f);
-                a0 = fmaf(wr[0][j], v, a0); a1 = fmaf(wr[1][j], v, a1); a2 = fmaf(wr[2][j], v, a2); a3 = fmaf(wr[3][j], v, a3);
+                if (tr) v = fmaxf(fmaf(v, scr[j], shr[j]), 0.f);
+                const unsigned long long vv = pack_f32x2(v, v);
+                a01 = fma_f32x2(w01[j], vv, a01);
+                a23 = fma_f32x2(w23[j], vv, a23);
             }
+            acc[u * 2] = a01; acc[u * 2 + 1] = a23;
+        }
+        // reduce-scatter over the 8 threads of the pixel group: every step halves the values a thread still owns (7 packed shuffles
+        // instead of 48 scalar ones); thread `sub` ends with acc[0] = outputs (2*(sub&1), +1) of pixel sub>>1
 #pragma unroll
-            for (int sft = 4; sft > 0; sft >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, sft); a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-                a2 += __shfl_xor_sync(0xffffffffu, a2, sft); a3 += __shfl_xor_sync(0xffffffffu, a3, sft);
+        for (int step = 0; step < 3; ++step) {
+            const int half = 4 >> step, bit = 4 >> step;
+            const bool up = (sub & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i >= half) continue;
+                const unsigned long long send = up ? acc[i] : acc[i + half], keep = up ? acc[i + half] : acc[i];
+                const unsigned long long got = __shfl_xor_sync(0xffffffffu, send, bit);
+                acc[i] = add_f32x2(keep, got);
             }
-            if (p0 + u < P && sub == 0) {
-                T* o = out + (p0 + u) * 4;
-                o[0] = from_f32<T>(a0); o[1] = from_f32<T>(a1); o[2] = from_f32<T>(a2); o[3] = from_f32<T>(a3);
-            }
+        }
+        const int pu = sub >> 1;
+        if (p0 + pu < P) {
+            const float2 r = unpack_f32x2(acc[0]);
+            T* o = out + (p0 + pu) * 4 + (sub & 1) * 2;
+            o[0] = from_f32<T>(r.x); o[1] = from_f32<T>(r.y);
         }
     }
 }
