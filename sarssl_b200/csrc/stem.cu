@@ -93,12 +93,14 @@ __global__ void __launch_bounds__(256, 3) pw_expand_kernel(const void* __restric
     __syncthreads();
     const int sub = threadIdx.x & 7;
     const bool bn = scale != nullptr;
-    float wr[8][4], sh[8];
+    // channel pairs packed for fma.rn.f32x2: wp[jp][c] = (W[2jp][c], W[2jp+1][c]), shp[jp] = (shift[2jp], shift[2jp+1])
+    unsigned long long wp[4][4], shp[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sh[j] = bn ? shift[sub * 8 + j] : 0.f;
+    for (int jp = 0; jp < 4; ++jp) {
+        const int o = sub * 8 + 2 * jp;
+        shp[jp] = bn ? pack_f32x2(shift[o], shift[o + 1]) : 0ull;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wr[j][c] = ws[sub * 8 + j][c];
+        for (int c = 0; c < 4; ++c) wp[jp][c] = pack_f32x2(ws[o][c], ws[o + 1][c]);
     }
     // 4 pixels per thread per iteration (independent loads in flight)
     for (long long p0 = ((long long)blockIdx.x * 32 + (threadIdx.x >> 3)) * 4; p0 < P; p0 += (long long)gridDim.x * 128) {
@@ -117,10 +119,17 @@ __global__ void __launch_bounds__(256, 3) pw_expand_kernel(const void* __restric
         for (int u = 0; u < 4; ++u) {
             if (p0 + u >= P) break;
             float o[8];
+            const unsigned long long x0 = pack_f32x2(x[u].x, x[u].x), x1 = pack_f32x2(x[u].y, x[u].y), x2 = pack_f32x2(x[u].z, x[u].z),
+                                     x3 = pack_f32x2(x[u].w, x[u].w);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                o[j] = wr[j][0] * x[u].x + wr[j][1] * x[u].y + wr[j][2] * x[u].z + wr[j][3] * x[u].w;
-                if (bn) o[j] = fmaxf(o[j] + sh[j], 0.f);
+            for (int jp = 0; jp < 4; ++jp) {
+                unsigned long long a = fma_f32x2(wp[jp][0], x0, shp[jp]);
+                a = fma_f32x2(wp[jp][1], x1, a);
+                a = fma_f32x2(wp[jp][2], x2, a);
+                a = fma_f32x2(wp[jp][3], x3, a);
+                const float2 r = unpack_f32x2(a);
+                o[2 * jp] = bn ? fmaxf(r.x, 0.f) : r.x;
+                o[2 * jp + 1] = bn ? fmaxf(r.y, 0.f) : r.y;
             }
             Vec8<T>::store(out + (p0 + u) * 64 + sub * 8, o);
         }
@@ -540,16 +549,30 @@ __global__ void __launch_bounds__(256, 3) stem_tail_bwd_apply_kernel(const __nv_
             x[u] = load_narrow<__nv_bfloat16>(dq, p, 0, nullptr, nullptr, 0, 0);
             Vec8<__nv_bfloat16>::load(y + p * 64 + sub * 8, v[u]);
         }
+        // the 4 upstream-gradient channels of every pixel packed with themselves, so one f32x2 FMA serves two of the 4 pixels
+        unsigned long long xp[2][4];                                      // [pixel pair][c] = (x[2q][c], x[2q+1][c])
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            xp[q2][0] = pack_f32x2(x[2 * q2].x, x[2 * q2 + 1].x); xp[q2][1] = pack_f32x2(x[2 * q2].y, x[2 * q2 + 1].y);
+            xp[q2][2] = pack_f32x2(x[2 * q2].z, x[2 * q2 + 1].z); xp[q2][3] = pack_f32x2(x[2 * q2].w, x[2 * q2 + 1].w);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             asm volatile("" ::: "memory");                                // keep the constant loads where they are used (register pressure)
             const float4 w = cw[j * 8 + sub], b = cb[j * 8 + sub];
+            const unsigned long long w0 = pack_f32x2(w.x, w.x), w1 = pack_f32x2(w.y, w.y), w2 = pack_f32x2(w.z, w.z), w3 = pack_f32x2(w.w, w.w);
+            const unsigned long long c1n = pack_f32x2(-b.w, -b.w), c0n = pack_f32x2(-b.z, -b.z);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float yv = v[u][j];
-                const float dzs = w.x * x[u].x + w.y * x[u].y + w.z * x[u].z + w.w * x[u].w;
-                const float gs = fmaf(yv, b.x, b.y) > 0.f ? dzs : 0.f;
-                v[u][j] = gs - fmaf(b.w, yv, b.z);
+            for (int q2 = 0; q2 < 2; ++q2) {
+                unsigned long long dz = fma_f32x2(w0, xp[q2][0], 0ull);
+                dz = fma_f32x2(w1, xp[q2][1], dz);
+                dz = fma_f32x2(w2, xp[q2][2], dz);
+                dz = fma_f32x2(w3, xp[q2][3], dz);
+                const float ya = v[2 * q2][j], yb = v[2 * q2 + 1][j];
+                const float2 d = unpack_f32x2(dz);
+                const unsigned long long gs = pack_f32x2(fmaf(ya, b.x, b.y) > 0.f ? d.x : 0.f, fmaf(yb, b.x, b.y) > 0.f ? d.y : 0.f);
+                const float2 r = unpack_f32x2(add_f32x2(gs, fma_f32x2(c1n, pack_f32x2(ya, yb), c0n)));      // gs - (c1*y + c0)
+                v[2 * q2][j] = r.x; v[2 * q2 + 1][j] = r.y;
             }
         }
 #pragma unroll
