@@ -12,25 +12,32 @@ namespace sarssl {
 
 constexpr int kDwT = 64, kDwD = 64, kDwMaxK = 31, kDwRows = kDwT + kDwMaxK - 1, kDwPer = kDwT / 4;
 
+// column -> position inside a 64-float tile row: columns 32..63 swap neighbouring float4 slots, so the eight 32-byte-strided float4
+// stores a quarter warp issues while staging a row land in 8 different bank groups (they were 2-way conflicting); the compute loops
+// read 32 consecutive columns per warp, which stays a permutation of 32 banks.
+__device__ __forceinline__ int dw_col(int c) { return c ^ ((c >> 5) << 2); }
+
 // rows [t0 - pad, t0 - pad + nrows) x channels [d0, d0 + 64) of `in` -> tile (fp32), zero outside the sequence / channel range.
 // 16-byte loads when D % 8 == 0.
 template <typename T>
 __device__ __forceinline__ void dw_stage(const T* __restrict__ in, float (*tile)[kDwD], int nrows, int b, int t_first, int d0, int Tn, int D) {
     if ((D & 7) == 0) {
-        for (int c = threadIdx.x; c < nrows * 8; c += 256) {
-            const int r = c >> 3, ch = (c & 7) * 8, t = t_first + r, d = d0 + ch;
+        const int ch = (threadIdx.x & 7) * 8, d = d0 + ch;
+        const T* src = in + ((long long)b * Tn + t_first) * D + d;     // row r of the tile is src + r * D
+        for (int r = threadIdx.x >> 3; r < nrows; r += 32) {
+            const int t = t_first + r;
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            if (t >= 0 && t < Tn && d < D) Vec8<T>::load(in + ((long long)b * Tn + t) * D + d, v);
-            *reinterpret_cast<float4*>(&tile[r][ch]) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(&tile[r][ch + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+            if (t >= 0 && t < Tn && d < D) Vec8<T>::load(src + (long long)r * D, v);
+            *reinterpret_cast<float4*>(&tile[r][dw_col(ch)]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(&tile[r][dw_col(ch + 4)]) = make_float4(v[4], v[5], v[6], v[7]);
         }
     } else {
         const int dl = threadIdx.x & 63, d = d0 + dl;
         for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
             const int t = t_first + r;
-            tile[r][dl] = (d < D && t >= 0 && t < Tn) ? to_f32(in[((long long)b * Tn + t) * D + d]) : 0.f;
+            tile[r][dw_col(dl)] = (d < D && t >= 0 && t < Tn) ? to_f32(in[((long long)b * Tn + t) * D + d]) : 0.f;
         }
     }
 }
@@ -45,11 +52,19 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
     const int d0 = blockIdx.x * kDwD, t0 = blockIdx.y * kDwT, b = blockIdx.z;
     const int dl = threadIdx.x & 63, tg = threadIdx.x >> 6;
     const int d = d0 + dl;
+    __shared__ float ws[kDwD * kDwMaxK];
     dw_stage<T>(in, tile, kDwRows, b, t0 - pad, d0, Tn, D);          // all 94 rows (finite data or zeros) whatever K is
+    // the 64 channels' taps are contiguous in global memory: coalesced copy to shared memory (a per-thread read of its own 31 taps
+    // would touch 32 different sectors per instruction), then each thread picks its row (stride K is odd: conflict-free)
+    {
+        const float* wsrc = w + (long long)d0 * K;
+        const int nw = min(kDwD, D - d0) * K;                        // taps of the channels that exist
+        for (int i = threadIdx.x; i < kDwD * K; i += 256) ws[i] = i < nw ? wsrc[i] : 0.f;
+    }
+    __syncthreads();
     float wr[kDwMaxK];
 #pragma unroll
-    for (int k = 0; k < kDwMaxK; ++k) wr[k] = (k < K && d < D) ? w[(long long)d * K + (flip ? K - 1 - k : k)] : 0.f;
-    __syncthreads();
+    for (int k = 0; k < kDwMaxK; ++k) wr[k] = k < K ? ws[dl * K + (flip ? K - 1 - k : k)] : 0.f;
     if (d >= D) return;
     const int tb = tg * kDwPer;
     float acc[kDwPer];
@@ -57,16 +72,16 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
     for (int o = 0; o < kDwPer; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int r = 0; r < kDwPer + kDwMaxK - 1; ++r) {
-        const float x = tile[tb + r][dl];
+        const float x = tile[tb + r][dw_col(dl)];
 #pragma unroll
         for (int o = 0; o < kDwPer; ++o)
             if (r - o >= 0 && r - o < kDwMaxK) acc[o] = fmaf(wr[r - o], x, acc[o]);
     }
+    T* op = out + ((long long)b * Tn + (t0 + tb)) * D + d;          // one 64-bit address, then a constant stride
+    const int nvalid = Tn - (t0 + tb);
 #pragma unroll
-    for (int o = 0; o < kDwPer; ++o) {
-        const int t = t0 + tb + o;
-        if (t < Tn) out[((long long)b * Tn + t) * D + d] = from_f32<T>(acc[o]);
-    }
+    for (int o = 0; o < kDwPer; ++o)
+        if (o < nvalid) op[(long long)o * D] = from_f32<T>(acc[o]);
 }
 
 // grid (D/64, nchunks); CTA loops over (b, t-tile) pairs chunk-strided; partials [nchunks][D][K].  Same register blocking as the
@@ -96,10 +111,10 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const T* __restrict__
         __syncthreads();
         float g[kDwPer];
 #pragma unroll
-        for (int o = 0; o < kDwPer; ++o) g[o] = tdc[tb + o][dl];
+        for (int o = 0; o < kDwPer; ++o) g[o] = tdc[tb + o][dw_col(dl)];
 #pragma unroll
         for (int r = 0; r < kDwPer + kDwMaxK - 1; ++r) {
-            const float x = ta[tb + r][dl];
+            const float x = ta[tb + r][dw_col(dl)];
 #pragma unroll
             for (int o = 0; o < kDwPer; ++o)
                 if (r - o >= 0 && r - o < kDwMaxK) acc[r - o] = fmaf(g[o], x, acc[r - o]);

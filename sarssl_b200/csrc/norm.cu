@@ -11,48 +11,64 @@ namespace sarssl {
 
 constexpr int kLnChunks = 4;           // cols <= 1024, cols % 8 == 0: lane owns elements [c*256 + lane*8, +8) of every 256-column chunk c
 
-// ---------------------------------------------------------------- LayerNorm forward: one warp per row
-template <typename T>
+// ---------------------------------------------------------------- LayerNorm forward: one warp per row, R rows in flight per warp
+// NCH = 256-column chunks per row (compile time); rows row0 + q * (gridDim.x * 8), q < R, are loaded before the first reduction.
+template <typename T, int NCH, int R>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, T* __restrict__ out, long long ldo,
                                                    float* __restrict__ mean, float* __restrict__ rstd, int rows, int cols, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= rows) return;
-    const T* xr = x + (long long)row * ldx;
-    float v[kLnChunks][8];
-    float s = 0.f;
+    const int row0 = blockIdx.x * 8 + warp, rstride = gridDim.x * 8;
+    float v[R][NCH][8];
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
-        const int col = c * 256 + lane * 8;
-        if (col < cols) {
-            Vec8<T>::load(xr + col, v[c]);
+    for (int q = 0; q < R; ++q) {
+        const int row = row0 + q * rstride;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += v[c][j];
+        for (int c = 0; c < NCH; ++c) {
+            const int col = c * 256 + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[q][c][j] = 0.f;
+            if (row < rows && col < cols) Vec8<T>::load(x + (long long)row * ldx + col, v[q][c]);
         }
     }
-    const float mu = warp_sum(s) / cols;
-    float q = 0.f;
+    float g[NCH][8], bt[NCH][8];
 #pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
-        if (c * 256 + lane * 8 < cols) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mu; q += d * d; }
-        }
-    }
-    const float rs = rsqrtf(warp_sum(q) / cols + eps);
-    if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
-    T* orow = out + (long long)row * ldo;
-#pragma unroll
-    for (int c = 0; c < kLnChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int col = c * 256 + lane * 8;
-        if (col < cols) {
-            float g[8], bt[8], o[8];
-            load8f(gamma + col, g);
-            load8f(beta + col, bt);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mu) * rs * g[j] + bt[j];
-            Vec8<T>::store(orow + col, o);
+        for (int j = 0; j < 8; ++j) { g[c][j] = 0.f; bt[c][j] = 0.f; }
+        if (col < cols) { load8f(gamma + col, g[c]); load8f(beta + col, bt[c]); }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const int row = row0 + q * rstride;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[q][c][j];                 // (columns past `cols` hold zeros)
+        const float mu = warp_sum(s) / cols;
+        float qq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (c * 256 + lane * 8 < cols) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[q][c][j] - mu; qq += d * d; }
+            }
+        }
+        const float rs = rsqrtf(warp_sum(qq) / cols + eps);
+        if (row >= rows) continue;
+        if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
+        T* orow = out + (long long)row * ldo;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < cols) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (v[q][c][j] - mu) * rs * g[c][j] + bt[c][j];
+                Vec8<T>::store(orow + col, o);
+            }
         }
     }
 }
@@ -455,8 +471,13 @@ extern "C" int sarssl_layernorm_fwd(const void* x, long long ldx, const float* g
     SARSSL_CHECK_ARG(x && gamma && beta && out && rows > 0 && cols > 0, "layernorm_fwd: bad arguments");
     SARSSL_CHECK_ARG(cols <= 256 * kLnChunks && cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm_fwd: cols=%d must be a multiple of 8, <= %d", cols,
                      256 * kLnChunks);
-    DISPATCH_T(dtype, (ln_fwd_kernel<T><<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const T*>(x), ldx, gamma, beta, static_cast<T*>(out), ldo,
-                                                                        mean, rstd, rows, cols, eps)));
+#define LN_FWD_LAUNCH(NCH, R)                                                                                                                  \
+    DISPATCH_T(dtype, (ln_fwd_kernel<T, NCH, R><<<(rows + 8 * R - 1) / (8 * R), 256, 0, stream>>>(static_cast<const T*>(x), ldx, gamma, beta,    \
+                                                                                              static_cast<T*>(out), ldo, mean, rstd, rows, cols, eps)))
+    if (cols <= 256) LN_FWD_LAUNCH(1, 4);
+    else if (cols <= 512) LN_FWD_LAUNCH(2, 2);
+    else LN_FWD_LAUNCH(4, 1);
+#undef LN_FWD_LAUNCH
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
