@@ -201,135 +201,177 @@ __global__ void attn_unshift_kernel(const T* __restrict__ dscore, T* __restrict_
     }
 }
 
-// ---- vector versions of the three score kernels for T % 8 == 0, T <= 256 (one warp per row, 8 consecutive columns per lane, 16-byte
-// global accesses).  The relative shift is a sliding window: shift(pos)[i][j] = S[T-1-i+j] with S = [pos row i | 0 | pos row i+1], and
-// its inverse dpos[r][k] = S'[r+1+k] with S' = [dscore row r-1 | dscore row r]; the rows are staged in shared memory as fp32 with one
-// pad word every 8 (lane stride 9 words: conflict-free for both the chunked stores and the windowed loads).
+// ---- vector versions of the three score kernels for T % 8 == 0, T <= 1024 (one warp per row; lane owns the 8 consecutive columns
+// of chunks lane, lane + 32, ... (NCH = ceil(T / 256) chunks), 16-byte global accesses).  The relative shift is a sliding window:
+// shift(pos)[i][j] = S[T-1-i+j] with S = [pos row i | 0 | pos row i+1], and its inverse dpos[r][k] = S'[r+1+k] with
+// S' = [dscore row r-1 | dscore row r]; the rows are staged in (dynamic) shared memory as fp32 with one pad word every 8 (lane stride
+// 9 words: conflict-free for both the chunked stores and the windowed loads).
 __device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
-constexpr int kScoreMaxT = 256, kScoreRow = kScoreMaxT + kScoreMaxT / 8 + 8;
+constexpr int kScoreMaxT = 1024;
+static inline int score_row_floats(int Tn) { return Tn + Tn / 8 + 8; }
 
-template <typename T>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __restrict__ content, const T* __restrict__ pos, T* __restrict__ prob,
                                                                  T* __restrict__ attn, int B, int H, int Tn, float scale, float drop_p,
                                                                  unsigned long long seed) {
-    __shared__ float win[8][2][kScoreRow];
+    extern __shared__ float score_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rowf = Tn + Tn / 8 + 8;
+    float* win0 = score_smem + (size_t)w * 2 * rowf;
+    float* win1 = win0 + rowf;
     const long long row = (long long)blockIdx.x * 8 + w;
     if (row >= (long long)B * H * Tn) return;
     const int i = (int)(row % Tn);
     const long long bh = row / Tn;
     const int h = (int)(bh % H), b = (int)(bh / H);
     const T* pbase = pos + ((long long)h * B + b) * Tn * Tn;
-    const bool active = lane * 8 < Tn;
-    float v[8];
-    if (active) {
-        float t[8];
-        Vec8<T>::load(pbase + (long long)i * Tn + lane * 8, t);
+    float v[NCH][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) win[w][0][lane * 9 + e] = t[e];
-        if (i + 1 < Tn) {
-            Vec8<T>::load(pbase + (long long)(i + 1) * Tn + lane * 8, t);
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 < Tn) {
+            float t[8];
+            Vec8<T>::load(pbase + (long long)i * Tn + c * 8, t);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) win[w][1][lane * 9 + e] = t[e];
+            for (int e = 0; e < 8; ++e) win0[c * 9 + e] = t[e];
+            if (i + 1 < Tn) {
+                Vec8<T>::load(pbase + (long long)(i + 1) * Tn + c * 8, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) win1[c * 9 + e] = t[e];
+            }
+            Vec8<T>::load(content + row * Tn + c * 8, v[k]);
         }
-        Vec8<T>::load(content + row * Tn + lane * 8, v);
     }
     __syncwarp();
     float mx = -INFINITY;
-    if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int idx = Tn - 1 - i + lane * 8 + e;
-            const float ps = idx < Tn ? win[w][0][pad8(idx)] : (idx == Tn ? 0.f : win[w][1][pad8(idx - Tn - 1)]);
-            v[e] = (v[e] + ps) * scale;
-            mx = fmaxf(mx, v[e]);
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 < Tn) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = Tn - 1 - i + c * 8 + e;
+                const float ps = idx < Tn ? win0[pad8(idx)] : (idx == Tn ? 0.f : win1[pad8(idx - Tn - 1)]);
+                v[k][e] = (v[k][e] + ps) * scale;
+                mx = fmaxf(mx, v[k][e]);
+            }
         }
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { v[e] = __expf(v[e] - mx); sum += v[e]; }
+    for (int k = 0; k < NCH; ++k) {
+        if ((lane + 32 * k) * 8 < Tn) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[k][e] = __expf(v[k][e] - mx); sum += v[k][e]; }
+        }
     }
     sum = warp_sum(sum);
-    if (!active) return;
     const float inv = 1.0f / sum;
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const uint32_t thr = drop_threshold(drop_p);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] *= inv;
-    const long long off = row * Tn + lane * 8;
-    Vec8<T>::store(prob + off, v);
-    if (attn != nullptr) {            // Dropout(attn) (attention.py:98) materialised for the tensor-core context GEMM
-        const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-        const uint32_t thr = drop_threshold(drop_p);
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            const uint32_t kp = keep_pair(seed, (unsigned long long)(off + e) >> 1, thr);
-            v[e] = (kp & 1u) ? v[e] * ks : 0.f;
-            v[e + 1] = (kp & 2u) ? v[e + 1] * ks : 0.f;
+        for (int e = 0; e < 8; ++e) v[k][e] *= inv;
+        const long long off = row * Tn + c * 8;
+        Vec8<T>::store(prob + off, v[k]);
+        if (attn != nullptr) {            // Dropout(attn) (attention.py:98) materialised for the tensor-core context GEMM
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                const uint32_t kp = keep_pair(seed, (unsigned long long)(off + e) >> 1, thr);
+                v[k][e] = (kp & 1u) ? v[k][e] * ks : 0.f;
+                v[k][e + 1] = (kp & 2u) ? v[k][e + 1] * ks : 0.f;
+            }
+            Vec8<T>::store(attn + off, v[k]);
         }
-        Vec8<T>::store(attn + off, v);
     }
 }
 
-template <typename T>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256) attn_softmax_bwd_vec_kernel(T* __restrict__ dattn, const T* __restrict__ prob, long long rows, int Tn,
                                                                  float scale, float drop_p, unsigned long long seed) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const bool active = lane * 8 < Tn;
-    const long long off = row * Tn + lane * 8;
-    float d[8], pr[8];
+    float d[NCH][8], pr[NCH][8];
     float dot = 0.f;
-    if (active) {
-        Vec8<T>::load(dattn + off, d);
-        Vec8<T>::load(prob + off, pr);
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const uint32_t thr = drop_threshold(drop_p);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
+        const long long off = row * Tn + c * 8;
+        Vec8<T>::load(dattn + off, d[k]);
+        Vec8<T>::load(prob + off, pr[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
+        const long long off = row * Tn + c * 8;
         if (drop_p > 0.f) {
-            const float ks = 1.0f / (1.0f - drop_p);
-            const uint32_t thr = drop_threshold(drop_p);
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
                 const uint32_t kp = keep_pair(seed, (unsigned long long)(off + e) >> 1, thr);
-                d[e] = (kp & 1u) ? d[e] * ks : 0.f;
-                d[e + 1] = (kp & 2u) ? d[e + 1] * ks : 0.f;
+                d[k][e] = (kp & 1u) ? d[k][e] * ks : 0.f;
+                d[k][e + 1] = (kp & 2u) ? d[k][e + 1] * ks : 0.f;
             }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dot = fmaf(d[e], pr[e], dot);
+        for (int e = 0; e < 8; ++e) dot = fmaf(d[k][e], pr[k][e], dot);
     }
     dot = warp_sum(dot);
-    if (!active) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = scale * pr[e] * (d[e] - dot);
-    Vec8<T>::store(dattn + off, d);
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[k][e] = scale * pr[k][e] * (d[k][e] - dot);
+        Vec8<T>::store(dattn + row * Tn + c * 8, d[k]);
+    }
 }
 
-template <typename T>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256) attn_unshift_vec_kernel(const T* __restrict__ dscore, T* __restrict__ dpos, int B, int H, int Tn) {
-    __shared__ float win[8][2 * kScoreRow];
+    extern __shared__ float score_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* win = score_smem + (size_t)w * 2 * (Tn + Tn / 8 + 8);
     const long long orow = (long long)blockIdx.x * 8 + w;              // output row (h, b, r)
     if (orow >= (long long)B * H * Tn) return;
     const int r = (int)(orow % Tn);
     const long long hb = orow / Tn;
     const int b = (int)(hb % B), h = (int)(hb / B);
     const T* base = dscore + ((long long)b * H + h) * Tn * Tn;
-    if (lane * 8 >= Tn) return;
-    float t[8];
-    if (r >= 1) Vec8<T>::load(base + (long long)(r - 1) * Tn + lane * 8, t);
-    else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] = 0.f;
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
+        float t[8];
+        if (r >= 1) Vec8<T>::load(base + (long long)(r - 1) * Tn + c * 8, t);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) win[pad8(c * 8 + e)] = t[e];
+        Vec8<T>::load(base + (long long)r * Tn + c * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) win[pad8(Tn + c * 8 + e)] = t[e];
     }
+    __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 8; ++e) win[w][pad8(lane * 8 + e)] = t[e];
-    Vec8<T>::load(base + (long long)r * Tn + lane * 8, t);
+    for (int k = 0; k < NCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c * 8 >= Tn) continue;
+        float t[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) win[w][pad8(Tn + lane * 8 + e)] = t[e];
-    __syncwarp(__activemask());
-#pragma unroll
-    for (int e = 0; e < 8; ++e) t[e] = win[w][pad8(r + 1 + lane * 8 + e)];
-    Vec8<T>::store(dpos + orow * Tn + lane * 8, t);
+        for (int e = 0; e < 8; ++e) t[e] = win[pad8(r + 1 + c * 8 + e)];
+        Vec8<T>::store(dpos + orow * Tn + c * 8, t);
+    }
 }
 
 // pooled[b][d] = mean_t x[b][t][d] (fp32 out);  dx[b][t][d] = dpooled[b][d] / T        (torch.mean(embed, dim=1), model.py:705)
@@ -443,11 +485,26 @@ extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, voi
                                        float drop_p, unsigned long long seed, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(content && pos && prob && B > 0 && H > 0 && T_ > 0, "attn_softmax_fwd: bad arguments");
     const long long rows = (long long)B * H * T_;
-    if (T_ % 8 == 0 && T_ <= kScoreMaxT)
-        DISPATCH_T(dtype, (attn_softmax_fwd_vec_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(content), static_cast<const T*>(pos),
-                                                                                                        static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_,
-                                                                                                        scale, drop_p, seed)));
-    else
+    if (T_ % 8 == 0 && T_ <= kScoreMaxT) {
+        const size_t smem = (size_t)8 * 2 * score_row_floats(T_) * sizeof(float);
+#define SCORE_FWD(NCH)                                                                                                                           \
+        do {                                                                                                                                     \
+            static bool set_f = false, set_h = false;                                                                                            \
+            bool& set = dtype == SARSSL_F32 ? set_f : set_h;                                                                                     \
+            if (!set) {                                                                                                                          \
+                if (dtype == SARSSL_F32) SARSSL_CUDA(cudaFuncSetAttribute(attn_softmax_fwd_vec_kernel<float, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
+                else SARSSL_CUDA(cudaFuncSetAttribute(attn_softmax_fwd_vec_kernel<__nv_bfloat16, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));      \
+                set = true;                                                                                                                      \
+            }                                                                                                                                    \
+            DISPATCH_T(dtype, (attn_softmax_fwd_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, smem, stream>>>(                           \
+                                   static_cast<const T*>(content), static_cast<const T*>(pos), static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_, \
+                                   scale, drop_p, seed)));                                                                                       \
+        } while (0)
+        if (T_ <= 256) SCORE_FWD(1);
+        else if (T_ <= 512) SCORE_FWD(2);
+        else SCORE_FWD(4);
+#undef SCORE_FWD
+    } else
         DISPATCH_T(dtype, (attn_softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(content), static_cast<const T*>(pos),
                                                                                                     static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_, scale,
                                                                                                     drop_p, seed)));
@@ -460,17 +517,33 @@ extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void
     SARSSL_CHECK_ARG(dattn_inout && prob && dpos && B > 0 && H > 0 && T_ > 0, "attn_softmax_bwd: bad arguments");
     const long long rows = (long long)B * H * T_;
     const bool vec = T_ % 8 == 0 && T_ <= kScoreMaxT;
-    if (vec)
-        DISPATCH_T(dtype, (attn_softmax_bwd_vec_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout), static_cast<const T*>(prob),
-                                                                                                        rows, T_, scale, drop_p, seed)));
-    else
+    const size_t smem = (size_t)8 * 2 * score_row_floats(T_) * sizeof(float);
+#define SCORE_BWD(NCH)                                                                                                                           \
+    do {                                                                                                                                         \
+        static bool set_f = false, set_h = false;                                                                                                \
+        bool& set = dtype == SARSSL_F32 ? set_f : set_h;                                                                                         \
+        if (!set) {                                                                                                                              \
+            if (dtype == SARSSL_F32) SARSSL_CUDA(cudaFuncSetAttribute(attn_unshift_vec_kernel<float, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
+            else SARSSL_CUDA(cudaFuncSetAttribute(attn_unshift_vec_kernel<__nv_bfloat16, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));          \
+            set = true;                                                                                                                          \
+        }                                                                                                                                        \
+        DISPATCH_T(dtype, (attn_softmax_bwd_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout),     \
+                               static_cast<const T*>(prob), rows, T_, scale, drop_p, seed)));                                                    \
+        SARSSL_LAUNCH_CHECK();                                                                                                                   \
+        DISPATCH_T(dtype, (attn_unshift_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, smem, stream>>>(static_cast<const T*>(dattn_inout), \
+                               static_cast<T*>(dpos), B, H, T_)));                                                                               \
+    } while (0)
+    if (vec) {
+        if (T_ <= 256) SCORE_BWD(1);
+        else if (T_ <= 512) SCORE_BWD(2);
+        else SCORE_BWD(4);
+    } else {
         DISPATCH_T(dtype, (attn_softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout), static_cast<const T*>(prob),
                                                                                                     rows, T_, scale, drop_p, seed)));
-    SARSSL_LAUNCH_CHECK();
-    if (vec)
-        DISPATCH_T(dtype, (attn_unshift_vec_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(dattn_inout), static_cast<T*>(dpos), B, H, T_)));
-    else
+        SARSSL_LAUNCH_CHECK();
         DISPATCH_T(dtype, (attn_unshift_kernel<T><<<ew_grid(rows * T_), 256, 0, stream>>>(static_cast<const T*>(dattn_inout), static_cast<T*>(dpos), B, H, T_)));
+    }
+#undef SCORE_BWD
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -228,10 +228,12 @@ def test_pretrain_evaluate_matches_oracle_math():
     assert res["pesq"].shape == (nb, 2)
 
 
-def test_long_clip_nt1024_config5():
-    """BASELINE.json configs[4] shape (16.4 s clips, nt = 1024): the attention / score kernels leave their T <= 256 fast paths.
-    fp32 forward vs the CPU oracle (1e-4), then a bf16 forward + backward: loss within 2e-2 of fp32, finite gradients."""
-    nb, nt = 1, 1024
+@pytest.mark.parametrize("nt", [1024, 512, 264])
+def test_long_clip_config5(nt):
+    """BASELINE.json configs[4] shape (16.4 s clips, nt = 1024) and the other chunk counts of the score kernels (2 and 4 chunks of 256
+    columns per lane, a ragged last chunk).  fp32 forward vs the CPU oracle (1e-4), then a bf16 forward + backward: loss within 2e-2
+    of fp32, finite gradients."""
+    nb = 1
     sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=21)
     m = build(nt)
     L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
