@@ -388,14 +388,18 @@ def run_finetune(args):
     for _ in range(max(3, args.warmup)):
         step()
     ms = timed(step, args.steps)
-    e2e_ms = timed(lambda: L.train_epoch([(host_sig, {"TDOA": host_lab})] * args.steps, lr=1e-5), 1)
+    # end to end through the reference-facing call with host buffers; an epoch re-creates Adam (like the reference), so it is warmed up once
+    # and timed over enough steps that this per-epoch cost does not dominate a 7 ms step
+    e2e_steps = max(args.steps, 20)
+    L.train_epoch([(host_sig, {"TDOA": host_lab})] * 2, lr=1e-5)
+    e2e_ms = timed(lambda: L.train_epoch([(host_sig, {"TDOA": host_lab})] * e2e_steps, lr=1e-5), 1)
     if rank == 0:
         line = {"metric": "finetune_clips_per_s", "value": nb * world * args.steps / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": f"downstream fine-tune step (TDOA head, MSE, Adam), 2-mic, {FT_NSAMPLE} samples (1.04 s), batch {nb}/GPU (BASELINE.json configs[3])",
                            "per_gpu_batch": nb, "nt": FT_NT, "parallelism": f"dp{world}"},
-                "e2e": {"value": nb * world * args.steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
+                "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": int(model.engine.k.launches)}
         if world == 1 and not args.no_cpu_baseline:
