@@ -6,8 +6,8 @@ import torch
 
 def run(dev):
     from oracle import sarssl_oracle as O
-    from .learner import STFTLearner
-    from .model import SARSSL
+    from sarssl_b200.learner import STFTLearner
+    from sarssl_b200.model import SARSSL
     nb, nt = 2, 8
     sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=2)
     m = SARSSL(sig_shape=(256, nt, 2, 2), device=dev)
