@@ -125,7 +125,9 @@ def run_reference_arm(args):
     sample = f"{nb} clips/step x {steps} steps (+{warmup} warm-up) of the same training step, oracle port of the reference (torch CPU fp32, dropout on)"
     line = {"impl": "reference", "metric": "pretrain_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * nb / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args.gpus, nb, "f32"),
+            "data": "synthetic",
+            # the same workload name as our arm (the driver matches the two lines); each timed step is a bounded sample of it
+            "config": dict(workload_config(args.gpus, args.batch, args.dtype), reference_step=f"{nb} clips per step, fp32, all {cores} host cores"),
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
