@@ -69,7 +69,9 @@ int sarssl_stft_spectrum(const float* sig, float* spec, int nb, long long nsampl
 size_t sarssl_stft_workspace_bytes(int nb, long long nsample, int nch, int generic);
 int sarssl_stft_frontend(const float* sig, float* patches, int nb, long long nsample, int nch, int win_len, int hop, int nfft,
                          float eps, int force_generic, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-/* Synchronises `stream`; *flag_host != 0 means the fused kernel's clip rendezvous timed out (never expected). */
+/* Synchronises `stream`; *flag_host != 0 means the fused kernel's clip rendezvous timed out (never expected) in some launch
+ * on this workspace: the flag is sticky (only a fresh zeroed workspace clears it), so one check per epoch covers every step.
+ * The workspace must be zero-initialised when it is first handed to sarssl_stft_frontend. */
 int sarssl_stft_frontend_error_flag(const void* workspace, int* flag_host, cudaStream_t stream);
 
 /* ISTFT.forward (inv=False)                                               common/utils_module.py:91-113

@@ -26,7 +26,7 @@ def sample_idx(n, k=16):
     return np.unique(np.linspace(0, n - 1, num=min(k, n)).astype(np.int64))
 
 
-def run_case(name, nb, nt, sig_seed, sd_seed, mask_seed, keep_full):
+def run_case(name, nb, nt, sig_seed, sd_seed, mask_seed, keep_full, grad_samples=0):
     rm, rl, rops, ru = ref_shim.load_reference()
     nsample = (nt + 1) * 256
     sig = O.synthetic_waveforms(nb, nsample, 2, seed=sig_seed)
@@ -96,6 +96,10 @@ def run_case(name, nb, nt, sig_seed, sd_seed, mask_seed, keep_full):
         out["grad_idx/" + k] = idx
         out["grad_val/" + k] = g.numpy()[idx]
         out["grad_norm/" + k] = float(g.norm())
+        if grad_samples:                   # a large pseudo-random sample for norm-wise gradient gates (indices are re-derived, not stored)
+            out["grad_rand/" + k] = g.numpy()[O.fixture_sample_idx(k, g.numel(), grad_samples)].astype(np.float32)
+    if grad_samples:
+        out["grad_samples"] = grad_samples
     for k, v in net.state_dict().items():
         if "running_" in k:
             out["bn/" + k] = v.numpy().copy()
@@ -169,5 +173,6 @@ if __name__ == "__main__":
     lr_table()
     run_case("tiny_nt16_b3", nb=3, nt=16, sig_seed=5, sd_seed=7, mask_seed=11, keep_full=True)
     run_case("full_nt256_b2", nb=2, nt=256, sig_seed=6, sd_seed=7, mask_seed=400000001, keep_full=False)
+    run_case("full_nt256_b8", nb=8, nt=256, sig_seed=16, sd_seed=7, mask_seed=400000003, keep_full=False, grad_samples=2048)
     run_downstream_case("downstream_nt16_b4", nb=4, nt=16, embed="spec_spat", sig_seed=8, sd_seed=9)
     run_downstream_case("downstream_spat_nt64_b2", nb=2, nt=64, embed="spat", sig_seed=10, sd_seed=9)

@@ -424,6 +424,18 @@ def synthetic_waveforms(nb, nsample, nch=2, seed=1234):
     return torch.stack(chans, dim=-1).contiguous()
 
 
+def fixture_sample_idx(key, n, k):
+    """Deterministic pseudo-random sample of min(k, n) element indices of a tensor with n elements (sorted, unique), keyed by the
+    tensor's name: the gradient fixtures store the reference's values at these positions instead of whole 17.5 M-element gradients
+    (an evenly spaced sample would alias with the tap / channel structure of the convolution weights)."""
+    import zlib
+    import numpy as np
+    if n <= k:
+        return np.arange(n, dtype=np.int64)
+    rng = np.random.default_rng(zlib.crc32(key.encode()))
+    return np.sort(rng.choice(n, size=k, replace=False)).astype(np.int64)
+
+
 def adam_step(params, grads, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
     """torch.optim.Adam (weight_decay 0, amsgrad off) as used at learner.py:83: in-place on the lists."""
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step

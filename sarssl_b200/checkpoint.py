@@ -59,9 +59,14 @@ class CheckpointMixin:
             return True
         return False
 
-    def save_checkpoint(self, epoch, checkpoints_dir, is_best_epoch=False, save_extra_hist=False):
-        """learner.py:344-374"""
-        state = {"epoch": epoch, "max_score": self.max_score, "model": self.model.state_dict()}
+    def save_checkpoint(self, epoch, checkpoints_dir, is_best_epoch=False, save_extra_hist=False, dataparallel_keys=False):
+        """learner.py:344-374.  dataparallel_keys=True writes every key with the `module.` prefix an nn.DataParallel-wrapped reference
+        model expects (learner.py:28-31: after mul_gpu() the reference saves and loads `module.`-prefixed state_dicts); the default
+        writes the plain keys a single-GPU reference run reads.  Our own loaders accept both."""
+        sd = self.model.state_dict()
+        if dataparallel_keys:
+            sd = {"module." + k: v for k, v in sd.items()}
+        state = {"epoch": epoch, "max_score": self.max_score, "model": sd}
         if self.use_amp:
             state["scaler"] = self.scaler.state_dict()
         torch.save(state, _path(checkpoints_dir, "latest_model.tar"))

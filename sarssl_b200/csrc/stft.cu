@@ -449,6 +449,14 @@ __global__ void pair_normalize_kernel(const float2* __restrict__ spec, const flo
 
 static int items_per_clip(int nt) { return (nt + kFPI - 1) / kFPI; }
 
+// Clears the work-queue head and the per-clip arrival counters; counters[1], the rendezvous-timeout flag, is STICKY: it is only ever
+// set by the kernels, so a caller can check it once per epoch (sarssl_stft_frontend_error_flag) instead of once per launch.
+static cudaError_t reset_counters(unsigned* counters, int nb, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(counters + 2, 0, 248 + (size_t)nb * sizeof(unsigned), stream);
+}
+
 }  // namespace sarssl
 
 using namespace sarssl;
@@ -527,7 +535,7 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
         const int ipc3 = (nt + kPF - 1) / kPF;
         const long long resident3 = (long long)max_ctas_v3 * sm_count(), items3 = (long long)nb * ipc3;
         if (nch == 2 && (nsample % 2 == 0) && resident3 >= ipc3) {
-            SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
+            SARSSL_CUDA(reset_counters(counters, nb, stream));
             const int grid = (int)(items3 < resident3 ? items3 : resident3);
             stft_frontend_pipe_kernel<<<grid, kThreads, sizeof(PipeSmem), stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt,
                                                                                    ipc3, eps);
@@ -553,7 +561,7 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     // (the warp-worker kernel needs every frame of a clip's round resident: resident warps >= nt)
     const bool fused_ok = force_generic != 1 && nch == 2 && (nsample % 2 == 0) && max_ctas_per_sm > 0 &&
                           (v1 ? resident >= ipc : resident * kWarpsPerCta >= nt);
-    SARSSL_CUDA(cudaMemsetAsync(counters, 0, 256 + (size_t)nb * sizeof(unsigned), stream));
+    SARSSL_CUDA(reset_counters(counters, nb, stream));
     if (fused_ok) {
         const long long items = (long long)nb * ipc;
         const int grid = (int)(items < resident ? items : resident);

@@ -124,7 +124,7 @@ class WaveformBatchLoader:
         self.epoch = epoch
 
     def __len__(self):
-        n = len(self.ds) // self.world
+        n = len(self._order())                        # same truncation as iteration: whole global batches only when world > 1
         return n // self.bs if self.drop_last else (n + self.bs - 1) // self.bs
 
     def _order(self):
@@ -162,10 +162,22 @@ class WaveformBatchLoader:
             return ds.annotations(ids[j]) if ds.load_anno else None
 
         annos = list(pool.map(one, range(len(ids))))
+        ret = [batch]
         if ds.load_anno:
             keys = annos[0].keys()
-            return [batch, {k: torch.from_numpy(np.stack([np.asarray(a[k], dtype=np.float32) for a in annos])) for k in keys}]      # stacked like default_collate
-        return [batch]
+            ret.append({k: torch.from_numpy(np.stack([np.asarray(a[k], dtype=np.float32) for a in annos])) for k in keys})      # stacked like default_collate
+        if ds.load_dp:                                 # direct-path signals as the last item, like FixMicSigDataset.__getitem__ (dataset.py:170-176)
+            dp = torch.empty_like(batch)
+
+            def one_dp(j):
+                sig = torch.as_tensor(ds._signal(str(ds.files[ids[j]]).replace(".wav", "_dp.wav")))
+                m = min(ns, sig.shape[0])
+                dp[j, :m] = sig[:m]
+                dp[j, m:] = 0
+
+            list(pool.map(one_dp, range(len(ids))))
+            ret.append(dp)
+        return ret
 
     def __iter__(self):
         order = self._order()

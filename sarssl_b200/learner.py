@@ -103,28 +103,57 @@ class Learner(CheckpointMixin, ABC):
                 t.record_stream(compute)         # allocated on the copy stream, consumed on the compute stream
             yield out
 
-    def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True):
+    def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True, accum_steps=1):
         """learner.py:76-131: one epoch of pre-training.  A fresh Adam (moments reset) per epoch like the reference; loss / diff
-        of every step are kept on the device and read back once at the end of the epoch (the reference syncs 3x per step)."""
+        of every step are kept on the device and read back once at the end of the epoch (the reference syncs 3x per step).
+
+        accum_steps > 1: gradient accumulation - `accum_steps` consecutive micro-batches form one optimizer step (their gradients
+        add up in the flat gradient arena, 1/accum_steps is folded into the Adam kernel, and under data parallelism the all-reduce
+        runs once per optimizer step instead of once per micro-batch).  This is how 1 / 2 / 4 GPUs reach BASELINE.json's global batch
+        of 2048 with 256-clip micro-batches; BatchNorm statistics stay per micro-batch, as under the reference's
+        DataParallel replicas.  A trailing partial group is applied with its real count."""
         from .optim import FusedAdam
         self.model.train()
         optimizer = FusedAdam(self.model, lr=lr)
         optimizer.zero_grad()
         sync = getattr(self, "grad_sync", None)
-        log, vis_batch = [], None
+        accum_steps = max(int(accum_steps), 1)
+        log, vis_batch, pending = [], None, 0
+
+        def apply(count):
+            scale = 1.0 / count
+            if sync is not None:
+                scale *= sync.all_reduce()
+            optimizer.step(lr, grad_scale=scale, zero_grad=True)
+
         for batch_idx, (mic_sig_batch,) in enumerate(self.device_batches(dataset)):
             in_batch, = self.data_preprocess(mic_sig_batch, None)
+            if sync is not None:
+                sync.defer = pending + 1 < accum_steps      # only the last micro-batch of a group announces its buckets
             loss_batch, diff_batch, vis_batch = self.model(in_batch)
             loss_batch.backward()
-            scale = 1.0
-            if sync is not None:
-                scale = sync.all_reduce()
-            optimizer.step(lr, grad_scale=scale, zero_grad=True)
+            pending += 1
+            if pending == accum_steps:
+                apply(pending)
+                pending = 0
             log.append(torch.stack([loss_batch.detach(), diff_batch.detach()]))
-        vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]
+        if pending:
+            apply(pending)
+        vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]      # the epoch's only device -> host read
+        self.check_frontend()
         if return_diff:
             return vals[0], vals[1], vis_batch
         return vals[0]
+
+    def check_frontend(self):
+        """Raise if the fused front-end kernel's per-clip rendezvous ever timed out during the epoch (it would have written
+        patches scaled with an incomplete mean).  Reads one flag; called right after the epoch's loss read-back, when the
+        device is idle anyway."""
+        if torch.device(self.device).type == "cuda":
+            dev = torch.device(self.device)
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            ops.stft_frontend_check(dev)
 
     def pretest_epoch(self, dataset, return_diff=True, return_eval=False):
         """learner.py:133-167: eval-mode pass (BatchNorm running statistics, no dropout, masks still random)."""
@@ -136,6 +165,7 @@ class Learner(CheckpointMixin, ABC):
                 loss_batch, diff_batch, vis_batch = self.model(in_batch)
                 log.append(torch.stack([loss_batch, diff_batch]))
         vals = torch.stack(log).mean(0).tolist() if log else [0.0, 0.0]
+        self.check_frontend()
         if return_diff:
             if return_eval:      # metrics of the last batch only, like the reference (learner.py:160-162)
                 result = self.pretrain_evaluate(pred_batch=vis_batch["pred"], gt_batch=vis_batch["tar"], mask_batch=vis_batch["mask"])
@@ -208,6 +238,7 @@ class STFTLearner(Learner):
             if return_metric:
                 metrics.append(self.evaluate(pred_batch=pred_batch, gt_batch=tar_batch))
         loss = float(torch.stack(losses).mean()) if losses else 0.0
+        self.check_frontend()
         if return_metric:
             return loss, (torch.stack(metrics).mean() if metrics else torch.zeros(()))
         return loss

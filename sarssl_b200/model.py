@@ -55,7 +55,7 @@ class _PretrainFn(torch.autograd.Function):
     def forward(ctx, anchor, model, patches, flag, ch, want):
         out2, pred, saved = model.engine.forward(patches, flag, ch, model.nmasked_patch, training=model.training, want_grad=want)
         ctx.model, ctx.saved = model, saved
-        model._last = {"pred": pred, "saved": saved}
+        model._last = {"pred": pred}          # only the prediction (data_vis); the saved activations live in ctx until backward frees them
         return out2[0].clone(), out2[1].clone()
 
     @staticmethod

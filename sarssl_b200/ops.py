@@ -42,7 +42,7 @@ def _workspace(device, nbytes, tag):
     key = (str(device), tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)      # zeroed: the front-end's sticky error flag lives here
         _ws_cache[key] = buf
     return buf
 
@@ -71,7 +71,8 @@ def stft_frontend(signal, eps=1e-6, win_len=WIN, hop=HOP, nfft=NFFT, force_gener
 
 
 def stft_frontend_check(device):
-    """Debug helper: synchronises and raises if the fused kernel's clip rendezvous ever timed out."""
+    """Synchronises and raises if the fused kernel's clip rendezvous timed out in ANY launch since the workspace was created (the
+    flag is sticky).  Learner checks it once per epoch, at the loss read-back."""
     ws = _ws_cache.get((str(device), "stft"))
     if ws is None:
         return

@@ -47,6 +47,7 @@ class GradientSync:
         self.buckets = bucket_ranges(model.store)
         self.pending = {name for name, _, _ in self.buckets}
         self.stream = None
+        self.defer = False                  # True while accumulating micro-batches: backward must not start the exchange yet
         if backend == "nccl":
             L = lib()
             nbytes = L.sarssl_comm_unique_id_bytes()
@@ -63,7 +64,7 @@ class GradientSync:
 
     # called by the engine as backward finishes each parameter group
     def bucket_ready(self, name):
-        if name not in self.pending:
+        if self.defer or name not in self.pending:      # gradient accumulation: only the group's last backward announces buckets
             return
         self.pending.discard(name)
         _, off, n = next(b for b in self.buckets if b[0] == name)
@@ -80,6 +81,7 @@ class GradientSync:
     def all_reduce(self):
         """Finish the exchange (reduce whatever backward did not announce), make the compute stream wait for it, and return the
         1/world scale the optimizer applies."""
+        self.defer = False
         for name, _, _ in self.buckets:
             self.bucket_ready(name)
         if self.backend == "nccl":

@@ -1,4 +1,5 @@
-"""GPU: the CNN-stem kernels.  CUDA-core 3x3 conv / wgrad vs torch (CPU fp32 conv2d); tcgen05 versions vs the CUDA-core ones."""
+"""GPU: the CNN-stem kernels.  CUDA-core 3x3 conv / wgrad vs torch (CPU fp32 conv2d); tcgen05 versions vs a plain PyTorch fp32
+conv2d / its autograd weight gradient (TF32 off) on the same bf16 operands."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,8 +10,21 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+torch.backends.cuda.matmul.allow_tf32 = False          # fp32 torch references must not run on TF32 tensor cores
+torch.backends.cudnn.allow_tf32 = False
+
+
 def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def unpack(wp):      # [o][tap = kw*3 + kh][ci] -> torch (o, ci, kh[bin], kw[frame])
+    return wp.reshape(64, 3, 3, 64).permute(0, 3, 2, 1).contiguous()
+
+
+def conv_ref_fp32(x, wp):
+    """x [B][H = frame][W = bin][64] (any float dtype), packed weights -> fp32 conv2d in our layout."""
+    return F.conv2d(x.float().permute(0, 3, 2, 1), unpack(wp.float()), padding=1).permute(0, 3, 2, 1).contiguous()
 
 
 def pack(w):        # reference (o, ci, kh[bin], kw[frame]) -> [o][tap = kw*3 + kh][ci]   (image is [frame][bin])
@@ -45,18 +59,18 @@ def test_simt_conv3x3_and_wgrad_fp32_vs_torch(B, H, W):
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 1, 128), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 5, 64), (8, 256, 256)])
-def test_tc_conv3x3_matches_simt(B, H, W):
+def test_tc_conv3x3_vs_torch_fp32(B, H, W):
     k = KernelSet(DEV, torch.bfloat16)
     g = torch.Generator(device=DEV).manual_seed(B * 7 + H + W)
     x = torch.randn(B, H, W, 64, device=DEV, generator=g).bfloat16()
     wp = (torch.randn(64, 9, 64, device=DEV, generator=g) / 24).bfloat16()
-    ref, out = torch.empty(B, H, W, 64, device=DEV, dtype=torch.bfloat16), torch.full((B, H, W, 64), 7.0, device=DEV, dtype=torch.bfloat16)
-    k.conv3x3(x, None, wp, ref, B, H, W)
+    out = torch.full((B, H, W, 64), 7.0, device=DEV, dtype=torch.bfloat16)
+    ref = conv_ref_fp32(x, wp)
     gamma, beta = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV)
     rm, rv, nbt = torch.zeros(64, device=DEV), torch.ones(64, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
     stats = k.conv3x3_tc(x, wp, out, B, H, W, bn=(gamma, beta, rm, rv, nbt))
     torch.cuda.synchronize()
-    assert rel(out.float(), ref.float()) < 3e-3, rel(out.float(), ref.float())     # both round the same fp32 sums to bf16
+    assert rel(out.float(), ref) < 3e-3, rel(out.float(), ref)     # one bf16 rounding of the fp32 sums
     # fused BatchNorm statistics of the (bf16-rounded) conv output
     o = out.float().reshape(-1, 64)
     mean, var = o.mean(0), o.var(0, unbiased=False)
@@ -65,16 +79,17 @@ def test_tc_conv3x3_matches_simt(B, H, W):
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 1, 64), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 70, 64), (8, 256, 256)])
-def test_tc_conv3x3_wgrad_matches_simt(B, H, W):
+def test_tc_conv3x3_wgrad_vs_torch_fp32(B, H, W):
     k = KernelSet(DEV, torch.bfloat16)
     g = torch.Generator(device=DEV).manual_seed(B * 5 + H + W)
     z = torch.randn(B, H, W, 64, device=DEV, generator=g).bfloat16()
     dy = (torch.randn(B, H, W, 64, device=DEV, generator=g) / (B * H * W) ** 0.5).bfloat16()
-    ref, out = torch.empty(64, 9, 64, device=DEV), torch.empty(64, 9, 64, device=DEV)
-    k.conv3x3_wgrad(dy, z, None, ref, B, H, W)
+    out = torch.empty(64, 9, 64, device=DEV)
     k.conv3x3_wgrad_tc(dy, z, out, B, H, W)
     torch.cuda.synchronize()
-    assert rel(out, ref) < 1e-4, rel(out, ref)
+    w = torch.zeros(64, 64, 3, 3, device=DEV, requires_grad=True)
+    F.conv2d(z.float().permute(0, 3, 2, 1), w, padding=1).backward(dy.float().permute(0, 3, 2, 1))
+    assert rel(out, pack(w.grad)) < 1e-4, rel(out, pack(w.grad))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -1,5 +1,6 @@
-"""GPU: the two GEMM kernels through the C ABI.  CUDA-core kernel vs torch (CPU fp32 matmul); tensor-core (tcgen05) kernel vs
-the CUDA-core kernel on identical bf16 operands (both accumulate in fp32, so they agree to accumulation-order noise)."""
+"""GPU: the two GEMM kernels through the C ABI.  CUDA-core kernel vs torch (CPU fp32 matmul); tensor-core (tcgen05) kernel vs a plain
+PyTorch fp32 matmul (TF32 off) of the same bf16 operands (products of bf16 values are exact in fp32, both sides accumulate in fp32, so
+they agree to accumulation-order noise), plus the CUDA-core kernel as a second witness for the fused epilogue / dropout pattern."""
 import ctypes as C
 
 import pytest
@@ -12,8 +13,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+torch.backends.cuda.matmul.allow_tf32 = False          # the fp32 torch references below must not run on TF32 tensor cores
+torch.backends.cudnn.allow_tf32 = False
+
+
 def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def mm32(A, B):
+    """fp32 reference: A [M, K] @ B [N, K]^T with fp32 accumulation of the (exact) bf16 products."""
+    return A.float() @ B.float().t()
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 64, 16), (100, 70, 33), (257, 129, 200), (1, 5, 7)])
@@ -82,20 +92,22 @@ def _tc(k, A, B, Cmat, M, N, K, sA, sB, ldc, **kw):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 200, 136), (4096, 512, 2048), (128, 64, 64), (1000, 48, 1024),
                                    (65536 // 8, 1024, 3072)])
-def test_tc_gemm_k_major_matches_simt(M, N, K):
+def test_tc_gemm_k_major_vs_torch_fp32(M, N, K):
     k = KernelSet(DEV, torch.bfloat16)
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
     A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
     B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
-    ref, out = k.empty(M, N, dtype=torch.float32), k.empty(M, N, dtype=torch.float32)
-    k.use_tc = False
-    k.linear(A, B, ref, M, N, K)
+    out = k.empty(M, N, dtype=torch.float32)
     _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N)
     torch.cuda.synchronize()
-    assert rel(out, ref) < 1e-4, rel(out, ref)
+    assert rel(out, mm32(A, B)) < 5e-5, rel(out, mm32(A, B))          # fp32 accumulation order / tensor-core alignment truncation only
+    outb = k.empty(M, N)                                   # bf16 output (TMA-store epilogue when N % 32 == 0): one rounding of the fp32 sum
+    _tc(k, A, B, outb, M, N, K, (K, 1), (K, 1), N)
+    torch.cuda.synchronize()
+    assert rel(outb.float(), mm32(A, B)) < 3e-3
 
 
-def test_tc_gemm_epilogue_matches_simt():
+def test_tc_gemm_epilogue_vs_torch_fp32():
     k = KernelSet(DEV, torch.bfloat16)
     M, N, K = 384, 256, 192
     g = torch.Generator(device=DEV).manual_seed(3)
@@ -109,8 +121,21 @@ def test_tc_gemm_epilogue_matches_simt():
     k.linear(A, B, ref, M, N, K, pre=pre_ref, **kw)
     _tc(k, A, B, out, M, N, K, (K, 1), (K, 1), N, pre=pre, **kw)
     torch.cuda.synchronize()
+    u = mm32(A, B) + bias                                    # plain PyTorch fp32 restatement of the epilogue
+    assert rel(pre.float(), u) < 3e-3                         # bf16 rounding of the stored pre-activation
+    kept = out != R                                          # dropped entries are exactly the residual
+    assert 0.85 < float(kept.float().mean()) < 0.95
+    want = R.float() + 0.5 * (u * torch.sigmoid(u)) / 0.9
+    assert rel(out.float()[kept], want[kept]) < 5e-3
+    assert torch.equal(out == R, ref == R)                     # identical dropout pattern as the CUDA-core kernel (same counter-based generator)
     assert rel(pre.float(), pre_ref.float()) < 1e-3 and rel(out.float(), ref.float()) < 5e-3
-    assert torch.equal(out == R, ref == R)                     # identical dropout pattern
+    # every compile-time epilogue variant of the model's layer types, without dropout, against torch
+    for kw2, fn in ((dict(bias=bias), lambda u0: u0 + bias), (dict(bias=bias, act=ACT_RELU), lambda u0: torch.relu(u0 + bias)),
+                    (dict(), lambda u0: u0), (dict(bias=bias, resid=R, ldr=N, beta=1.0), lambda u0: R.float() + u0 + bias)):
+        o2 = k.empty(M, N)
+        _tc(k, A, B, o2, M, N, K, (K, 1), (K, 1), N, **kw2)
+        torch.cuda.synchronize()
+        assert rel(o2.float(), fn(mm32(A, B))) < 3e-3, kw2.keys()
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 256, 4096), (200, 72, 1000), (1024, 64, 8192), (2048, 512, 65536 // 4)])
@@ -120,13 +145,12 @@ def test_tc_gemm_mn_major_weight_gradient(M, N, K):
     g = torch.Generator(device=DEV).manual_seed(M * 3 + N + K)
     dY = torch.randn(K, M, device=DEV, generator=g).bfloat16()
     X = (torch.randn(K, N, device=DEV, generator=g) / K ** 0.5).bfloat16()
-    ref, out = k.zeros_f32(M, N), k.zeros_f32(M, N)
-    k.use_tc = False
-    k.gemm(dY, X, ref, M, N, K, (1, M), (1, N), N, accumulate=True)
+    out = k.zeros_f32(M, N)
     _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)
     _tc(k, dY, X, out, M, N, K, (1, M), (1, N), N, accumulate=True)          # accumulates: 2x
     torch.cuda.synchronize()
-    assert rel(out, 2 * ref) < 1e-4, rel(out, 2 * ref)      # fp32 accumulation-order noise only
+    ref = dY.float().t() @ X.float()
+    assert rel(out, 2 * ref) < 5e-5, rel(out, 2 * ref)      # fp32 accumulation-order noise only
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 520, 2048), (512, 64, 256)])
@@ -136,12 +160,34 @@ def test_tc_gemm_data_gradient_mixed_majors(M, N, K):
     g = torch.Generator(device=DEV).manual_seed(M + 7 * N + K)
     dY = torch.randn(M, K, device=DEV, generator=g).bfloat16()
     W = (torch.randn(K, N, device=DEV, generator=g) / K ** 0.5).bfloat16()
-    ref, out = k.empty(M, N, dtype=torch.float32), k.empty(M, N, dtype=torch.float32)
-    k.use_tc = False
-    k.gemm(dY, W, ref, M, N, K, (K, 1), (1, N), N)
+    ref = dY.float() @ W.float()
+    out = k.empty(M, N, dtype=torch.float32)
     _tc(k, dY, W, out, M, N, K, (K, 1), (1, N), N)
     Wt, dYt = W.T.contiguous(), dY.T.contiguous()
     out2 = k.empty(M, N, dtype=torch.float32)
     _tc(k, dYt, Wt, out2, M, N, K, (1, M), (K, 1), N)              # A MN-major, B K-major
     torch.cuda.synchronize()
-    assert rel(out, ref) < 1e-4 and rel(out2, ref) < 1e-4
+    assert rel(out, ref) < 5e-5 and rel(out2, ref) < 5e-5
+
+
+def test_tc_gemm_batched_attention_shapes_vs_torch_fp32():
+    """The batched (4-D tensor map) forms the attention contractions use (engine.py: content / pos / context / their gradients)."""
+    k = KernelSet(DEV, torch.bfloat16)
+    B, H, T, D = 3, 4, 256, 256
+    dh = D // H
+    g = torch.Generator(device=DEV).manual_seed(5)
+    qkv = (torch.randn(B * T, 3 * D, device=DEV, generator=g) / 4).bfloat16()
+    qu = (torch.randn(B * T, D, device=DEV, generator=g) / 4).bfloat16()
+    content = k.empty(B, H, T, T)
+    k.gemm(qu, qkv, content, T, T, dh, (D, 1), (3 * D, 1), T, b_off=D, batch=(B, H), sAb=(T * D, dh), sBb=(T * 3 * D, dh), sCb=(H * T * T, T * T))
+    q4 = qu.float().view(B, T, H, dh).permute(0, 2, 1, 3)
+    k4 = qkv.float()[:, D:2 * D].reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    assert k.tc_launches == 1
+    assert rel(content.float(), q4 @ k4.transpose(-1, -2)) < 3e-3
+    prob = torch.softmax(content.float(), -1).bfloat16()
+    ctx = k.empty(B * T, D)
+    k.gemm(prob, qkv, ctx, T, dh, T, (T, 1), (1, 3 * D), D, b_off=2 * D, batch=(B, H), sAb=(H * T * T, T * T), sBb=(T * 3 * D, dh), sCb=(T * D, dh))
+    v4 = qkv.float()[:, 2 * D:].reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    want = (prob.float() @ v4).permute(0, 2, 1, 3).reshape(B * T, D)
+    assert k.tc_launches == 2
+    assert rel(ctx.float(), want) < 3e-3

@@ -1,0 +1,186 @@
+"""GPU: the training-step pieces around the model: fused Adam against the oracle's restatement of
+torch.optim.Adam, frozen parameters, gradient accumulation, the foreign-layout branch of as_patch_layout, and the north-star
+bf16 gate (loss and every gradient tensor within 2e-2, norm-wise) at the benchmarked clip size against fixtures the real
+reference produced (tests/golden/full_nt256_b{2,8}.npz, oracle/make_golden.py)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sarssl_oracle as O
+from sarssl_b200 import _lib
+from sarssl_b200.learner import STFTLearner
+from sarssl_b200.model import SARSSL
+from sarssl_b200.modules import as_patch_layout
+from sarssl_b200.optim import FusedAdam
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def build(nt, sd_seed=7, dtype=torch.float32, pretrain=True, **kw):
+    m = SARSSL(sig_shape=(256, nt, 2, 2), device=DEV, pretrain=pretrain, **kw)
+    m.load_state_dict(O.synthetic_state_dict(sd_seed, pretrain=pretrain, dembed_ds=768))
+    m.to(DEV)
+    m.set_dropout(0.0)
+    m.set_compute_dtype(dtype)
+    m.train()
+    L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None if pretrain else "TDOA", ch_mode="M")
+    L.device = DEV
+    return m, L
+
+
+# ---------------------------------------------------------------------------------------------------------------- A14: Adam
+def test_fused_adam_matches_oracle_three_steps():
+    """sarssl_adam_step (csrc/optim.cu) vs oracle.adam_step (= torch.optim.Adam, learner.py:83,111) over the whole 17.5 M-element
+    arena: three steps with fresh random gradients, a gradient scale (1/world or 1/accum) and the zero_grad side effect."""
+    m, _ = build(16)
+    st = m.store
+    opt = FusedAdam(m, lr=1e-3)
+    names = list(st.params)
+    ref_p = [st.p(k).detach().cpu().clone() for k in names]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for step, (lr, scale) in enumerate(((1e-3, 1.0), (7e-4, 0.5), (2e-4, 0.125)), start=1):
+        st.grad.copy_(torch.randn(st.total, device=DEV, generator=g) * (10.0 ** (step - 3)))
+        grads = [st.g(k).detach().cpu().clone() * scale for k in names]
+        opt.step(lr, grad_scale=scale, zero_grad=True)
+        O.adam_step(ref_p, grads, ref_m, ref_v, step, lr)
+        assert float(st.grad.abs().max()) == 0.0                       # cleared for the next step
+        worst = max(rel(st.p(k).detach().cpu(), r) for k, r in zip(names, ref_p))
+        assert worst < 1e-6, (step, worst)
+        o, n = st.offsets["decoder.proj.0.weight"]
+        assert rel(opt.m[o:o + n].cpu(), ref_m[names.index("decoder.proj.0.weight")].reshape(-1)) < 1e-6
+        assert rel(opt.v[o:o + n].cpu(), ref_v[names.index("decoder.proj.0.weight")].reshape(-1)) < 1e-6
+
+
+def test_frozen_parameters_stay_bit_identical_through_train_epoch():
+    """requires_grad=False (load_checkpoint_best(param_frozen=True), learner.py:441-446; linear evaluation of
+    run_downstream.py:256) must be honoured by the fused optimizer exactly like torch.optim.Adam skipping those parameters."""
+    nt = 16
+    m, L = build(nt, sd_seed=9, pretrain=False)
+    for k, p in m.named_parameters():
+        if "encoder" in k:
+            p.requires_grad = False
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    sig = O.synthetic_waveforms(4, (nt + 1) * 256, 2, seed=8)
+    labels = torch.linspace(-2e-4, 2e-4, 4)
+    L.train_epoch([(sig, {"TDOA": labels})] * 3, lr=1e-3)
+    moved = 0
+    for k, p in m.named_parameters():
+        if "encoder" in k:
+            assert torch.equal(p.detach(), before[k]), k               # bit-identical
+        else:
+            moved += int(not torch.equal(p.detach(), before[k]))
+    assert moved == 4                                                  # the mlp_head (LayerNorm gain / bias, Linear weight / bias) trained
+
+
+def test_gradient_accumulation_equals_one_big_optimizer_step():
+    """pretrain_epoch(accum_steps=2) over micro-batches [a, b] = one Adam step on (grad(a) + grad(b)) / 2 (learner.py:102-113 step
+    semantics; BatchNorm statistics per micro-batch): compare with backward on a and b by hand + one fused step."""
+    nt = 16
+    sa = O.synthetic_waveforms(2, (nt + 1) * 256, 2, seed=31)
+    sb = O.synthetic_waveforms(2, (nt + 1) * 256, 2, seed=32)
+    m1, L1 = build(nt)
+    random.seed(77)
+    L1.pretrain_epoch([[sa], [sb]], lr=1e-3, epoch=1, accum_steps=2)
+    m2, L2 = build(nt)
+    opt = FusedAdam(m2, lr=1e-3)
+    opt.zero_grad()
+    random.seed(77)
+    for s in (sa, sb):
+        x, = L2.data_preprocess(s.to(DEV))
+        loss, _, _ = m2(x)
+        loss.backward()
+    opt.step(1e-3, grad_scale=0.5, zero_grad=True)
+    # (BatchNorm running statistics are updated by both forwards in both runs; split-K partial sums make gradients agree to ~1e-6)
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if k.endswith("key_proj.linear.bias"):       # analytically zero gradient (softmax is shift invariant): pure rounding noise below Adam's eps
+            continue
+        assert torch.allclose(p1, p2, rtol=0, atol=2e-6), k
+    # and it is NOT the same as two separate optimizer steps
+    m3, L3 = build(nt)
+    random.seed(77)
+    L3.pretrain_epoch([[sa], [sb]], lr=1e-3, epoch=1, accum_steps=1)
+    k = "decoder.proj.2.weight"
+    assert not torch.allclose(m3.store.p(k), m1.store.p(k), rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------- A3: layouts
+@pytest.mark.parametrize("nb,nf,nt", [(2, 256, 16), (1, 256, 7), (3, 64, 33)])
+def test_as_patch_layout_on_a_contiguous_reference_layout_tensor(nb, nf, nt):
+    """What the reference's data_preprocess returns is a CONTIGUOUS (nb, 2, nf, nt, 2) tensor (strides (.., 2nt, 2, 1), learner.py:551):
+    the non-view branch (sarssl_to_patch_layout, csrc/layout.cu) must produce PatchSplit's layout vec[b, t, f, r, m] = x[b, m, f, t, r]
+    (utils_module.py:196-205), and the view branch must stay zero-copy."""
+    g = torch.Generator().manual_seed(nb * 100 + nt)
+    x = torch.randn(nb, 2, nf, nt, 2, generator=g)
+    assert x.is_contiguous()
+    out = as_patch_layout(x.to(DEV))
+    assert out.shape == (nb, nt, nf, 2, 2) and out.is_contiguous()
+    assert torch.equal(out.cpu(), x.permute(0, 3, 2, 4, 1).contiguous())
+    v = out.permute(0, 4, 2, 1, 3)                                    # the view our own front-end hands out
+    assert as_patch_layout(v).data_ptr() == out.data_ptr()
+    with pytest.raises(_lib.SarsslError):
+        as_patch_layout(torch.zeros(nb, 3, nf, nt, 2, device=DEV))
+
+
+def test_model_accepts_reference_layout_input():
+    """SARSSL.forward on the reference's contiguous input layout gives the same loss as on our front-end's view."""
+    nt = 16
+    m, L = build(nt)
+    sig = O.synthetic_waveforms(2, (nt + 1) * 256, 2, seed=3)
+    x, = L.data_preprocess(sig.to(DEV))
+    random.seed(5)
+    la, _, _ = m(x)
+    random.seed(5)
+    lb, _, _ = m(x.contiguous())
+    assert float(la) == float(lb)
+
+
+# ---------------------------------------------------------------------------------------------------------------- north-star bf16 gate
+def bf16_gradient_table(fixture, dtype=torch.bfloat16):
+    """[(key, norm-wise relative error on the fixture's sample, reference norm)] of one bf16 step against the real reference's
+    fp32 gradients; plus (loss, reference loss)."""
+    g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"]))
+    m, L = build(nt, int(g["sd_seed"]), dtype=dtype)
+    x, = L.data_preprocess(sig.to(DEV))
+    random.seed(int(g["mask_seed"]))
+    loss, diff, vis = m(x)
+    loss.backward()
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    rows = []
+    for k, p in m.named_parameters():
+        mine = p.grad.detach().reshape(-1).cpu()
+        if "grad_rand/" + k in g.files:
+            idx = O.fixture_sample_idx(k, mine.numel(), int(g["grad_samples"]))
+            ref = torch.from_numpy(g["grad_rand/" + k]).double()
+        else:
+            idx = g["grad_idx/" + k]
+            ref = torch.from_numpy(g["grad_val/" + k]).double()
+        got = mine[torch.from_numpy(idx)].double()
+        floor = 1e-3 * gmax * (len(idx) / mine.numel()) ** 0.5         # analytically-zero gradients (key_proj bias) hold rounding noise only
+        rows.append((k, float((got - ref).norm()) / (float(ref.norm()) + floor), float(g["grad_norm/" + k]),
+                     abs(float(mine.norm()) - float(g["grad_norm/" + k])) / (float(g["grad_norm/" + k]) + 1e-3 * gmax)))
+    return rows, float(loss), float(g["loss"]), m
+
+
+@pytest.mark.parametrize("fixture", ["full_nt256_b8", "full_nt256_b2"])
+def test_bf16_loss_and_gradients_within_2e_2_at_benchmark_clip_size(fixture):
+    """BASELINE.json north star, literally: bf16 mode (tcgen05 GEMM + conv, bf16 activation storage) - loss and every gradient tensor
+    within 2e-2 relative (norm-wise per tensor) of the real reference's fp32 run at the benchmarked clip size (nt = 256)."""
+    rows, loss, ref_loss, m = bf16_gradient_table(fixture)
+    assert m.engine.k.tc_launches > 100
+    assert abs(loss - ref_loss) < 2e-2 * ref_loss
+    worst = max(rows, key=lambda r: r[1])
+    assert worst[1] < 2e-2, ("worst gradient tensor", worst, "median", sorted(r[1] for r in rows)[len(rows) // 2])
+    assert max(r[3] for r in rows) < 2e-2                             # and the whole-tensor norms
