@@ -9,7 +9,11 @@ One JSON line on stdout (rank 0).  metric = pre-training clips/s (BASELINE.json)
 (STFT front-end -> masks -> MC-Conformer forward -> masked reconstruction loss -> backward -> Adam) over one micro-batch of
 synthetic 2-microphone clips per GPU.  `value` has the waveforms resident in HBM; `e2e` goes through the reference-facing
 `STFTLearner.pretrain_epoch` from pinned host memory (H2D of the waveforms + D2H of the loss inside the timed region).
-The front-end + loss sub-path (BASELINE.json configs[1]) is reported in the same line under "frontend".
+The front-end + loss sub-path (BASELINE.json configs[1]) is reported in the same line under "frontend"; the other configurations of
+BASELINE.json (fine-tuning step configs[3], long clips configs[4]) ride along as short sub-runs under "other_configs" (or run alone:
+--workload finetune | longclip); "torch_eager_b200" is the real bar on the same GPU: the reference algorithm in plain PyTorch eager
+(cuDNN / cuBLAS / cuFFT), fp32+TF32 as shipped (run_pretrain.py:33-34) and under autocast(bf16).
+--accum-steps A runs BASELINE.json configs[2] literally (global batch = micro-batch x A x GPUs, one all-reduce + Adam per A micro-batches).
 """
 import argparse
 import json
@@ -73,12 +77,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
-def workload_config(world, per_gpu_batch, dtype):
+def workload_config(world, per_gpu_batch, dtype, accum_steps=1):
     return {"workload": "MC-Conformer pre-training step (STFT front-end + masks + fwd + masked recon loss + bwd + Adam), 2-mic, 65792 samples "
                         f"(4.112 s @16 kHz), micro-batch {per_gpu_batch}/GPU, {dtype} (BASELINE.json configs[2])",
-            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world, "nsample": NSAMPLE, "nmic": 2, "nt": NT, "nf": NF,
-            "dropout": 0.1, "optimizer": "Adam", "l2": "activations per step (tens of GB) far exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"dp{world}"}
+            "per_gpu_batch": per_gpu_batch, "accum_steps": accum_steps, "global_batch": per_gpu_batch * world * accum_steps, "nsample": NSAMPLE, "nmic": 2,
+            "nt": NT, "nf": NF, "dropout": 0.1, "optimizer": "Adam",
+            "l2": "activations per step (tens of GB) far exceed the 126 MB L2; no explicit flush", "parallelism": f"dp{world}"}
+
+
+def measured_traffic(kernel, clips):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json,
+    written by scripts/ncu_summary.py from the .ncu-rep of the same kernel build), scaled to `clips` per launch; None when no capture is recorded."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return rec["dram_bytes_per_clip"] * clips, rec["source"]
+    except Exception:
+        return None, "no ncu capture recorded for this kernel build (profiles/traffic.json)"
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -115,22 +129,111 @@ def cpu_pretrain_clips_per_s(nb, steps, warmup, threads):
     return nb * len(times) / sum(times)
 
 
+def reference_pretrain_clips_per_s(nb, steps, warmup, threads):
+    """The REAL reference (`STFTLearner.pretrain_epoch`, code/learner.py:76-131, per-item Python loops and all) on the host cores, when its
+    source tree is importable (build container: /root/reference/code; it cannot travel to the GPU box).  None when absent."""
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_root() is None:
+            return None
+        import torch
+        rm, rl, _, ru = ref_shim.load_reference()
+    except Exception:
+        return None
+    from oracle import sarssl_oracle as O
+    torch.set_num_threads(threads)
+    ru.set_seed(1)
+    net = rm.SARSSL(sig_shape=(NF, NT, 2, 2), pretrain=True, device="cpu")
+    L = rl.STFTLearner(net, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    L.cpu()
+    sig = O.synthetic_waveforms(nb, NSAMPLE, 2, seed=1234)
+    L.pretrain_epoch([[sig]] * warmup, lr=1e-3, epoch=1)
+    t0 = time.perf_counter()
+    L.pretrain_epoch([[sig]] * steps, lr=1e-3, epoch=1)
+    return nb * steps / (time.perf_counter() - t0)
+
+
+def cpu_arm(nb, steps, warmup, cores):
+    """(clips/s, kind, sample): the real reference when importable (kind "reference"), else the oracle port (kind "port")."""
+    v = reference_pretrain_clips_per_s(nb, steps, warmup, cores)
+    if v is not None:
+        return v, "reference", (f"{nb} clips/step x {steps} steps (+{warmup} warm-up) of the unmodified reference's STFTLearner.pretrain_epoch "
+                                "(torch CPU fp32, dropout on, its own per-item loops)")
+    v = cpu_pretrain_clips_per_s(nb, steps, warmup, cores)
+    return v, "port", (f"{nb} clips/step x {steps} steps (+{warmup} warm-up) of the same training step, oracle port of the reference (torch CPU fp32, "
+                       "dropout on); the reference source tree is not present on this box. Build-container calibration (8 cores): see DESIGN.md section 6")
+
+
 def run_reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
     nb = 8                                                   # BASELINE.json configs[0]: the reference's own CPU-runnable case
-    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
-    v = cpu_pretrain_clips_per_s(nb, steps, warmup, cores)
-    sample = f"{nb} clips/step x {steps} steps (+{warmup} warm-up) of the same training step, oracle port of the reference (torch CPU fp32, dropout on)"
+    steps, warmup = max(1, min(args.steps, 30)), max(1, min(args.warmup, 3))     # 8 clips/step at ~7 clips/s: 30 steps stay under a minute
+    v, kind, sample = cpu_arm(nb, steps, warmup, cores)
     line = {"impl": "reference", "metric": "pretrain_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * nb / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             # the same workload name as our arm (the driver matches the two lines); each timed step is a bounded sample of it
-            "config": dict(workload_config(args.gpus, args.batch, args.dtype), reference_step=f"{nb} clips per step, fp32, all {cores} host cores"),
-            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.gpus, args.batch, args.dtype, args.accum_steps),
+            "reference_step": f"{nb} clips per step, fp32, all {cores} host cores, CPU ({kind}); this arm uses no GPU",
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the real bar on the same GPU: the reference algorithm in plain PyTorch eager (cuDNN / cuBLAS / cuFFT)
+# --------------------------------------------------------------------------------------------------------------
+
+def torch_eager_b200(dev, nb, steps=2, warmup=1):
+    """SURVEY.md 2.2 / BASELINE.md section 4 step 6: the oracle's restatement of the reference (plain torch ops + autograd + torch.optim.Adam)
+    on one B200, once in fp32 with TF32 enabled (what run_pretrain.py:33-34 ships) and once under torch.autocast(bfloat16) (the reference's
+    --use-amp route in bf16).  An informational baseline: nothing of sarssl_b200 runs here."""
+    import torch
+    from oracle import sarssl_oracle as O
+    out = {"what": "reference algorithm (oracle restatement) in PyTorch eager on this GPU: STFT + masks + fwd + loss + autograd bwd + torch.optim.Adam, dropout 0.1"}
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for mode in ("fp32_tf32", "autocast_bf16"):
+            b = nb
+            while b >= 8:
+                try:
+                    sd = {k: v.to(dev) for k, v in O.synthetic_state_dict(7).items()}
+                    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+                    for k in names:
+                        sd[k].requires_grad_(True)
+                    opt = torch.optim.Adam([sd[k] for k in names], lr=1e-3)
+                    sig = 0.1 * torch.randn(b, NSAMPLE, 2, device=dev)
+                    random.seed(400000001)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    for i in range(warmup + steps):
+                        if i == warmup:
+                            torch.cuda.synchronize(dev)
+                            e0.record()
+                        x = O.preprocess(sig)
+                        pidx, cidx = O.draw_masks(b, NT, NT // 2, 2)
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "autocast_bf16")):
+                            loss, diff, _ = O.pretrain_forward(x, sd, pidx.to(dev), cidx.to(dev), training=True, dropout_p=0.1)
+                        loss.backward()
+                        opt.step()
+                        opt.zero_grad(set_to_none=True)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                    out[mode] = {"clips_per_s": b * steps / (e0.elapsed_time(e1) * 1e-3), "batch": b, "steps": steps, "loss": float(loss)}
+                    break
+                except torch.OutOfMemoryError:
+                    b //= 2
+                finally:
+                    sd = opt = sig = x = loss = diff = None
+                    torch.cuda.empty_cache()
+            if mode not in out:
+                out[mode] = {"clips_per_s": None, "note": "out of memory at every batch tried"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -158,25 +261,7 @@ def run_ours(args):
     nb = args.batch
     warmup = max(args.warmup, 3)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
+    timed = make_timed(world, dev)       # barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks
 
     # ---------------- model + learner (identical weights on every rank)
     torch.manual_seed(1)
@@ -198,11 +283,17 @@ def run_ours(args):
     opt = FusedAdam(model, lr=1e-3)
     losses = []
 
+    accum = max(args.accum_steps, 1)
+
     def step_resident():
-        x, = learner.data_preprocess(sig)
-        loss, diff, _ = model(x)
-        loss.backward()
-        scale = sync.all_reduce() if sync is not None else 1.0
+        """One optimizer step = `accum` micro-batches (forward + backward each), then one all-reduce + Adam."""
+        for a in range(accum):
+            if sync is not None:
+                sync.defer = a + 1 < accum
+            x, = learner.data_preprocess(sig)
+            loss, diff, _ = model(x)
+            loss.backward()
+        scale = (sync.all_reduce() if sync is not None else 1.0) / accum
         opt.step(1e-3, grad_scale=scale, zero_grad=True)
         losses.append(loss.detach())
 
@@ -217,13 +308,13 @@ def run_ours(args):
     sampler.join(timeout=10)              # an nvidia-smi query still in flight would stall the end-to-end region that follows
     launches = eng.k.launches + opt.k.launches - l0 + args.steps       # + the front-end kernel
     ops.stft_frontend_check(dev)
-    value = nb * world * args.steps / (ms * 1e-3)
+    value = nb * world * accum * args.steps / (ms * 1e-3)
     loss_first, loss_last = float(losses[0]), float(losses[-1])
 
     # ---------------- end to end through the reference-facing API, host buffers
-    e2e_steps = max(args.steps, 10)       # one epoch call; long enough that its fixed costs (fresh Adam, first un-overlapped copy, final read-back) stay small
-    learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1)          # warm-up epoch of the same length (allocator / pinned pools at their steady size)
-    e2e_ms = timed(lambda: learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1), 1)
+    e2e_steps = max(args.steps, 10) * accum       # one epoch call; long enough that its fixed costs (fresh Adam, first un-overlapped copy, final read-back) stay small
+    learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1, accum_steps=accum)          # warm-up epoch of the same length (allocator / pinned pools at their steady size)
+    e2e_ms = timed(lambda: learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1, accum_steps=accum), 1)
     e2e_value = nb * world * e2e_steps / (e2e_ms * 1e-3)
 
     # ---------------- dominant kernel of the step alone: 3x3 conv 64->64 (69 % of the FLOPs), CUDA events on the launching stream
@@ -237,6 +328,7 @@ def run_ours(args):
         conv()
     conv_ms = timed(conv, 5) / 5
     pk = peaks()
+    conv_traffic, conv_traffic_src = measured_traffic("conv3x3_tc_kernel", cb)
     conv_tflops = cb * CONV3_FLOP_PER_CLIP / (conv_ms * 1e-3) / 1e12
     del xin, yout
 
@@ -259,21 +351,29 @@ def run_ours(args):
     fe_gbs = fb * STFT_BYTES_PER_CLIP / (fe_ms * 1e-3) / 1e9
     ls_gbs = fb * LOSS_BYTES_PER_CLIP / (ls_ms * 1e-3) / 1e9
 
+    # ---------------- the other configurations of BASELINE.json, short sub-runs (every rank takes part: weak scaling like the headline)
+    extras = {}
+    if not args.no_other_configs:
+        del fsig, fpred, patches, dpred
+        torch.cuda.empty_cache()
+        extras["longclip"] = bench_pretrain_shape(dev, world, timed, nt=LC_NT, nb=args.longclip_batch, steps=3, dtype=dtype, sync_learner=None,
+                                                  label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step")
+        extras["finetune"] = bench_finetune_core(dev, world, rank, timed, nb=64, steps=10, dtype=dtype)
+
     if rank == 0:
         step_tflops = value * FLOP_PER_CLIP / 1e12 / world
         line = {"metric": "pretrain_clips_per_s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-                "data": "synthetic", "config": workload_config(world, nb, args.dtype), "clocks": sampler.summary(),
-                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * NT + nb * 4),
+                "data": "synthetic", "config": workload_config(world, nb, args.dtype, accum), "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * NT + nb * 4) * accum,
                         "d2h_bytes_per_step": 8},
                 "gpu_launches": int(launches), "tensor_core_gemm_launches": int(eng.k.tc_launches),
                 "loss_first_step": loss_first, "loss_last_step": loss_last,
                 "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / pk["bf16_tflops_sustained"],
                 "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 conv 64->64 implicit GEMM, forward)" if dtype == torch.bfloat16 else "conv3x3_kernel (CUDA cores, fp32)", "achieved": conv_tflops,
                              "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": conv_tflops / pk["bf16_tflops"],
-                             # dram__bytes_read + dram__bytes_write of one launch, ncu --set full (profiles/r01b_conv3x3_tc_kernel.txt, 64 clips):
-                             # 1056.6 MB vs 1073.7 MB algorithmic (read + write one bf16 64-channel map) -> no redundant HBM traffic
-                             "traffic": 1056.6e6 * cb / 64.0, "traffic_source": "ncu --set full (profiles/r01h_conv3x3_tc_kernels.txt), 64-clip launch, scaled by clips per launch",
+                             "traffic": conv_traffic, "traffic_source": conv_traffic_src,
+                             "algorithmic_bytes_per_launch": cb * 2 * NT * NF * 64 * 2,        # read + write one bf16 64-channel map
                              "peak_source": pk["source"], "kernel_ms": conv_ms, "algorithmic_flops_per_launch": cb * CONV3_FLOP_PER_CLIP,
                              "clips_per_launch": cb},
                 "frontend": {"workload": f"stft_frontend + masked_recon_loss fwd+bwd, batch {fb} (BASELINE.json configs[1])",
@@ -282,21 +382,103 @@ def run_ours(args):
                                       "frac": fe_gbs / pk["hbm_gbs"], "kernel_ms": fe_ms, "algorithmic_bytes_per_launch": fb * STFT_BYTES_PER_CLIP},
                              "loss": {"bound": "hbm", "kernel": "masked_loss_kernel", "achieved": ls_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                       "frac": ls_gbs / pk["hbm_gbs"], "kernel_ms": ls_ms, "algorithmic_bytes_per_launch": fb * LOSS_BYTES_PER_CLIP}}}
+        line["other_configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cpu_v = cpu_pretrain_clips_per_s(8, 2, 1, cores)
-            line["cpu_baseline"] = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
-                                    "sample": "8 clips/step x 2 steps (+1 warm-up) of the same training step, oracle port (torch CPU fp32, dropout on)"}
+            cpu_v, kind, sample = cpu_arm(8, 2, 1, cores)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample}
+        if world == 1 and not args.no_torch_eager:
+            del model, learner, opt, sig
+            torch.cuda.empty_cache()
+            line["torch_eager_b200"] = torch_eager_b200(dev, nb)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------------------------
-# downstream fine-tuning step (BASELINE.json configs[3]): --workload finetune
+# the other configurations of BASELINE.json: long clips (configs[4]) and the downstream fine-tuning step (configs[3])
 # --------------------------------------------------------------------------------------------------------------
+LC_NT = 1024                                # 16.4 s clips: 262,400 samples -> 1024 frames
+LC_FLOP_PER_CLIP = 361.5e9                  # fwd+bwd at nt = 1024
 FT_NT = 64                                  # TDOA fine-tuning uses 1.04 s clips -> 64 frames (run_downstream.py:71-84)
 FT_NSAMPLE = (FT_NT + 1) * 256
+
+
+def make_timed(world, dev):
+    import torch
+    import torch.distributed as dist
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+    return timed
+
+
+def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, label):
+    """A pre-training step at another clip length (same path as the headline: front-end, masks, fwd, loss, bwd, all-reduce, Adam)."""
+    import torch
+    from sarssl_b200 import ops
+    from sarssl_b200.learner import STFTLearner
+    from sarssl_b200.model import SARSSL
+    from sarssl_b200.optim import FusedAdam
+    rank = int(os.environ.get("RANK", "0"))
+    torch.manual_seed(1)
+    model = SARSSL(sig_shape=(NF, nt, 2, 2), device=dev)
+    model.to(dev)
+    model.set_compute_dtype(dtype)
+    model.set_dropout(0.1)
+    model.rng_state = ops.mt_seed(400000101 + rank)
+    model.train()
+    L = STFTLearner(model, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    L.device = dev
+    if world > 1:
+        L.mul_gpu()
+    sync = getattr(L, "grad_sync", None)
+    sig = 0.1 * torch.randn(nb, (nt + 1) * 256, 2, device=dev)
+    host_sig = sig.cpu().pin_memory()
+    opt = FusedAdam(model, lr=1e-3)
+
+    def step():
+        x, = L.data_preprocess(sig)
+        loss, _, _ = model(x)
+        loss.backward()
+        opt.step(1e-3, grad_scale=sync.all_reduce() if sync is not None else 1.0, zero_grad=True)
+
+    for _ in range(3):
+        step()
+    l0 = model.engine.k.launches + opt.k.launches
+    ms = timed(step, steps)
+    launches = model.engine.k.launches + opt.k.launches - l0 + steps
+    e2e_steps = max(steps, 4)
+    L.pretrain_epoch([[host_sig]] * 2, lr=1e-3, epoch=1)
+    e2e_ms = timed(lambda: L.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1), 1)
+    v = nb * world * steps / (ms * 1e-3)
+    pk = peaks()
+    flop = LC_FLOP_PER_CLIP * (nt / LC_NT) if nt != NT else FLOP_PER_CLIP
+    return {"workload": f"{label}, {nb} clips/GPU", "metric": "pretrain_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": ms / steps, "per_gpu_batch": nb, "nt": nt, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
+            "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * nt + nb * 4),
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": v / world * flop / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": v / world * flop / 1e12 / pk["bf16_tflops_sustained"], "what": "whole step: algorithmic fwd+bwd FLOPs per clip x clips/s per GPU "
+                         "against the sustained bf16 peak", "flop_per_clip": flop, "peak_source": pk["source"]}}
 
 
 def cpu_finetune_clips_per_s(nb, steps, warmup, threads):
@@ -327,27 +509,12 @@ def cpu_finetune_clips_per_s(nb, steps, warmup, threads):
     return nb * len(times) / sum(times)
 
 
-def run_finetune(args):
+def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype):
+    """configs[3]: downstream fine-tuning step (TDOA head, MSE, Adam) on 1.04 s clips."""
     import torch
-    import torch.distributed as dist
     from sarssl_b200.learner import STFTLearner
     from sarssl_b200.model import SARSSL
     from sarssl_b200.optim import FusedAdam
-    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        if rank == 0:
-            cores = os.cpu_count() or 1
-            v = cpu_finetune_clips_per_s(8, max(1, min(args.steps, 4)), 1, cores)
-            print(json.dumps({"impl": "reference", "metric": "finetune_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "higher_is_better": True,
-                              "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": "8 clips/step, oracle port, torch CPU fp32"},
-                              "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    nb = args.batch if args.batch != 256 else 64                      # configs[3]: batch 512 over 8 GPUs
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     model = SARSSL(sig_shape=(NF, FT_NT, 2, 2), pretrain=False, device=dev)
     model.to(dev)
     model.set_compute_dtype(dtype)
@@ -369,48 +536,54 @@ def run_finetune(args):
         L.loss(pred_batch=pred, gt_batch=tar).backward()
         opt.step(1e-5, grad_scale=sync.all_reduce() if sync is not None else 1.0)
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    for _ in range(max(3, args.warmup)):
+    for _ in range(3):
         step()
     l0 = model.engine.k.launches + opt.k.launches
-    ms = timed(step, args.steps)
-    launches = model.engine.k.launches + opt.k.launches - l0 + args.steps      # + the front-end kernel
+    ms = timed(step, steps)
+    launches = model.engine.k.launches + opt.k.launches - l0 + steps      # + the front-end kernel
     # end to end through the reference-facing call with host buffers; an epoch re-creates Adam (like the reference), so it is warmed up once
     # and timed over enough steps that this per-epoch cost does not dominate a 7 ms step
-    e2e_steps = max(args.steps, 20)
+    e2e_steps = max(steps, 20)
     L.train_epoch([(host_sig, {"TDOA": host_lab})] * 2, lr=1e-5)
     e2e_ms = timed(lambda: L.train_epoch([(host_sig, {"TDOA": host_lab})] * e2e_steps, lr=1e-5), 1)
-    if rank == 0:
-        line = {"metric": "finetune_clips_per_s", "value": nb * world * args.steps / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": f"downstream fine-tune step (TDOA head, MSE, Adam), 2-mic, {FT_NSAMPLE} samples (1.04 s), batch {nb}/GPU (BASELINE.json configs[3])",
-                           "per_gpu_batch": nb, "nt": FT_NT, "parallelism": f"dp{world}"},
-                "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
-                        "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches)}
+    return {"workload": f"configs[3]: downstream fine-tune step (TDOA head, MSE, Adam), 2-mic, {FT_NSAMPLE} samples (1.04 s), batch {nb}/GPU",
+            "metric": "finetune_clips_per_s", "value": nb * world * steps / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": ms / steps, "per_gpu_batch": nb, "nt": FT_NT, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
+            "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches)}
+
+
+def run_sub_workload(args):
+    """--workload finetune | longclip as a stand-alone JSON line."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cores = os.cpu_count() or 1
+            v = cpu_finetune_clips_per_s(8, max(1, min(args.steps, 4)), 1, cores) if args.workload == "finetune" else None
+            print(json.dumps({"impl": "reference", "metric": args.workload + "_clips_per_s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "higher_is_better": True,
+                              "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": "8 clips/step, oracle port, torch CPU fp32"},
+                              "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    timed = make_timed(world, dev)
+    if args.workload == "finetune":
+        line = bench_finetune_core(dev, world, rank, timed, nb=args.batch if args.batch != 256 else 64, steps=args.steps, dtype=dtype)   # configs[3]: batch 512 over 8 GPUs
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = {"value": cpu_finetune_clips_per_s(8, 2, 1, cores), "unit": "clips/s", "cores": cores, "kind": "port",
                                     "sample": "8 clips/step x 2 steps, oracle port (torch CPU fp32, dropout on)"}
+    else:
+        line = bench_pretrain_shape(dev, world, timed, nt=LC_NT, nb=args.longclip_batch, steps=args.steps, dtype=dtype, sync_learner=None,
+                                    label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step")
+    line.update({"warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": line["workload"], "parallelism": f"dp{world}"}})
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -423,13 +596,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step (micro-batch)")
+    ap.add_argument("--accum-steps", type=int, default=1, help="micro-batches per optimizer step (configs[2]: global batch 2048 = 256 x accum x GPUs)")
     ap.add_argument("--frontend-batch", type=int, default=1024)
+    ap.add_argument("--longclip-batch", type=int, default=32, help="clips per GPU of the long-clip sub-run (configs[4]: 256 over 8 GPUs)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"], help="pretrain = headline (configs[2]); finetune = configs[3]")
+    ap.add_argument("--no-torch-eager", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune", "longclip"],
+                    help="pretrain = headline (configs[2]); finetune = configs[3]; longclip = configs[4]")
     args = ap.parse_args()
-    if args.workload == "finetune":
-        run_finetune(args)
+    if args.workload != "pretrain":
+        run_sub_workload(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:
