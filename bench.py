@@ -317,6 +317,11 @@ def run_ours(args):
     e2e_ms = timed(lambda: learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1, accum_steps=accum), 1)
     e2e_value = nb * world * e2e_steps / (e2e_ms * 1e-3)
 
+    # ---------------- the input pipeline in front of the path, from REAL WAV files: loader alone, then through pretrain_epoch
+    pipeline = None
+    if world == 1 and not args.no_input_pipeline:
+        pipeline = bench_input_pipeline(learner, nb, timed)
+
     # ---------------- dominant kernel of the step alone: 3x3 conv 64->64 (69 % of the FLOPs), CUDA events on the launching stream
     k = KernelSet(dev, dtype)
     cb = min(nb, 64)
@@ -383,6 +388,8 @@ def run_ours(args):
                              "loss": {"bound": "hbm", "kernel": "masked_loss_kernel", "achieved": ls_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                       "frac": ls_gbs / pk["hbm_gbs"], "kernel_ms": ls_ms, "algorithmic_bytes_per_launch": fb * LOSS_BYTES_PER_CLIP}}}
         line["other_configs"] = extras
+        if pipeline is not None:
+            line["input_pipeline"] = pipeline
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cpu_v, kind, sample = cpu_arm(8, 2, 1, cores)
@@ -394,6 +401,58 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# input pipeline from real WAV files (FixMicSigDataset + DataLoader of run_pretrain.py:175-199)
+# --------------------------------------------------------------------------------------------------------------
+
+def write_synthetic_wavs(root, nfiles, nsample, nch=2, fs=16000, seed=0):
+    """16-bit PCM RIFF/WAVE files of seeded noise (the format the reference's simulated data set is saved in)."""
+    import struct
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    os.makedirs(root, exist_ok=True)
+    base = np.round(rng.standard_normal((nsample + nfiles, nch)) * 3000).astype("<i2")
+    hdr = struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + nsample * nch * 2, b"WAVE", b"fmt ", 16, 1, nch, fs, fs * nch * 2, nch * 2, 16, b"data", nsample * nch * 2)
+    for i in range(nfiles):
+        with open(os.path.join(root, f"clip{i:05d}.wav"), "wb") as f:
+            f.write(hdr)
+            f.write(base[i:i + nsample].tobytes())          # every file a different window of the same noise: cheap to generate, all distinct
+
+
+def bench_input_pipeline(learner, nb, timed, nfiles=1024, workers=None):
+    import shutil
+    import tempfile
+    from sarssl_b200.data import FixMicSigDataset, WaveformBatchLoader
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    root = tempfile.mkdtemp(prefix="sarssl_wavs_", dir=shm)
+    try:
+        write_synthetic_wavs(root, nfiles, NSAMPLE)
+        workers = workers or min(os.cpu_count() or 8, 32)
+        ds = FixMicSigDataset(data_dir=root, fs=16000, load_anno=False, dataset_sz=None)
+        loader = WaveformBatchLoader(ds, batch_size=nb, shuffle=True, num_workers=workers, pin_memory=True, drop_last=True, prefetch=3)
+        for _ in loader:                                    # warm-up epoch: page cache, pinned-memory pool
+            pass
+        epochs = 3
+        t0 = time.perf_counter()
+        n = 0
+        for e in range(epochs):
+            loader.set_epoch(e + 1)
+            for (b,) in loader:
+                n += b.shape[0]
+        dt = time.perf_counter() - t0
+        loader.set_epoch(9)
+        learner.pretrain_epoch(loader, lr=1e-3, epoch=1)   # warm-up epoch through the training call
+        steps = len(loader)
+        ms = timed(lambda: learner.pretrain_epoch(loader, lr=1e-3, epoch=1), 1)
+        return {"what": f"{nfiles} real 16-bit PCM WAV files (2 ch x {NSAMPLE} samples) on {'tmpfs' if shm else 'local disk'} -> FixMicSigDataset -> WaveformBatchLoader "
+                        f"(native batch decoder, {workers} threads, pinned batches of {nb}) [-> H2D on a side stream -> STFTLearner.pretrain_epoch]",
+                "loader_clips_per_s": n / dt, "loader_f32_gb_per_s": n * NSAMPLE * 2 * 4 / dt / 1e9, "loader_pcm16_gb_per_s": n * NSAMPLE * 2 * 2 / dt / 1e9,
+                "decoder_threads": workers, "host_cores": os.cpu_count(),
+                "train_from_wav_clips_per_s": nb * steps / (ms * 1e-3), "train_from_wav_steps": steps}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -603,6 +662,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-eager", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-input-pipeline", action="store_true")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune", "longclip"],
                     help="pretrain = headline (configs[2]); finetune = configs[3]; longclip = configs[4]")
     args = ap.parse_args()

@@ -255,12 +255,19 @@ int sarssl_fill_f32(float* p, float value, long long n, cudaStream_t stream);
 int sarssl_wav_info(const char* path, int* fs, int* nch, long long* nsample);
 /* frames [first, first + count) -> out_host[count][nch]; frames past the end are zero-filled, *nread = real frames */
 int sarssl_wav_read_f32(const char* path, long long first, long long count, float* out_host, long long* nread);
+/* A whole batch in one call (the DataLoader workers + default_collate of run_pretrain.py:191-199): file i -> out_host[i][count][nch], decoded by
+ * `nthreads` host threads.  Every file must have nch channels at fs Hz (fs <= 0: any) and, with exact != 0, exactly first + count frames (else frames
+ * past the end are zero-filled).  On error *bad_index (nullable) is the first failing file. */
+int sarssl_wav_read_batch_f32(const char* const* paths, int nfiles, long long first, long long count, int nch, int fs, int exact, float* out_host,
+                              int nthreads, int* bad_index);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A6  CNN patch-embedding stem on channel-last images [B][H = frame][W = bin][C]      model.py:50-64,203-208
  * ---------------------------------------------------------------------------------------------------------- */
 /* 1x1 conv 4 -> 64.  mode 0: `in` is [P][4] of `dtype`; mode 1 / 2: `in` is the fp32 patch tensor and the spectral /
- * spatial input masking of model.py:541 / :563 is applied on load (frame_flag (B,H) uint8, ch_idx (B) int32). */
+ * spatial input masking of model.py:541 / :563 is applied on load (frame_flag (B,H) uint8, ch_idx (B) int32); mode 3: fp32 patches,
+ * un-masked (downstream branch, model.py:676-678); mode 4: spectral input of the frozen-encoder branch (model.py:622: masked frames keep
+ * their un-masked microphone, the other frames are zero). */
 int sarssl_stem_expand(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, void* out,
                        long long P, int W, int H, int dtype, cudaStream_t stream);
 /* conv 4 -> 64 + BatchNorm + ReLU in one pass: out = relu(scale * conv(in) + shift).  The batch statistics of the conv output are
@@ -311,9 +318,11 @@ int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packe
 /* ------------------------------------------------------------------------------------------------------------
  * A14  optimizer: torch.optim.Adam(betas (0.9, 0.999), eps 1e-8, wd 0) over flat fp32 arenas      learner.py:83,111-113
  * ---------------------------------------------------------------------------------------------------------- */
-/* g is multiplied by grad_scale first; param_bf16 (nullable) receives the refreshed bf16 copy; zero_grad != 0 clears g. */
-int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n, int step, float lr,
-                     float beta1, float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t stream);
+/* g is multiplied by grad_scale first; param_bf16 (nullable) receives the refreshed bf16 copy; zero_grad != 0 clears g.
+ * Hyper-parameters are doubles: 1 - beta, the bias corrections and lr / (1 - beta1^step) are formed in double on the host and rounded
+ * to fp32 once, exactly as torch.optim.Adam does with its Python floats. */
+int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n, int step, double lr,
+                     double beta1, double beta2, double eps, float grad_scale, int zero_grad, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A15  data-parallel gradient exchange (replaces nn.DataParallel, learner.py:25-31): NCCL sum all-reduce of contiguous buckets

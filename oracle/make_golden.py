@@ -144,6 +144,41 @@ def run_downstream_case(name, nb, nt, embed, sig_seed, sd_seed):
     print(name, "loss", out["loss"], "pred", out["pred"].ravel()[:3])
 
 
+def run_frozen_case(name, nb, nt, sig_seed, sd_seed, mask_seed):
+    """reference SARSSL(pretrain=False, pretrain_frozen_encoder=True) with the encoders' requires_grad cleared as
+    run_pretrain.py:364-371 does ('encoder' in key); one forward + backward."""
+    rm, rl, rops, ru = ref_shim.load_reference()
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=sig_seed)
+    net = rm.SARSSL(sig_shape=(256, nt, 2, 2), pretrain=False, device="cpu", pretrain_frozen_encoder=True)
+    net.load_state_dict(O.synthetic_state_dict(sd_seed, pretrain=False, frozen=True))
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    for k, p in net.named_parameters():
+        if "encoder" in k:
+            p.requires_grad = False
+    L = rl.STFTLearner(net, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
+    L.cpu()
+    net.train()
+    x, = L.data_preprocess(sig)
+    random.seed(mask_seed)
+    loss, zero, vis = net(x)
+    loss.backward()
+    out = {"nb": nb, "nt": nt, "sig_seed": sig_seed, "sd_seed": sd_seed, "mask_seed": mask_seed, "loss": float(loss), "zero": float(zero),
+           "pred": vis["pred"].numpy(), "keys": np.array(list(net.state_dict().keys()))}
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.reshape(-1)
+        out["grad_rand/" + k] = g.numpy()[O.fixture_sample_idx(k, g.numel(), 512)].astype(np.float32)
+        out["grad_norm/" + k] = float(g.norm())
+    for k, v in net.state_dict().items():
+        if "running_" in k:
+            out["bn/" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "grads for", sorted(k[10:] for k in out if k.startswith("grad_norm/")))
+
+
 def mask_streams():
     """Known-answer vectors for the mask RNG: python `random` (CPython MT19937) under the reference's seeds."""
     out = {}
@@ -176,3 +211,4 @@ if __name__ == "__main__":
     run_case("full_nt256_b8", nb=8, nt=256, sig_seed=16, sd_seed=7, mask_seed=400000003, keep_full=False, grad_samples=2048)
     run_downstream_case("downstream_nt16_b4", nb=4, nt=16, embed="spec_spat", sig_seed=8, sd_seed=9)
     run_downstream_case("downstream_spat_nt64_b2", nb=2, nt=64, embed="spat", sig_seed=10, sd_seed=9)
+    run_frozen_case("frozen_nt16_b3", nb=3, nt=16, sig_seed=12, sd_seed=13, mask_seed=21)

@@ -284,6 +284,28 @@ def pretrain_forward(x, sd, pidx, cidx, training=True, dropout_p=0.0, taps=None)
     return loss, diff, vis
 
 
+def frozen_encoder_forward(x, sd, pidx, cidx, training=True, dropout_p=0.0):
+    """model.py:603-666 (pretrain=False, pretrain_frozen_encoder=True): the spectral encoder only sees the un-masked channel of the
+    masked frames (model.py:622), the spatial encoder the un-masked frames; `spec_spat_decoder` predicts the patches and
+    gen_loss_spec(tar_maskch=True) (model.py:749-774) is the masked-channel MSE of gen_loss.  Returns (loss, loss * 0, vis)."""
+    nb, nmic, nf, nt, _ = x.shape
+    bn = BNState(training)
+    drop = (lambda t: F.dropout(t, dropout_p, True)) if (training and dropout_p > 0) else (lambda t: t)
+    vec = x.permute(0, 3, 2, 4, 1)
+    mask, mask_p, mask_c = dense_masks(pidx, cidx, nt, nf, nmic)
+    mp, mc = mask_p[:, :, :, None, :], mask_c[:, :, :, None, :]
+    spec_in = vec * (1 - mp) * mc                                 # model.py:622
+    spat_in = vec * mp                                            # model.py:628
+    e_spec = embed_encoder(spec_in.reshape(nb, nt, -1), sd, "spec_encoder", SPEC_LAYERS, NHEAD, bn, drop)
+    e_spat = embed_encoder(spat_in.reshape(nb, nt, -1), sd, "spat_encoder", SPAT_LAYERS, NHEAD, bn, drop)
+    e = torch.cat([e_spec, e_spat], dim=2)
+    pred = _lin(F.relu(_lin(e, sd, "spec_spat_decoder.proj.0")), sd, "spec_spat_decoder.proj.2").view(nb, nt, nf, 2, nmic)   # model.py:653-654
+    loss, _ = masked_loss(pred, vec, pidx, cidx)                  # gen_loss_spec, tar_maskch=True
+    vis = {"mask": mask.permute(0, 2, 1, 3).contiguous(), "pred": pred.detach().permute(0, 2, 1, 3, 4).contiguous(),
+           "tar": vec.detach().permute(0, 2, 1, 3, 4).contiguous()}
+    return loss, loss * 0.0, vis
+
+
 def downstream_forward(x, sd, embed_use="spec_spat", training=True, dropout_p=0.0):
     """model.py:667-719 (pretrain=False, head 'mlp', dlabel 1, token 'all'): both encoders on the un-masked input, concatenation (or
     one of them), mean over time, LayerNorm + Linear.  x (nb, 2, nf, nt, 2) -> (pred (nb, 1), pooled embedding (nb, dembed))."""
@@ -327,8 +349,10 @@ def positional_table(d_model, max_len=10000):
     return pe.unsqueeze(0)
 
 
-def state_dict_spec(nf=256, pretrain=True, dembed_ds=768):
+def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False):
     """[(key, shape, kind)] for the 214 state_dict entries of SARSSL(pretrain=True).
+    frozen=True: SARSSL(pretrain=False, pretrain_frozen_encoder=True) - three decoders instead of one (model.py:470-481; the spatial
+    decoder is built with the SPECTRAL width, as the reference does).
     kind: 'w' weight matrix / filter, 'b' bias, 'g' norm gain, 'rm' running mean, 'rv' running var,
     'n' num_batches_tracked, 'pe' positional table, 'uv' u/v bias."""
     out = []
@@ -374,21 +398,28 @@ def state_dict_spec(nf=256, pretrain=True, dembed_ds=768):
         stem(enc + ".patch_embed", D)
         for l in range(nl):
             block(f"{enc}.embed.layers.{l}", D, NHEAD)
+    def decoder(name, din):
+        out.extend([(name + ".proj.0.weight", (3 * 4 * nf, din), "w"), (name + ".proj.0.bias", (3 * 4 * nf,), "b"),
+                    (name + ".proj.2.weight", (4 * nf, 3 * 4 * nf), "w"), (name + ".proj.2.bias", (4 * nf,), "b")])
+
     if pretrain:
-        out.extend([("decoder.proj.0.weight", (3 * 4 * nf, 768), "w"), ("decoder.proj.0.bias", (3 * 4 * nf,), "b"),
-                    ("decoder.proj.2.weight", (4 * nf, 3 * 4 * nf), "w"), ("decoder.proj.2.bias", (4 * nf,), "b")])
+        decoder("decoder", 768)
+    elif frozen:
+        decoder("spec_spat_decoder", 768)
+        decoder("spec_decoder", 512)
+        decoder("spat_decoder", 512)
     else:       # downstream head (model.py:495-500)
         out.extend([("mlp_head.0.weight", (dembed_ds,), "g"), ("mlp_head.0.bias", (dembed_ds,), "b"),
                     ("mlp_head.1.weight", (1, dembed_ds), "w"), ("mlp_head.1.bias", (1,), "b")])
     return out
 
 
-def synthetic_state_dict(seed=7, nf=256, pretrain=True, dembed_ds=768):
+def synthetic_state_dict(seed=7, nf=256, pretrain=True, dembed_ds=768, frozen=False):
     """Seeded, non-degenerate weights (non-zero biases, non-unit gains) for parity tests.  Generated
     key by key from one torch.Generator so reference, oracle and CUDA path can all be loaded with it."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for key, shape, kind in state_dict_spec(nf, pretrain, dembed_ds):
+    for key, shape, kind in state_dict_spec(nf, pretrain, dembed_ds, frozen):
         if kind == "w":
             fan_in = 1
             for s in shape[1:]:

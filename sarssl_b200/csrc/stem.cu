@@ -37,6 +37,7 @@ __device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, un
 //   spectral: masked frame -> keep only the un-masked microphone; other frames -> keep only the masked microphone
 //   spatial : masked frame -> zeros; other frames -> both microphones
 // mode 3: fp32 patches, no masking (downstream fine-tuning branch)
+// mode 4: spectral input of the frozen-encoder branch (model.py:622): masked frame -> only the un-masked microphone; other frames -> zeros
 template <typename T>
 __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
     if (mode == 0) {
@@ -55,20 +56,21 @@ __device__ __forceinline__ float4 load_narrow(const void* in, long long p, int m
     const unsigned row = ((uw & (uw - 1)) == 0) ? (up >> (31 - __clz((int)uw))) : up / uw;
     const bool pm = flag[row] != 0;
     const int mc = ch[row / (unsigned)H];
-    if (mode == 1) {
+    if (mode == 1 || (mode == 4 && pm)) {
         const int keep = pm ? 1 - mc : mc;
         if (keep == 0) { x.y = 0.f; x.w = 0.f; } else { x.x = 0.f; x.z = 0.f; }
-    } else if (pm) x = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (mode == 4 || pm) x = make_float4(0.f, 0.f, 0.f, 0.f);
     return x;
 }
 
 // The mask of modes 1 / 2 depends only on the pixel's image row (frame): bit c set = channel c is zeroed.
 __device__ __forceinline__ unsigned narrow_zero_bits(long long p, int mode, const uint8_t* flag, const int32_t* ch, int W, int H) {
-    if (mode != 1 && mode != 2) return 0u;
+    if (mode != 1 && mode != 2 && mode != 4) return 0u;
     const unsigned up = (unsigned)p, uw = (unsigned)W;
     const unsigned row = ((uw & (uw - 1)) == 0) ? (up >> (31 - __clz((int)uw))) : up / uw;
     const bool pm = flag[row] != 0;
     if (mode == 2) return pm ? 0xFu : 0u;
+    if (mode == 4 && !pm) return 0xFu;
     const int mc = ch[row / (unsigned)H];
     const int keep = pm ? 1 - mc : mc;
     return keep == 0 ? 0xAu : 0x5u;                            // keep microphone 0: zero (re1, im1) = channels 1, 3
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256, 3) pw_expand_kernel(const void* __restric
         float4 x[4];
         if ((W & 3) == 0) {                // the 4 consecutive pixels share an image row: one mask lookup (p0 % 4 == 0)
             const unsigned zb = narrow_zero_bits(p0, mode, flag, ch, W, H);
-            const int lm = (mode == 1 || mode == 2) ? 3 : mode;
+            const int lm = (mode == 1 || mode == 2 || mode == 4) ? 3 : mode;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 x[u] = (p0 + u < P) ? apply_zero_bits(load_narrow<T>(in, p0 + u, lm, nullptr, nullptr, W, H), zb) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -774,7 +776,7 @@ using namespace sarssl;
 static int stem_expand_impl(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, const float* scale,
                             const float* shift, void* out, long long P, int W, int H, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight64x4 && out && P > 0 && P < 0xFFFFFFFFLL, "stem_expand: bad arguments (P must be in (0, 2^32))");
-    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_expand: mode %d needs masks", mode);
+    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2 || mode == 4)), "stem_expand: mode %d needs masks", mode);
     if (dtype == SARSSL_F32) pw_expand_kernel<float><<<pix_grid(pw_expand_kernel<float>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, scale, shift, (float*)out, P, W, H);
     else if (dtype == SARSSL_BF16) pw_expand_kernel<__nv_bfloat16><<<pix_grid(pw_expand_kernel<__nv_bfloat16>, P), 256, 0, stream>>>(in, mode, frame_flag, ch_idx, weight64x4, scale, shift, (__nv_bfloat16*)out, P, W, H);
     else { set_last_error("stem_expand: bad dtype"); return SARSSL_ERR_ARG; }
@@ -798,7 +800,7 @@ extern "C" int sarssl_stem_expand_bn_relu(const void* in, int mode, const uint8_
 extern "C" int sarssl_stem_input_stats(const void* in, int mode, const uint8_t* frame_flag, const int32_t* ch_idx, const float* weight64x4, float* sums2x64,
                                        long long P, int W, int H, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight64x4 && sums2x64 && workspace && P > 0 && P < 0xFFFFFFFFLL, "stem_input_stats: bad arguments (P must be in (0, 2^32))");
-    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2)), "stem_input_stats: mode %d needs masks", mode);
+    SARSSL_CHECK_ARG(mode == 0 || mode == 3 || (frame_flag && ch_idx && (mode == 1 || mode == 2 || mode == 4)), "stem_input_stats: mode %d needs masks", mode);
     SARSSL_CHECK_ARG(dtype == SARSSL_F32 || dtype == SARSSL_BF16, "stem_input_stats: bad dtype");
     long long g = (P + 255) / 256;
     const long long cap = dtype == SARSSL_F32 ? resident_ctas(narrow_moments_kernel<float>, 256) : resident_ctas(narrow_moments_kernel<__nv_bfloat16>, 256);

@@ -6,6 +6,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sarssl_b200.h"
@@ -74,13 +77,19 @@ extern "C" int sarssl_wav_info(const char* path, int* fs, int* nch, long long* n
 
 // Decodes frames [first, first + count) of all channels into out[count][nch] (float32).  Frames past the end of the file are
 // zero-filled; *nread receives the number of real frames.
-extern "C" int sarssl_wav_read_f32(const char* path, long long first, long long count, float* out, long long* nread) {
-    SARSSL_CHECK_ARG(path && out && first >= 0 && count >= 0, "wav_read_f32: bad arguments");
+// expect_nch / expect_fs > 0 and exact != 0 turn a channel-count, sample-rate or length mismatch into an error (the batch reader's checks)
+static int wav_read_impl(const char* path, long long first, long long count, float* out, long long* nread, int expect_nch, int expect_fs, int exact) {
     FILE* f = fopen(path, "rb");
     if (!f) { sarssl::set_last_error("wav: cannot open %s", path); return SARSSL_ERR_ARG; }
     WavHeader h;
     int rc = parse_header(f, path, h);
     if (rc) { fclose(f); return rc; }
+    if ((expect_nch > 0 && h.nch != expect_nch) || (expect_fs > 0 && h.fs != expect_fs) || (exact && h.data_bytes / h.block_align != first + count)) {
+        fclose(f);
+        sarssl::set_last_error("wav: %s has %d channels at %d Hz, %lld frames; the batch expects %d channels at %d Hz%s", path, h.nch, h.fs,
+                               (long long)(h.data_bytes / h.block_align), expect_nch, expect_fs, exact ? " and an exact length" : "");
+        return SARSSL_ERR_ARG;
+    }
     const long long total = h.data_bytes / h.block_align;
     long long n = total - first;
     if (n < 0) n = 0;
@@ -98,7 +107,10 @@ extern "C" int sarssl_wav_read_f32(const char* path, long long first, long long 
     const unsigned char* p = buf.data();
     if (h.format == 3 && h.bits == 32) memcpy(out, p, (size_t)nv * 4);
     else if (h.format == 3) { for (long long i = 0; i < nv; ++i) { double d; memcpy(&d, p + 8 * i, 8); out[i] = (float)d; } }
-    else if (h.bits == 16) { for (long long i = 0; i < nv; ++i) out[i] = (float)(int16_t)rd16(p + 2 * i) * (1.0f / 32768.0f); }
+    else if (h.bits == 16) {                                     // the common case: little-endian host, a loop the compiler vectorises
+        const int16_t* q = reinterpret_cast<const int16_t*>(p);  // (std::vector storage is suitably aligned)
+        for (long long i = 0; i < nv; ++i) out[i] = (float)q[i] * (1.0f / 32768.0f);
+    }
     else if (h.bits == 24) {
         for (long long i = 0; i < nv; ++i) {
             const int32_t v = (int32_t)((uint32_t)p[3 * i] << 8 | (uint32_t)p[3 * i + 1] << 16 | (uint32_t)p[3 * i + 2] << 24) >> 8;
@@ -108,5 +120,41 @@ extern "C" int sarssl_wav_read_f32(const char* path, long long first, long long 
     else { for (long long i = 0; i < nv; ++i) out[i] = (float)((int)p[i] - 128) * (1.0f / 128.0f); }
     for (long long i = nv; i < count * h.nch; ++i) out[i] = 0.f;
     if (nread) *nread = n;
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_wav_read_f32(const char* path, long long first, long long count, float* out, long long* nread) {
+    SARSSL_CHECK_ARG(path && out && first >= 0 && count >= 0, "wav_read_f32: bad arguments");
+    return wav_read_impl(path, first, count, out, nread, 0, 0, 0);
+}
+
+// One call decodes a whole batch: file i -> out[i][count][nch], `nthreads` host threads pulling files from a shared counter (no Python,
+// no GIL per clip).  Every file must have `nch` channels at `fs` Hz (fs <= 0: not checked) and, with exact != 0, exactly first + count frames;
+// otherwise frames past the end are zero-filled.  On failure the first failing file's message is in sarssl_last_error() and *bad_index names it.
+extern "C" int sarssl_wav_read_batch_f32(const char* const* paths, int nfiles, long long first, long long count, int nch, int fs, int exact,
+                                         float* out, int nthreads, int* bad_index) {
+    SARSSL_CHECK_ARG(paths && out && nfiles > 0 && first >= 0 && count >= 0 && nch > 0, "wav_read_batch_f32: bad arguments");
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > nfiles) nthreads = nfiles;
+    std::atomic<int> next(0), bad(-1), bad_rc(SARSSL_OK);
+    std::string bad_msg;
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= nfiles || bad.load() >= 0) return;
+            const int rc = wav_read_impl(paths[i], first, count, out + (size_t)i * (size_t)count * nch, nullptr, nch, fs, exact);
+            if (rc != SARSSL_OK) {
+                int none = -1;
+                if (bad.compare_exchange_strong(none, i)) { bad_rc = rc; bad_msg = sarssl_last_error(); }     // (the message is thread-local)
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (bad_index) *bad_index = bad.load();
+    if (bad.load() >= 0) { sarssl::set_last_error("%s", bad_msg.c_str()); return bad_rc.load(); }
     return SARSSL_OK;
 }

@@ -53,6 +53,18 @@ def wav_read(path, first=0, count=None, out=None):
     return out, fs
 
 
+def wav_read_batch(paths, count, nch, out, fs=0, first=0, exact=False, nthreads=8):
+    """Decode `paths[i]` frames [first, first+count) into out[i] (float32 (len(paths), count, nch), e.g. a pinned batch) with `nthreads`
+    native threads in ONE library call (no per-clip Python)."""
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (len(paths), count, nch):
+        raise SarsslError("wav_read_batch: `out` must be a contiguous float32 tensor (len(paths), count, nch)")
+    arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    bad = C.c_int(-1)
+    check(lib().sarssl_wav_read_batch_f32(C.cast(arr, C.c_void_p), len(paths), first, count, nch, int(fs), int(exact), C.c_void_p(out.data_ptr()),
+                                          int(nthreads), C.byref(bad)), "sarssl_wav_read_batch_f32")
+    return out
+
+
 class FixMicSigDataset:
     """dataset.py:107-178: presaved microphone signals (`*.wav`, direct-path copies `*_dp.wav`, annotations `*_info.npz`)."""
 
@@ -141,9 +153,12 @@ class WaveformBatchLoader:
         fs0, nch, ns0 = wav_info(ds.files[ids[0]])
         ns = self.nsample if self.nsample is not None else ns0
         plain = ds.transforms is None and not ds.load_dp
-        batch = torch.empty((len(ids), ns, nch), dtype=torch.float32)
-        if self.pin and torch.cuda.is_available():
-            batch = batch.pin_memory()
+        # pinned straight from torch's caching host allocator: after the first few batches no cudaHostAlloc and no staging copy happen
+        batch = torch.empty((len(ids), ns, nch), dtype=torch.float32, pin_memory=bool(self.pin and torch.cuda.is_available()))
+        if plain and not ds.load_anno:
+            # the pre-training case (run_pretrain.py:191-199): the whole batch in one native call, `workers` decoder threads, no per-clip Python
+            wav_read_batch([ds.files[i] for i in ids], ns, nch, batch, fs=ds.fs, exact=self.nsample is None, nthreads=self.workers)
+            return [batch]
 
         def one(j):
             path = ds.files[ids[j]]

@@ -92,28 +92,35 @@ class Engine:
         return self._pe_cache[ck]
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, patches, flag, ch, nmasked, training, want_grad):
-        """patches (B, T, F, 2, 2) f32; flag (B, T) uint8; ch (B,) int32.  Returns (out2 = [loss, diff], pred (B*T, F*4), saved)."""
+    def forward(self, patches, flag, ch, nmasked, training, want_grad, frozen=False):
+        """patches (B, T, F, 2, 2) f32; flag (B, T) uint8; ch (B,) int32.  Returns (out2 = [loss, diff], pred (B*T, F*4), saved).
+        frozen: the pretrain_frozen_encoder branch (model.py:603-666) - spectral input mode 4, `spec_spat_decoder` instead of `decoder`."""
         k, st = self.k, self.store
         B, T, F = patches.shape[:3]
         M, P = B * T, B * T * F
         self.step_seed += 1
         p_drop = self.dropout_p if training else 0.0
         self._prepare_weights(F)
-        sv = {"B": B, "T": T, "F": F, "p_drop": p_drop, "seed": self.step_seed, "flag": flag, "ch": ch, "patches": patches} if want_grad else None
+        dec = "spec_spat_decoder" if frozen else "decoder"
+        sv = {"B": B, "T": T, "F": F, "p_drop": p_drop, "seed": self.step_seed, "flag": flag, "ch": ch, "patches": patches, "dec": dec,
+              "frozen": frozen} if want_grad else None
         cat = k.empty(M, SPEC_D + SPAT_D)
         site = [0]
+        # encoders whose parameters are all frozen keep no activations (their backward is skipped, see backward())
+        enc_sv = sv if (sv is not None and any(p.requires_grad for key, p in st.params.items() if "_encoder." in key)) else None
         for enc, D, nl, mode, col in ENCODERS:
-            e = self._stem_fwd(enc, D, mode, patches, flag, ch, B, T, F, training, sv)
+            if frozen and mode == 1:
+                mode = 4
+            e = self._stem_fwd(enc, D, mode, patches, flag, ch, B, T, F, training, enc_sv)
             for l in range(nl):
                 last = l == nl - 1
-                e = self._block_fwd(f"{enc}.embed.layers.{l}", D, e, B, T, training, p_drop, site, sv, out=(cat, col, SPEC_D + SPAT_D) if last else None)
+                e = self._block_fwd(f"{enc}.embed.layers.{l}", D, e, B, T, training, p_drop, site, enc_sv, out=(cat, col, SPEC_D + SPAT_D) if last else None)
         # decoder MLP                                                                             model.py:297-301,582
-        dff = st.shapes["decoder.proj.0.weight"][0]
+        dff = st.shapes[dec + ".proj.0.weight"][0]
         hdec = k.empty(M, dff)
-        k.linear(cat, self.w("decoder.proj.0.weight"), hdec, M, dff, SPEC_D + SPAT_D, bias=st.p("decoder.proj.0.bias"), act=ACT_RELU)
+        k.linear(cat, self.w(dec + ".proj.0.weight"), hdec, M, dff, SPEC_D + SPAT_D, bias=st.p(dec + ".proj.0.bias"), act=ACT_RELU)
         pred = k.empty(M, 4 * F)
-        k.linear(hdec, self.w("decoder.proj.2.weight"), pred, M, 4 * F, dff, bias=st.p("decoder.proj.2.bias"))
+        k.linear(hdec, self.w(dec + ".proj.2.weight"), pred, M, 4 * F, dff, bias=st.p(dec + ".proj.2.bias"))
         # masked reconstruction loss (+ dpred in the same launch)                                  model.py:585-592,721-747
         from . import ops
         out2, dpred = ops.masked_loss(pred.view(B, T, 4 * F), patches, flag, ch, nmasked, want_grad=want_grad)
@@ -330,22 +337,29 @@ class Engine:
         if gscale is not None:
             _lib.check(_lib.lib().sarssl_scale_masked_rows(_lib.ptr(dpred), _lib.dtype_code(dpred), _lib.ptr(sv["flag"]), _lib.ptr(gscale), B, T, F,
                                                            k.stream), "scale_masked_rows")
-        dff = st.shapes["decoder.proj.0.weight"][0]
+        dec = sv["dec"]
+        dff = st.shapes[dec + ".proj.0.weight"][0]
         Dc = SPEC_D + SPAT_D
         # decoder
-        k.linear_wgrad(dpred, sv["hdec"], st.g("decoder.proj.2.weight"), M, 4 * F, dff)
-        k.colsum(dpred, 4 * F, st.g("decoder.proj.2.bias"), M, 4 * F)
+        k.linear_wgrad(dpred, sv["hdec"], st.g(dec + ".proj.2.weight"), M, 4 * F, dff)
+        k.colsum(dpred, 4 * F, st.g(dec + ".proj.2.bias"), M, 4 * F)
         dh = k.empty(M, dff)
-        k.linear_dgrad(dpred, self.w("decoder.proj.2.weight"), dh, M, 4 * F, dff)
+        k.linear_dgrad(dpred, self.w(dec + ".proj.2.weight"), dh, M, 4 * F, dff)
         k.relu_bwd(dh, sv["hdec"], dh, M * dff)
-        k.linear_wgrad(dh, sv["cat"], st.g("decoder.proj.0.weight"), M, dff, Dc)
-        k.colsum(dh, dff, st.g("decoder.proj.0.bias"), M, dff)
-        dcat = k.empty(M, Dc)
-        k.linear_dgrad(dh, self.w("decoder.proj.0.weight"), dcat, M, dff, Dc)
-        del dh
+        k.linear_wgrad(dh, sv["cat"], st.g(dec + ".proj.0.weight"), M, dff, Dc)
+        k.colsum(dh, dff, st.g(dec + ".proj.0.bias"), M, dff)
         ready = on_ready if on_ready is not None else (lambda name: None)
         ready("decoder")
+        if not any(p.requires_grad for key, p in st.params.items() if "_encoder." in key):      # every encoder parameter is frozen (run_pretrain.py:364-371): nothing below the decoder needs a gradient
+            for name in ("spec_encoder", "spat_blocks_1_2", "spat_stem_block_0"):
+                ready(name)
+            return
+        dcat = k.empty(M, Dc)
+        k.linear_dgrad(dh, self.w(dec + ".proj.0.weight"), dcat, M, dff, Dc)
+        del dh
         for enc, D, nl, mode, col in ENCODERS:
+            if sv["frozen"] and mode == 1:
+                mode = 4
             d = None
             for l in reversed(range(nl)):
                 last = l == nl - 1

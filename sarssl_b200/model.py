@@ -53,7 +53,8 @@ class _PretrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, model, patches, flag, ch, want):
-        out2, pred, saved = model.engine.forward(patches, flag, ch, model.nmasked_patch, training=model.training, want_grad=want)
+        out2, pred, saved = model.engine.forward(patches, flag, ch, model.nmasked_patch, training=model.training, want_grad=want,
+                                                 frozen=model.pretrain_frozen_encoder)
         ctx.model, ctx.saved = model, saved
         model._last = {"pred": pred}          # only the prediction (data_vis); the saved activations live in ctx until backward frees them
         return out2[0].clone(), out2[1].clone()
@@ -110,17 +111,18 @@ class VisDict(dict):
 
 
 class SARSSL(nn.Module):
-    """model.py:350-601 (pre-training branch, spec/spat = ['cnn', 'conformer'], in_ver 'separate', decoder ['', 'fc'])."""
+    """model.py:350-719: pre-training branch, frozen-encoder continuation (pretrain_frozen_encoder) and the downstream branch
+    (spec/spat = ['cnn', 'conformer'], in_ver 'separate', decoders ['', 'fc'])."""
 
     def __init__(self, sig_shape=[256, 256, 2, 2], patch_shape=(256, 1), patch_mode="T", nmasked_patch=128 * 1, pretrain=True, use_cls=False,
                  downstream_token="all", downstream_head="mlp", downstream_embed="spec_spat", downstream_dlabel=1, device="cpu",
                  pretrain_frozen_encoder=False):
         super().__init__()
         nf, nt, nreim, nmic = sig_shape
-        if pretrain_frozen_encoder or use_cls:
-            raise _lib.SarsslError("sarssl_b200.SARSSL implements pretrain=True and the downstream branch pretrain=False; use_cls / "
-                                   "pretrain_frozen_encoder (model.py:603-666) are not built")
-        if not pretrain and (downstream_head != "mlp" or downstream_dlabel != 1 or downstream_token != "all" or
+        if use_cls:
+            raise _lib.SarsslError("sarssl_b200.SARSSL implements pretrain=True, pretrain_frozen_encoder=True and the downstream branch; use_cls is not built")
+        pretrain_frozen_encoder = bool(pretrain_frozen_encoder) and not pretrain            # model.py:463,469: `pretrain` wins
+        if not pretrain and not pretrain_frozen_encoder and (downstream_head != "mlp" or downstream_dlabel != 1 or downstream_token != "all" or
                              downstream_embed not in ("spec_spat", "spec", "spat")):
             raise _lib.SarsslError("downstream branch: only head 'mlp', dlabel 1, token 'all', embed in {spec_spat, spec, spat} (the shipped defaults)")
         if tuple(patch_shape) != (nf, 1) or patch_mode != "T" or nreim != 2 or nmic != 2:
@@ -133,7 +135,7 @@ class SARSSL(nn.Module):
         self.device = torch.device(device if str(device) != "cpu" else ("cuda" if torch.cuda.is_available() else "cpu"))
         self.embed_use4ds = downstream_embed
         dembed_ds = {"spec_spat": 768, "spec": 512, "spat": 256}.get(downstream_embed, 768)
-        self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds)
+        self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds, frozen=pretrain_frozen_encoder)
         # the rest are plain attributes (not sub-modules) so that state_dict() holds exactly the reference's 214 entries
         object.__setattr__(self, "patch_split", PatchSplit(patch_shape=patch_shape, f_first=False))
         object.__setattr__(self, "patch_recover", PatchRecover(output_shape=(nf, nt), patch_shape=patch_shape, f_first=False))
@@ -177,13 +179,15 @@ class SARSSL(nn.Module):
     # ---- forward
     def forward(self, x):
         """pretrain=True : x (nb, 2, nf, nt, 2) -> (loss, diff, {'mask': (nb,nf,nt,2), 'pred': (nb,nf,nt,2,2), 'tar': (nb,nf,nt,2,2)})   model.py:519-601
-        pretrain=False: x -> (pred (nb, 1), time-mean embedding (nb, dembed))                                                       model.py:667-719"""
+        pretrain=False: x -> (pred (nb, 1), time-mean embedding (nb, dembed))                                                       model.py:667-719
+        pretrain_frozen_encoder=True (with pretrain=False): x -> (loss, loss * 0, data_vis): un-masked channel of the masked frames into the spectral
+        encoder, `spec_spat_decoder`, gen_loss_spec(tar_maskch=True)                                                               model.py:603-666,749-774"""
         self._engine()
         patches = as_patch_layout(x)
         nb, nt, nf = patches.shape[:3]
         if (nf, nt) != tuple(self.sig_shape[:2]):
             raise _lib.SarsslError(f"input is {nf} bins x {nt} frames but the model was built for {self.sig_shape[:2]}")
-        if not self.pretrain:
+        if not self.pretrain and not self.pretrain_frozen_encoder:
             want = torch.is_grad_enabled() and self.training
             return _DownstreamFn.apply(self._anchor, self, patches, want)
         pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state, dp=self.dp)
@@ -191,4 +195,6 @@ class SARSSL(nn.Module):
         loss, diff = _PretrainFn.apply(self._anchor, self, patches, flag, cidx, want)
         vis = VisDict(self._last["pred"], patches, flag, cidx)
         vis.mask_patch_idx, vis.mask_ch_idx = pidx, cidx
+        if self.pretrain_frozen_encoder:
+            return loss, loss * 0.0, vis                 # model.py:666
         return loss, diff, vis

@@ -15,8 +15,10 @@ import torch.nn as nn
 SPEC_D, SPAT_D, SPEC_LAYERS, SPAT_LAYERS, NHEAD, CNN_CH, DW_K = 512, 256, 1, 3, 4, 64, 31
 
 
-def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D):
-    """[(key, shape, kind)] in the reference's state_dict order.  kind: conv / lin_x (xavier Linear wrapper,
+def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=False, head="mlp"):
+    """[(key, shape, kind)] in the reference's state_dict order.  pretrain: one `decoder`; frozen (pretrain_frozen_encoder, model.py:470-481):
+    `spec_spat_decoder`, `spec_decoder`, `spat_decoder` (the last one built with the spectral width, as the reference does); otherwise the
+    downstream head (`mlp_head`, or nothing for head '').  kind: conv / lin_x (xavier Linear wrapper,
     conformer/modules.py:36-49) / lin_k (default nn.Linear) / bias0 / bias_k / gain / beta / rm / rv / nbt / pe / uv."""
     out = []
 
@@ -60,11 +62,18 @@ def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D):
         stem(enc + ".patch_embed", D)
         for l in range(nl):
             block(f"{enc}.embed.layers.{l}", D)
-    if pretrain:
+    def decoder(name, din):                      # EmbedDecoder(model=['', 'fc'])   model.py:295-301
         dff = 3 * 4 * nf
-        out.extend([("decoder.proj.0.weight", (dff, SPEC_D + SPAT_D), "lin_k"), ("decoder.proj.0.bias", (dff,), "bias_k"),
-                    ("decoder.proj.2.weight", (4 * nf, dff), "lin_k"), ("decoder.proj.2.bias", (4 * nf,), "bias_k")])
-    else:        # downstream head: nn.Sequential(LayerNorm(dembed_ds), Linear(dembed_ds, 1))   model.py:495-500
+        out.extend([(name + ".proj.0.weight", (dff, din), "lin_k"), (name + ".proj.0.bias", (dff,), "bias_k"),
+                    (name + ".proj.2.weight", (4 * nf, dff), "lin_k"), (name + ".proj.2.bias", (4 * nf,), "bias_k")])
+
+    if pretrain:
+        decoder("decoder", SPEC_D + SPAT_D)
+    elif frozen:
+        decoder("spec_spat_decoder", SPEC_D + SPAT_D)
+        decoder("spec_decoder", SPEC_D)
+        decoder("spat_decoder", SPEC_D)
+    elif head == "mlp":        # downstream head: nn.Sequential(LayerNorm(dembed_ds), Linear(dembed_ds, 1))   model.py:495-500
         out.extend([("mlp_head.0.weight", (dembed_ds,), "gain"), ("mlp_head.0.bias", (dembed_ds,), "beta"),
                     ("mlp_head.1.weight", (1, dembed_ds), "lin_k"), ("mlp_head.1.bias", (1,), "bias_k")])
     return out
@@ -116,8 +125,8 @@ def _arena_order(layout):
 class ParamStore:
     """Builds the tree under `root`, owns the arenas, and resolves keys to tensors for the engine."""
 
-    def __init__(self, root, nf=256, device="cpu", seed_generator=None, pretrain=True, dembed_ds=SPEC_D + SPAT_D):
-        self.layout = state_dict_layout(nf, pretrain, dembed_ds)
+    def __init__(self, root, nf=256, device="cpu", seed_generator=None, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=False, head="mlp"):
+        self.layout = state_dict_layout(nf, pretrain, dembed_ds, frozen, head)
         self.shapes = {k: tuple(s) for k, s, _ in self.layout}
         self.kinds = {k: kind for k, _, kind in self.layout}
         self.order = _arena_order(self.layout)

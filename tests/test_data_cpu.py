@@ -124,3 +124,30 @@ def test_batch_loader_order_sharding_and_rows(tmp_path):
     scipy.io.wavfile.write(tmp_path / "short.wav", 16000, np.zeros((100, 2), dtype=np.int16))
     with pytest.raises(SarsslError):
         list(D.WaveformBatchLoader(D.FixMicSigDataset(str(tmp_path), 16000, False, None), 16, pin_memory=False))
+
+
+def test_native_batch_reader_matches_per_file_reads_and_reports_the_bad_file(tmp_path):
+    """sarssl_wav_read_batch_f32 (one call, native threads) == sarssl_wav_read_f32 per file; mismatching files fail loudly."""
+    rng = np.random.default_rng(3)
+    paths = []
+    for i in range(9):
+        p = tmp_path / f"c{i}.wav"
+        scipy.io.wavfile.write(p, 16000, np.round(rng.uniform(-0.9, 0.9, size=(700, 2)) * 32767).astype(np.int16))
+        paths.append(p)
+    out = torch.empty(9, 700, 2)
+    D.wav_read_batch(paths, 700, 2, out, fs=16000, exact=True, nthreads=4)
+    for i, p in enumerate(paths):
+        assert np.array_equal(out[i].numpy(), D.wav_read(p)[0])
+    longer = torch.empty(9, 800, 2)                                     # crop / zero-pad mode
+    D.wav_read_batch(paths, 800, 2, longer, fs=16000, exact=False, nthreads=3)
+    assert torch.equal(longer[:, :700], out) and float(longer[:, 700:].abs().max()) == 0.0
+    scipy.io.wavfile.write(tmp_path / "short.wav", 16000, np.zeros((650, 2), dtype=np.int16))
+    with pytest.raises(SarsslError, match="short.wav"):
+        D.wav_read_batch(paths[:4] + [tmp_path / "short.wav"] + paths[4:], 700, 2, torch.empty(10, 700, 2), fs=16000, exact=True, nthreads=4)
+    with pytest.raises(SarsslError, match="8000|16000"):
+        D.wav_read_batch(paths, 700, 2, out, fs=8000, exact=True)
+    ds = D.FixMicSigDataset(data_dir=str(tmp_path), fs=16000, load_anno=False, dataset_sz=None)
+    ds.files = paths
+    ds.dataset_sz = len(paths)
+    got = [b[0] for b in D.WaveformBatchLoader(ds, batch_size=4, num_workers=3, pin_memory=False)]
+    assert [tuple(b.shape) for b in got] == [(4, 700, 2), (4, 700, 2), (1, 700, 2)] and torch.equal(torch.cat(got), out)

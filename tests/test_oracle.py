@@ -162,3 +162,32 @@ def test_downstream_branch_matches_reference_fixture(name, embed):
             gr = sd[key].grad
             mine = float(gr.norm()) if gr is not None else 0.0
             assert abs(mine - float(g[k])) <= 1e-3 * float(g[k]) + 1e-6 * gmax, key
+
+
+def test_frozen_encoder_branch_matches_reference_fixture():
+    """oracle.frozen_encoder_forward vs the reference's SARSSL(pretrain_frozen_encoder=True) forward/backward
+    (model.py:603-666, gen_loss_spec :749-774) - loss, the prediction and the gradients of the only trainable module (spec_spat_decoder)."""
+    import random
+    g = np.load(os.path.join(GOLDEN, "frozen_nt16_b3.npz"))
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sd = O.synthetic_state_dict(int(g["sd_seed"]), pretrain=False, frozen=True)
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]                       # the reference's state_dict keys, in its order
+    names = [k for k in sd if k.startswith("spec_spat_decoder.")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    x = O.preprocess(O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"])))
+    random.seed(int(g["mask_seed"]))
+    pidx, cidx = O.draw_masks(nb, nt, nt // 2, 2)
+    loss, zero, vis = O.frozen_encoder_forward(x, sd, pidx, cidx, training=True)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"]) and float(zero) == 0.0 == float(g["zero"])
+    assert np.allclose(vis["pred"].numpy(), g["pred"], rtol=1e-4, atol=1e-5)
+    assert sorted(k[10:] for k in g.files if k.startswith("grad_norm/")) == sorted(names)      # the encoders received no gradient in the reference
+    for k in names:
+        gr = sd[k].grad.reshape(-1)
+        assert abs(float(gr.norm()) - float(g["grad_norm/" + k])) <= 1e-4 * float(g["grad_norm/" + k]), k
+        samp = gr.numpy()[O.fixture_sample_idx(k, gr.numel(), 512)]
+        assert np.abs(samp - g["grad_rand/" + k]).max() <= 1e-4 * np.abs(g["grad_rand/" + k]).max() + 1e-9, k
+    for k in g.files:
+        if k.startswith("bn/"):
+            assert np.allclose(sd[k[3:]].numpy(), g[k], rtol=1e-4, atol=1e-6), k
