@@ -375,6 +375,131 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) stft_frontend_warp_kerne
     }
 }
 
+// ---------------- third-generation fused kernel: independent warps, rendezvous one frame behind ---------------------------------
+// The warp-worker kernel above stalls because every warp waits for its clip's rendezvous right after publishing: the 257 warps of a clip
+// meet after every frame and the SM alternates between a compute phase and a store phase.  Here the wait is software-pipelined: a warp
+// transforms frame r (round-robin list order, f = warp_id + r * warps), publishes its |X_ch0| partial sum, and only THEN finishes frame
+// r - 1 (whose un-scaled bins wait in the second transpose buffer): by that time the other warps have had a whole transform's time to
+// publish their frames of that clip, so the spin almost never spins, nothing runs in lock step, and loads, butterflies and the scaled
+// stores of different warps overlap freely.  The input needs one 4 KB buffer per warp: the next frame's bulk-TMA copy is issued as soon
+// as this frame's samples are in registers.
+// Deadlock-free when every warp is resident and warps >= nt - 1: a warp publishes round r before it waits for round r - 1, and a clip that
+// holds a round r - 1 frame ends before frame (r + 1) * warps.
+constexpr int kW2Warps = 8;
+struct Warp2Smem {
+    float2 in[kW2Warps][kFftN];                   // 32 KB   per-warp staged samples (ch0, ch1)
+    float2 tb[kW2Warps][2][kWTransFloat2];        // 66 KB   per-warp transpose buffer / staged un-scaled output, double buffered
+    float win[kFftN];                             // 2 KB
+    uint64_t bar[kW2Warps];
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(const float* __restrict__ sig, float4* __restrict__ out, float* partials,
+                                                                              unsigned* counters, int nb, long long nsample, int nt, float eps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Warp2Smem& sm = *reinterpret_cast<Warp2Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    WarpFftLane lc;
+    lc.init(lane);
+    for (int i = tid; i < kFftN; i += kW2Warps * 32) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
+    if (lane == 0) {
+        mbar_init(&sm.bar[warp], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const long long total = (long long)nb * nt;
+    const long long gw = (long long)blockIdx.x * kW2Warps + warp, G = (long long)gridDim.x * kW2Warps;
+    const int k1 = lane & 15, h = lane >> 4;
+    const int kbase = h == 0 ? k1 : (((16 - k1) & 15) + 128);       // bin of out[j] is kbase + 16*j
+    const float inv_bins = 1.0f / (float)((long long)kBins * nt);
+    float2* in = sm.in[warp];
+    auto issue = [&](long long f) {
+        if (lane == 0) {
+            const long long b = f / nt, t = f - b * nt;
+            mbar_expect_tx(&sm.bar[warp], kFftN * sizeof(float2));
+            tma_bulk_g2s(in, sig + ((size_t)b * nsample + (size_t)t * kHop) * 2, kFftN * sizeof(float2), &sm.bar[warp]);
+        }
+    };
+    // scale and store the frame staged in `stage` once its clip is complete
+    auto finish = [&](long long f, const float4* stage) {
+        const long long b = f / nt;
+        const int t = (int)(f - b * nt);
+        if (lane == 0) {
+            unsigned spins = 0;
+            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)nt) {
+                __nanosleep(32);
+                if (++spins > (1u << 24)) { atomicExch(&counters[1], 1u); break; }      // never expected; report instead of hanging
+            }
+        }
+        __syncwarp();
+        float s = 0.f;
+        for (int i = lane; i < nt; i += 32) s += __ldcg(&partials[(size_t)b * nt + i]);        // fixed order: deterministic
+        s = warp_sum(s);
+        const float scale = 1.0f / (s * inv_bins + eps);
+        float4* dst = out + ((size_t)b * nt + t) * kHop;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float4 ov = stage[lane + 32 * r];
+            ov.x *= scale; ov.y *= scale; ov.z *= scale; ov.w *= scale;
+            st_stream_f4(dst + lane + 32 * r, ov);
+        }
+    };
+    uint32_t ph = 0;
+    int cur = 0;
+    long long pf = -1;                                               // published, not yet stored
+    if (gw < total) issue(gw);
+    for (long long f = gw; f < total; f += G) {
+        const long long b = f / nt;
+        const int t = (int)(f - b * nt);
+        mbar_wait(&sm.bar[warp], ph);
+        ph ^= 1u;
+        float2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const float2 sx = in[32 * n1 + lane];
+            const float w = sm.win[32 * n1 + lane];
+            v[n1] = make_float2(sx.x * w, sx.y * w);
+        }
+        __syncwarp();                                                // every lane has its samples: the buffer can take the next frame
+        if (f + G < total) issue(f + G);
+        float2* tb = sm.tb[warp][cur];
+        wfft_stage1(v, lc, tb, lane);
+        __syncwarp();
+        wfft_stage2(v, tb, lane);
+        wfft_combine(v, lane);
+        float4 o[8], nyq;
+        wfft_split_all(v, lane, o, nyq);
+        float4* stage = reinterpret_cast<float4*>(tb);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kbase + 16 * j;
+            part += sqrt_approx(o[j].x * o[j].x + o[j].z * o[j].z);
+            if (k >= 1) stage[k - 1] = o[j];
+        }
+        if (lane == 16) {
+            part += sqrt_approx(nyq.x * nyq.x + nyq.z * nyq.z);
+            stage[255] = nyq;
+        }
+        part = warp_sum(part);
+        if (lane == 0) {
+            partials[(size_t)b * nt + t] = part;
+            __threadfence();
+            atomicAdd(&counters[2 + b], 1u);
+        }
+        __syncwarp();                                                // staged bins visible to the whole warp
+        if (pf >= 0) finish(pf, reinterpret_cast<const float4*>(sm.tb[warp][cur ^ 1]));
+        pf = f;
+        cur ^= 1;
+    }
+    if (pf >= 0) finish(pf, reinterpret_cast<const float4*>(sm.tb[warp][cur ^ 1]));
+}
+
 // ---------------- generic path ----------------
 // grid.x = nb * ipc * npair.  Pair p covers channels (2p, 2p+1) (second one zero if absent).
 // spec: complex64 [nb][nt][257][nch] (interleaved re, im);  partials: |X_ch0| sums per (clip, frame block).
@@ -539,6 +664,23 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
             const int grid = (int)(items3 < resident3 ? items3 : resident3);
             stft_frontend_pipe_kernel<<<grid, kThreads, sizeof(PipeSmem), stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt,
                                                                                    ipc3, eps);
+            SARSSL_LAUNCH_CHECK();
+            return SARSSL_OK;
+        }
+    }
+    if (force_generic == 5) {      // independent warps, rendezvous one frame behind
+        static int max_ctas_v5 = -1;
+        if (max_ctas_v5 < 0) {
+            SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Warp2Smem)));
+            int n = 0;
+            SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp2_kernel, kW2Warps * 32, sizeof(Warp2Smem)));
+            max_ctas_v5 = n;
+        }
+        const long long resident5 = (long long)max_ctas_v5 * sm_count(), frames = (long long)nb * nt, ctas = (frames + kW2Warps - 1) / kW2Warps;
+        if (nch == 2 && (nsample % 2 == 0) && max_ctas_v5 > 0 && (ctas <= resident5 || resident5 * kW2Warps >= nt)) {
+            SARSSL_CUDA(reset_counters(counters, nb, stream));
+            stft_frontend_warp2_kernel<<<(int)(ctas < resident5 ? ctas : resident5), kW2Warps * 32, sizeof(Warp2Smem), stream>>>(
+                sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, eps);
             SARSSL_LAUNCH_CHECK();
             return SARSSL_OK;
         }

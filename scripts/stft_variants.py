@@ -1,4 +1,4 @@
-"""Time the STFT front-end variants (GPU box): 4 = fused kernel (64-lane FFT groups), 3 = the same with the load / rendezvous / store pipelined inside the CTA (default), 2 = experimental warp-worker kernel, 1 = generic 3-kernel path."""
+"""Time the STFT front-end variants (GPU box): 4 = fused kernel (64-lane FFT groups), 3 = the same with the load / rendezvous / store pipelined inside the CTA (default), 2 = experimental warp-worker kernel, 5 = independent warps with the rendezvous one frame behind, 1 = generic 3-kernel path."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from sarssl_b200 import ops
@@ -6,7 +6,7 @@ nb, ns = 1024, 65792
 sig = 0.1 * torch.randn(nb, ns, 2, device='cuda')
 out = torch.empty(nb, 256, 256, 2, 2, device='cuda')
 ref = None
-for variant in (4, 3, 2, 1):
+for variant in (4, 5, 2, 1):
     for _ in range(3): ops.stft_frontend(sig, out=out, force_generic=variant)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

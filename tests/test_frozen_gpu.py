@@ -80,7 +80,12 @@ def test_unfrozen_encoders_get_gradients_matching_oracle():
     lo, _, _ = O.frozen_encoder_forward(O.preprocess(sig), sd, pidx, cidx, training=True)
     lo.backward()
     assert abs(float(loss) - float(lo)) <= 1e-4 * float(lo)
-    worst = max((rel(m.store.p(k).grad.cpu(), sd[k].grad), k) for k in names)
+    gmax = max(float(sd[k].grad.norm()) for k in names)
+
+    def err(k):        # analytically-zero gradients (key_proj bias: softmax is shift invariant) hold rounding noise only, hence the floor
+        a, b = m.store.p(k).grad.cpu().double(), sd[k].grad.double()
+        return float((a - b).norm() / (b.norm() + 1e-4 * gmax))
+    worst = max((err(k), k) for k in names)
     assert worst[0] < 1e-2, worst
     for k in ("spec_decoder.proj.0.weight", "spat_decoder.proj.2.bias"):           # built but unused by forward (model.py:638-651 are commented out)
         assert float(m.store.p(k).grad.abs().max()) == 0.0
