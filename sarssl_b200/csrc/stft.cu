@@ -158,239 +158,26 @@ __global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const flo
     }
 }
 
-// ---------------- pipelined fused kernel -------------------------------------------------------------------------------------
-// Same work split as stft_frontend_fused_kernel (item = kPF consecutive frames of one clip, one frame per 64-lane group), but the
-// three latencies that kernel exposes are overlapped inside the CTA:
-//   * the bulk-TMA load of item n+1 is in flight while item n is transformed            (double-buffered input);
-//   * the per-clip rendezvous and the scaled store of item n-1 happen after item n has been transformed and published, so the
-//     other CTAs working on that clip had a whole transform's time to arrive          (double-buffered un-scaled output).
-// Items are assigned statically, item(n) = blockIdx.x + n * gridDim.x, with gridDim.x >= items per clip: a CTA owns at most one
-// item of any clip, items n-1 and n+1 lie in different clips, and a CTA only ever waits for a clip after publishing everything it
-// has transformed - with all CTAs resident the rendezvous cannot dead-lock (induction over the clip index).
-constexpr int kPF = 4;
-struct PipeSmem {
-    float2 in[2][(kPF + 1) * kHop];               // 2 x 10 KB  staged samples (ch0, ch1)
-    float4 out[2][kPF * kHop];                    // 2 x 16 KB  un-scaled bins 1..256, (re0, re1, im0, im1)
-    float scratch[kGroups][kFftScratchFloats];    // 18 KB
-    float red[32];
-    uint64_t bar[2];
-    float scale;
-};
-
-__global__ void __launch_bounds__(kThreads) stft_frontend_pipe_kernel(const float* __restrict__ sig, float4* __restrict__ out,
-                                                                    float* partials, unsigned* counters, int nb,
-                                                                    long long nsample, int nt, int ipc, float eps) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
-    const int tid = threadIdx.x, g = tid >> 6, l = tid & 63;
-    FftLane lane;
-    lane.init(l);
-    float* sre = sm.scratch[g];
-    float* sim = sre + kFftPlane;
-    const long long nitems = (long long)nb * ipc;
-    auto issue_load = [&](long long item, int buf) {          // thread 0 only
-        const int b = (int)(item / ipc), fb = (int)(item - (long long)b * ipc);
-        const int f0 = fb * kPF, nfr = min(kPF, nt - f0);
-        const uint32_t bytes = (uint32_t)(nfr + 1) * kHop * sizeof(float2);
-        mbar_expect_tx(&sm.bar[buf], bytes);
-        tma_bulk_g2s(sm.in[buf], sig + ((size_t)b * nsample + (size_t)f0 * kHop) * 2, bytes, &sm.bar[buf]);
-    };
-    if (tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
-        mbar_fence_init();
-        if (blockIdx.x < nitems) issue_load(blockIdx.x, 0);
-    }
-    __syncthreads();
-    uint32_t phases = 0;                                      // bit buf = parity to wait for on bar[buf]
-    int pb = -1, pfb = 0, pnfr = 0;                            // the published, not yet stored item (clip, item in clip, frames)
-    for (int n = 0;; ++n) {
-        const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
-        const int buf = n & 1;
-        const bool valid = item < nitems;
-        int b = 0, fb = 0, nfr = 0;
-        if (valid) {
-            if (tid == 0 && item + gridDim.x < nitems) issue_load(item + gridDim.x, buf ^ 1);      // in[buf ^ 1] was last read two barriers ago
-            b = (int)(item / ipc); fb = (int)(item - (long long)b * ipc);
-            nfr = min(kPF, nt - fb * kPF);
-            mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
-            phases ^= 1u << buf;
-            float part = 0.f;
-            if (g < nfr) {
-                float2 v[8];
-                fft_frame(sm.in[buf] + g * kHop, lane, sre, sim, l, g, v);
-                float4* orow = sm.out[buf] + g * kHop;
-#pragma unroll
-                for (int k3 = 0; k3 < 4; ++k3) {
-                    const float4 o = split_bin(v, sre, sim, l, k3);
-                    part += sqrtf(o.x * o.x + o.z * o.z);
-                    const int k = l + 64 * k3;
-                    if (k >= 1) orow[k - 1] = o;
-                }
-                if (l == 0) {
-                    const float4 o = split_bin(v, sre, sim, 0, 4);
-                    part += sqrtf(o.x * o.x + o.z * o.z);
-                    orow[255] = o;
-                }
-            }
-            const float total = block_sum(part, sm.red);
-            if (tid == 0) {
-                partials[(size_t)b * ipc + fb] = total;
-                __threadfence();
-                atomicAdd(&counters[2 + b], 1u);
-            }
-        }
-        if (pb >= 0) {                                        // finish the previous item: rendezvous, scale, store
-            if (tid == 0) {
-                unsigned spins = 0;
-                while (ld_acquire_u32(&counters[2 + pb]) < (unsigned)ipc) {
-                    __nanosleep(32);
-                    if (++spins > (1u << 24)) { atomicExch(&counters[1], 1u); break; }      // never expected; report instead of hanging
-                }
-            }
-            __syncthreads();
-            if (tid < 32) {                                   // fixed-order (deterministic) sum of the clip's partials
-                float s = 0.f;
-                for (int i = tid; i < ipc; i += 32) s += __ldcg(&partials[(size_t)pb * ipc + i]);
-                s = warp_sum(s);
-                if (tid == 0) sm.scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
-            }
-            __syncthreads();
-            const float scale = sm.scale;
-            float4* dst = out + ((size_t)pb * nt + (size_t)pfb * kPF) * kHop;
-            const float4* src = sm.out[buf ^ 1];
-            for (int i = tid; i < pnfr * kHop; i += kThreads) {
-                float4 o = src[i];
-                o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
-                st_stream_f4(dst + i, o);
-            }
-        }
-        __syncthreads();
-        if (!valid) break;
-        pb = b; pfb = fb; pnfr = nfr;
-    }
-}
-
-// ---------------- second-generation fused kernel: independent warps, one transform each (fft512w.cuh) ----------------
-// Every warp of the persistent grid is its own worker: frame f = warp_global_id + round * total_warps of the (clip-major) frame list.
-// Per frame: bulk-TMA its 512 samples (double buffered: the next frame's samples are in flight while this one is transformed),
-// FFT in registers + one smem transpose, stage the un-scaled bins in the transpose buffer, publish |X_ch0| partial sum and arrive on
-// the clip's counter, spin (lane 0) until the clip's nt frames have arrived, add the nt partials in a fixed order, scale and write the
-// 4 KB frame row.  No block-level barrier exists after start-up, so the SM's warps drift into different phases and overlap load /
-// compute / store.  Deadlock-free: frames are assigned round-robin in list order, a warp publishes before it waits, and it only waits
-// for frames of the same or an earlier round; all warps are resident (grid sized by the occupancy query).
-constexpr int kWarpsPerCta = 8;
-struct WarpWorkerSmem {
-    float2 in[kWarpsPerCta][2][kFftN];            // 64 KB   per-warp double-buffered samples
-    float2 tb[kWarpsPerCta][kWTransFloat2];       // 33 KB   per-warp transpose buffer / staged output
-    float win[kFftN];                             // 2 KB
-    uint64_t bar[kWarpsPerCta][2];
-};
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) stft_frontend_warp_kernel(const float* __restrict__ sig, float4* __restrict__ out, float* partials,
-                                                                                 unsigned* counters, int nb, long long nsample, int nt, float eps) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WarpWorkerSmem& sm = *reinterpret_cast<WarpWorkerSmem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    WarpFftLane lc;
-    lc.init(lane);
-    for (int i = tid; i < kFftN; i += kWarpsPerCta * 32) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
-    if (lane == 0) {
-        mbar_init(&sm.bar[warp][0], 1);
-        mbar_init(&sm.bar[warp][1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const long long total = (long long)nb * nt;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp, G = (long long)gridDim.x * kWarpsPerCta;
-    const int k1 = lane & 15, h = lane >> 4;
-    const int kbase = h == 0 ? k1 : (((16 - k1) & 15) + 128);       // bin of out[j] is kbase + 16*j
-    float2* tb = sm.tb[warp];
-    float4* stage = reinterpret_cast<float4*>(tb);
-    uint32_t ph0 = 0, ph1 = 0;
-    int buf = 0;
-    auto issue = [&](long long f, int bsel) {
-        if (lane == 0) {
-            const long long b = f / nt, t = f - b * nt;
-            mbar_expect_tx(&sm.bar[warp][bsel], kFftN * sizeof(float2));
-            tma_bulk_g2s(sm.in[warp][bsel], sig + ((size_t)b * nsample + (size_t)t * kHop) * 2, kFftN * sizeof(float2), &sm.bar[warp][bsel]);
-        }
-    };
-    if (gw < total) issue(gw, 0);
-    for (long long f = gw; f < total; f += G) {
-        const long long b = f / nt;
-        const int t = (int)(f - b * nt);
-        if (f + G < total) issue(f + G, buf ^ 1);                    // prefetch the next frame of this warp
-        mbar_wait(&sm.bar[warp][buf], buf ? ph1 : ph0);
-        if (buf) ph1 ^= 1u; else ph0 ^= 1u;
-        const float2* frame = sm.in[warp][buf];
-        float2 v[16];
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const float2 sx = frame[32 * n1 + lane];
-            const float w = sm.win[32 * n1 + lane];
-            v[n1] = make_float2(sx.x * w, sx.y * w);
-        }
-        wfft_stage1(v, lc, tb, lane);
-        __syncwarp();
-        wfft_stage2(v, tb, lane);
-        wfft_combine(v, lane);
-        float4 o[8], nyq;
-        wfft_split_all(v, lane, o, nyq);
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = kbase + 16 * j;
-            part += sqrtf(o[j].x * o[j].x + o[j].z * o[j].z);
-            if (k >= 1) stage[k - 1] = o[j];
-        }
-        if (lane == 16) {
-            part += sqrtf(nyq.x * nyq.x + nyq.z * nyq.z);
-            stage[255] = nyq;
-        }
-        part = warp_sum(part);
-        if (lane == 0) {
-            partials[(size_t)b * nt + t] = part;
-            __threadfence();
-            atomicAdd(&counters[2 + b], 1u);
-            unsigned spins = 0;
-            while (ld_acquire_u32(&counters[2 + b]) < (unsigned)nt) {
-                __nanosleep(32);
-                if (++spins > (1u << 24)) { atomicExch(&counters[1], 1u); break; }
-            }
-        }
-        __syncwarp();
-        float s = 0.f;
-        for (int i = lane; i < nt; i += 32) s += __ldcg(&partials[(size_t)b * nt + i]);
-        s = warp_sum(s);
-        const float scale = 1.0f / (s / (float)((long long)kBins * nt) + eps);
-        float4* dst = out + ((size_t)b * nt + t) * kHop;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float4 ov = stage[lane + 32 * r];
-            ov.x *= scale; ov.y *= scale; ov.z *= scale; ov.w *= scale;
-            st_stream_f4(dst + lane + 32 * r, ov);
-        }
-        __syncwarp();
-        buf ^= 1;
-    }
-}
-
-// ---------------- third-generation fused kernel: independent warps, rendezvous one frame behind ---------------------------------
-// The warp-worker kernel above stalls because every warp waits for its clip's rendezvous right after publishing: the 257 warps of a clip
-// meet after every frame and the SM alternates between a compute phase and a store phase.  Here the wait is software-pipelined: a warp
-// transforms frame r (round-robin list order, f = warp_id + r * warps), publishes its |X_ch0| partial sum, and only THEN finishes frame
-// r - 1 (whose un-scaled bins wait in the second transpose buffer): by that time the other warps have had a whole transform's time to
-// publish their frames of that clip, so the spin almost never spins, nothing runs in lock step, and loads, butterflies and the scaled
-// stores of different warps overlap freely.  The input needs one 4 KB buffer per warp: the next frame's bulk-TMA copy is issued as soon
-// as this frame's samples are in registers.
-// Deadlock-free when every warp is resident and warps >= nt - 1: a warp publishes round r before it waits for round r - 1, and a clip that
-// holds a round r - 1 frame ends before frame (r + 1) * warps.
+// ---------------- fused kernel, independent warps (default) ---------------------------------------------------------------------
+// Every warp of the persistent grid is its own worker with its own transform (fft512w.cuh: 16 points per lane, one shared-memory
+// transpose, no block-level barrier after start-up): frame f = warp_id + r * warps of the clip-major frame list in round r.
+// The per-clip normalisation needs the clip's nt partial sums of |X_ch0| before anything can be written.  A warp that waited for its
+// clip right after publishing would meet the clip's other 256 warps after every frame and the SM would alternate between a compute
+// phase and a store phase (measured: 1.3 ms).  Instead the wait is software-pipelined: a warp transforms frame r, publishes its partial
+// sum, and only THEN finishes frame r - 1, whose spectrum waits in the second Z buffer - by then the clip's other warps have had a
+// whole transform's time to publish, nothing runs in lock step, and loads, butterflies and scaled stores of different warps overlap.
+// The rendezvous carries no fence and no atomic: a partial sum is published as ONE 64-bit store {sum, launch epoch}; a clip is complete
+// when all nt of its words carry this launch's epoch (L2-coherent loads; the words are the only data exchanged, so nothing else has to
+// be ordered).
+// (__threadfence + atomicAdd + ld.acquire cost 48 % of the stall samples of the first version: profiles/r02_stft_frontend.txt.)
+// One 4 KB input buffer per warp: the next frame's bulk-TMA copy is issued as soon as this frame's samples are in registers.
+// Deadlock-free when every warp is resident and warps >= nt - 1: a warp publishes round r before it waits for round r - 1, and a clip
+// that holds a round r - 1 frame ends before frame (r + 1) * warps.
 constexpr int kW2Warps = 8;
 struct Warp2Smem {
     float2 in[kW2Warps][kFftN];                   // 32 KB   per-warp staged samples (ch0, ch1)
-    float2 tb[kW2Warps][2][kWTransFloat2];        // 66 KB   per-warp transpose buffer / staged un-scaled output, double buffered
-    float win[kFftN];                             // 2 KB
+    float2 tb[kW2Warps][2][kWTransFloat2];        // 66 KB   per-warp transpose buffer, then the frame's Z in bin order; double buffered
+    float2 win2[kFftN];                           // 4 KB    periodic Hann window as (w, w) pairs (one packed multiply per sample pair)
     uint64_t bar[kW2Warps];
 };
 
@@ -399,10 +186,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
-// The rendezvous carries no fence and no atomic: a frame's |X_ch0| partial sum is published as ONE 64-bit store {sum, launch epoch}, and a
-// clip is complete when all nt of its words carry this launch's epoch (read with L2-coherent loads; the words are the only data exchanged,
-// so nothing else has to be ordered).  __threadfence + atomicAdd + ld.acquire cost 48 % of this kernel's stall samples before.
 __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -410,42 +193,44 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
 }
 
 __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(const float* __restrict__ sig, float4* __restrict__ out,
-                                                                              unsigned long long* partials, unsigned* counters, unsigned epoch, int nb,
-                                                                              long long nsample, int nt, float eps) {
+                                                                              unsigned long long* partials, unsigned* counters, unsigned epoch, int nb, long long nsample, int nt,
+                                                                              float eps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Warp2Smem& sm = *reinterpret_cast<Warp2Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     WarpFftLane lc;
     lc.init(lane);
-    for (int i = tid; i < kFftN; i += kW2Warps * 32) sm.win[i] = 0.5f - 0.5f * cospif((float)i / 256.0f);
+    for (int i = tid; i < kFftN; i += kW2Warps * 32) {
+        const float w = 0.5f - 0.5f * cospif((float)i / 256.0f);
+        sm.win2[i] = make_float2(w, w);
+    }
     if (lane == 0) {
         mbar_init(&sm.bar[warp], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    const long long total = (long long)nb * nt;
-    const long long gw = (long long)blockIdx.x * kW2Warps + warp, G = (long long)gridDim.x * kW2Warps;
-    const int k1 = lane & 15, h = lane >> 4;
-    const int kbase = h == 0 ? k1 : (((16 - k1) & 15) + 128);       // bin of out[j] is kbase + 16*j
+    const unsigned total = (unsigned)nb * (unsigned)nt, unt = (unsigned)nt;
+    const unsigned gw = blockIdx.x * kW2Warps + warp, G = gridDim.x * kW2Warps;
+    const unsigned db = G / unt, dt = G - db * unt;                  // frame f + G = (b + db, t + dt) with one carry
     const float inv_bins = 1.0f / (float)((long long)kBins * nt);
+    const float2 sgn = lane < 16 ? make_float2(1.f, 1.f) : make_float2(-1.f, -1.f);
     float2* in = sm.in[warp];
-    auto issue = [&](long long f) {
+    auto issue = [&](unsigned b, unsigned t) {
         if (lane == 0) {
-            const long long b = f / nt, t = f - b * nt;
             mbar_expect_tx(&sm.bar[warp], kFftN * sizeof(float2));
             tma_bulk_g2s(in, sig + ((size_t)b * nsample + (size_t)t * kHop) * 2, kFftN * sizeof(float2), &sm.bar[warp]);
         }
     };
-    // scale and store the frame staged in `stage` once its clip is complete
-    auto finish = [&](long long f, const float4* stage) {
-        const long long b = f / nt;
-        const int t = (int)(f - b * nt);
-        const unsigned long long* pp = partials + (size_t)b * nt;
+    // scale and store the frame whose Z sits in `zb`, once its clip is complete
+    auto finish = [&](unsigned b, unsigned t, const float2* zb) {
+        // (a per-clip {scale, epoch} word published by the first finisher was tried: the clip's 257 warps arrive together, all miss it, and
+        //  their loads of the one hot word serialise on a single L2 slice - 3.5 ms instead of 0.47)
+        const unsigned long long* pp = partials + (size_t)b * unt;
         float s;
         for (unsigned spins = 0;; ++spins) {
             s = 0.f;
             bool ok = true;
-            for (int i = lane; i < nt; i += 32) {                    // fixed order: deterministic
+            for (unsigned i = lane; i < unt; i += 32) {              // fixed order: deterministic
                 const unsigned long long w = ld_cg_u64(pp + i);
                 ok = ok && (unsigned)(w >> 32) == epoch;
                 s += __uint_as_float((unsigned)w);
@@ -455,60 +240,63 @@ __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(c
             if (spins > (1u << 22)) { if (lane == 0) atomicExch(&counters[1], 1u); break; }      // never expected; report instead of hanging
         }
         s = warp_sum(s);
-        const float scale = 1.0f / (s * inv_bins + eps);
-        float4* dst = out + ((size_t)b * nt + t) * kHop;
+        // the bins below are 2 X and the partial sums 2 sum|X_ch0| (the split's factor 1/2 is folded in here): out = 2 X * scale
+        const float scale = 0.5f / (0.5f * s * inv_bins + eps);
+        const float2 sc2 = make_float2(scale, scale);
+        float4* dst = out + ((size_t)b * unt + t) * kHop + lane;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            float4 ov = stage[lane + 32 * r];
-            ov.x *= scale; ov.y *= scale; ov.z *= scale; ov.w *= scale;
-            st_stream_f4(dst + lane + 32 * r, ov);
+            const int k = 1 + lane + 32 * r;
+            const float4 o = wfft_split2(zb[wz_pos(k)], zb[wz_pos(512 - k)]);
+            const float2 lo = cscale2(make_float2(o.x, o.y), sc2), hi = cscale2(make_float2(o.z, o.w), sc2);
+            st_stream_f4(dst + 32 * r, make_float4(lo.x, lo.y, hi.x, hi.y));
         }
     };
     uint32_t ph = 0;
     int cur = 0;
-    long long pf = -1;                                               // published, not yet stored
-    if (gw < total) issue(gw);
-    for (long long f = gw; f < total; f += G) {
-        const long long b = f / nt;
-        const int t = (int)(f - b * nt);
+    unsigned b = gw / unt, t = gw - b * unt;
+    unsigned pb = 0, pt = 0;
+    bool have_prev = false;                                          // published, not yet stored
+    if (gw < total) issue(b, t);
+    for (unsigned f = gw; f < total; f += G) {
         mbar_wait(&sm.bar[warp], ph);
         ph ^= 1u;
         float2 v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const float2 sx = in[32 * n1 + lane];
-            const float w = sm.win[32 * n1 + lane];
-            v[n1] = make_float2(sx.x * w, sx.y * w);
-        }
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = cscale2(in[32 * n1 + lane], sm.win2[32 * n1 + lane]);
         __syncwarp();                                                // every lane has its samples: the buffer can take the next frame
-        if (f + G < total) issue(f + G);
+        unsigned nb_ = b + db, nt_ = t + dt;
+        if (nt_ >= unt) { nt_ -= unt; ++nb_; }
+        if (f + G < total) issue(nb_, nt_);
         float2* tb = sm.tb[warp][cur];
         wfft_stage1(v, lc, tb, lane);
         __syncwarp();
         wfft_stage2(v, tb, lane);
-        wfft_combine(v, lane);
-        float4 o[8], nyq;
-        wfft_split_all(v, lane, o, nyq);
-        float4* stage = reinterpret_cast<float4*>(tb);
+        float2 o[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) o[s] = make_float2(__shfl_xor_sync(0xffffffffu, v[s].x, 16), __shfl_xor_sync(0xffffffffu, v[s].y, 16));
+        wfft_store_z(v, o, sgn, tb, lane);                           // (the shuffles above ordered every lane's transpose reads before this)
+        __syncwarp();
         float part = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = kbase + 16 * j;
-            part += sqrt_approx(o[j].x * o[j].x + o[j].z * o[j].z);
-            if (k >= 1) stage[k - 1] = o[j];
+        for (int r = 0; r < 8; ++r) {
+            const int k = 1 + lane + 32 * r;
+            const float2 z = tb[wz_pos(k)], p = tb[wz_pos(512 - k)];
+            const float a = z.x + p.x, c = z.y - p.y;
+            part += sqrt_approx(a * a + c * c);
         }
-        if (lane == 16) {
-            part += sqrt_approx(nyq.x * nyq.x + nyq.z * nyq.z);
-            stage[255] = nyq;
+        {   // bin 0 (DC) is dropped from the patches but counts in the mean magnitude: X_ch0[0] = Re Z[0]
+            const float z0 = tb[0].x;
+            if (lane == 0) part += 2.f * fabsf(z0);
         }
         part = warp_sum(part);
-        if (lane == 0) __stcg(&partials[(size_t)b * nt + t], ((unsigned long long)epoch << 32) | __float_as_uint(part));
-        __syncwarp();                                                // staged bins visible to the whole warp
-        if (pf >= 0) finish(pf, reinterpret_cast<const float4*>(sm.tb[warp][cur ^ 1]));
-        pf = f;
+        if (lane == 0) __stcg(&partials[(size_t)b * unt + t], ((unsigned long long)epoch << 32) | __float_as_uint(part));
+        if (have_prev) finish(pb, pt, sm.tb[warp][cur ^ 1]);
+        pb = b; pt = t; have_prev = true;
+        b = nb_; t = nt_;
         cur ^= 1;
     }
-    if (pf >= 0) finish(pf, reinterpret_cast<const float4*>(sm.tb[warp][cur ^ 1]));
+    if (have_prev) finish(pb, pt, sm.tb[warp][cur ^ 1]);
 }
 
 // ---------------- generic path ----------------
@@ -608,7 +396,7 @@ extern "C" size_t sarssl_stft_workspace_bytes(int nb, long long nsample, int nch
     size_t bytes = 256;                                            // counters: head, error, pad
     bytes += ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;    // per-clip arrivals
     bytes += ((size_t)nb * (nt > 0 ? nt : 1) * sizeof(unsigned long long) + 255) / 256 * 256; // partial sums (one {sum, epoch} word per frame)
-    bytes += ((size_t)nb * sizeof(float) + 255) / 256 * 256;       // per-clip scale (generic path)
+    bytes += ((size_t)nb * sizeof(unsigned long long) + 255) / 256 * 256;       // per-clip scale (generic path: float; independent-warp kernel: {scale, epoch})
     if (nch != 2 || generic) bytes += (size_t)nb * (nt > 0 ? nt : 1) * kBins * nch * sizeof(float2);   // spectrum temp
     return bytes;
 }
@@ -653,33 +441,13 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     float* partials = reinterpret_cast<float*>(ws + off);
     off += ((size_t)nb * nt * sizeof(unsigned long long) + 255) / 256 * 256;
     float* scale = reinterpret_cast<float*>(ws + off);
-    off += ((size_t)nb * sizeof(float) + 255) / 256 * 256;
+    off += ((size_t)nb * sizeof(unsigned long long) + 255) / 256 * 256;
 
-    // force_generic: 0 / 4 = fused kernel with 64-lane FFT groups (default, fastest measured), 1 = generic three-kernel path,
-    // 3 = the fused kernel with load / rendezvous / store pipelined inside the CTA (same speed: the kernel is bound by the FFT's
-    // group barriers and shared-memory round trips, not by the exposed latencies),
-    // 2 = experimental warp-worker kernel (one warp per transform, no block barriers; measured slower: the per-clip rendezvous
-    // keeps its independent warps in lock step - profiles/r01_stft_variants.txt)
-    if (force_generic == 3) {      // pipelined kernel (its own frames-per-item granularity); measured equal to the default, profiles/r01_stft_variants.txt
-        static int max_ctas_v3 = -1;
-        if (max_ctas_v3 < 0) {
-            SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
-            int n = 0;
-            SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_pipe_kernel, kThreads, sizeof(PipeSmem)));
-            max_ctas_v3 = n;
-        }
-        const int ipc3 = (nt + kPF - 1) / kPF;
-        const long long resident3 = (long long)max_ctas_v3 * sm_count(), items3 = (long long)nb * ipc3;
-        if (nch == 2 && (nsample % 2 == 0) && resident3 >= ipc3) {
-            SARSSL_CUDA(reset_counters(counters, nb, stream));
-            const int grid = (int)(items3 < resident3 ? items3 : resident3);
-            stft_frontend_pipe_kernel<<<grid, kThreads, sizeof(PipeSmem), stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt,
-                                                                                   ipc3, eps);
-            SARSSL_LAUNCH_CHECK();
-            return SARSSL_OK;
-        }
-    }
-    if (force_generic == 5) {      // independent warps, rendezvous one frame behind
+    // force_generic: 0 = the fastest applicable kernel (independent-warp kernel, else the 64-lane-group kernel, else the generic path),
+    // 1 = generic three-kernel path, 4 = fused kernel with 64-lane FFT groups and a CTA-level clip rendezvous (round 1's default; kept as
+    // the A/B partner of scripts/stft_variants.py), 5 = independent-warp kernel
+    const bool pair_ok = nch == 2 && (nsample % 2 == 0);            // the bulk-TMA staging needs 16-byte aligned clip starts
+    if (pair_ok && (force_generic == 0 || force_generic == 5) && (long long)nb * nt < (1ll << 31)) {
         static int max_ctas_v5 = -1;
         if (max_ctas_v5 < 0) {
             SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Warp2Smem)));
@@ -688,7 +456,7 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
             max_ctas_v5 = n;
         }
         const long long resident5 = (long long)max_ctas_v5 * sm_count(), frames = (long long)nb * nt, ctas = (frames + kW2Warps - 1) / kW2Warps;
-        if (nch == 2 && (nsample % 2 == 0) && max_ctas_v5 > 0 && (ctas <= resident5 || resident5 * kW2Warps >= nt)) {
+        if (max_ctas_v5 > 0 && (ctas <= resident5 || resident5 * kW2Warps >= nt)) {
             static std::atomic<unsigned> g_epoch{0};
             unsigned epoch = ++g_epoch;
             if (epoch == 0) epoch = ++g_epoch;                        // 0 is what a fresh (zeroed) workspace holds
@@ -698,35 +466,20 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
             return SARSSL_OK;
         }
     }
-    static int max_ctas_v1 = -1, max_ctas_v2 = -1;
-    const bool v1 = force_generic != 2;
-    const size_t smem = v1 ? sizeof(FusedSmem) : sizeof(WarpWorkerSmem);
+    static int max_ctas_v1 = -1;
     if (max_ctas_v1 < 0) {
         SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
-        SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpWorkerSmem)));
         int n = 0;
         SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_fused_kernel, kThreads, sizeof(FusedSmem)));
         max_ctas_v1 = n;
-        SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp_kernel, kWarpsPerCta * 32, sizeof(WarpWorkerSmem)));
-        max_ctas_v2 = n;
     }
-    const int max_ctas_per_sm = v1 ? max_ctas_v1 : max_ctas_v2;
-    const long long resident = (long long)max_ctas_per_sm * sm_count();
-    // the bulk-TMA staging needs 16-byte aligned clip starts: nsample * 2 floats * 4 B -> nsample even
-    // (the warp-worker kernel needs every frame of a clip's round resident: resident warps >= nt)
-    const bool fused_ok = force_generic != 1 && nch == 2 && (nsample % 2 == 0) && max_ctas_per_sm > 0 &&
-                          (v1 ? resident >= ipc : resident * kWarpsPerCta >= nt);
+    const long long resident = (long long)max_ctas_v1 * sm_count();
+    const bool fused_ok = force_generic != 1 && pair_ok && max_ctas_v1 > 0 && resident >= ipc;
     SARSSL_CUDA(reset_counters(counters, nb, stream));
     if (fused_ok) {
         const long long items = (long long)nb * ipc;
         const int grid = (int)(items < resident ? items : resident);
-        if (v1)
-            stft_frontend_fused_kernel<<<grid, kThreads, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
-        else {
-            const long long frames = (long long)nb * nt, ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
-            stft_frontend_warp_kernel<<<(int)(ctas < resident ? ctas : resident), kWarpsPerCta * 32, smem, stream>>>(sig, reinterpret_cast<float4*>(patches), partials,
-                                                                                                                  counters, nb, nsample, nt, eps);
-        }
+        stft_frontend_fused_kernel<<<grid, kThreads, sizeof(FusedSmem), stream>>>(sig, reinterpret_cast<float4*>(patches), partials, counters, nb, nsample, nt, ipc, eps);
         SARSSL_LAUNCH_CHECK();
         return SARSSL_OK;
     }

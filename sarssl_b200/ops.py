@@ -55,7 +55,7 @@ def stft_frontend(signal, eps=1e-6, win_len=WIN, hop=HOP, nfft=NFFT, force_gener
     if out is None:
         out = torch.empty((nb * (nch - 1), nt, nfft // 2, 2, 2), dtype=torch.float32, device=signal.device)
     L = lib()
-    variant = int(force_generic)       # 0 / 4: fused kernel (default), 1: generic three-kernel path, 2: experimental warp-worker kernel, 3: fused kernel with intra-CTA pipelining
+    variant = int(force_generic)       # 0: fastest applicable kernel (independent-warp kernel), 1: generic three-kernel path, 4: 64-lane-group kernel, 5: independent-warp kernel
     generic = variant == 1
     for _ in range(2):
         nbytes = L.sarssl_stft_workspace_bytes(nb, nsample, nch, int(generic))

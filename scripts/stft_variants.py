@@ -6,7 +6,7 @@ nb, ns = 1024, 65792
 sig = 0.1 * torch.randn(nb, ns, 2, device='cuda')
 out = torch.empty(nb, 256, 256, 2, 2, device='cuda')
 ref = None
-for variant in (4, 5, 2, 1):
+for variant in (4, 5, 0, 1):
     for _ in range(3): ops.stft_frontend(sig, out=out, force_generic=variant)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -71,26 +71,30 @@ static int check_warp_fft() {
         }
         maxerr = fmax(maxerr, fmax(fabs(Z[l][s].x - X.real()), fabs(Z[l][s].y - X.imag()))); maxref = fmax(maxref, std::abs(X));
     }
-    // mirror algebra used by wfft_split_all: Z[512 - k] location
+    // natural-order Z buffer (wfft_store_z) and the split the kernel does from it: bins k = 1 + lane + 32 r against X_ch0 / X_ch1 computed directly
+    static float2 zb[kWTransFloat2];
+    for (int l = 0; l < 32; ++l) {
+        float2 sgn = l < 16 ? make_float2(1.f, 1.f) : make_float2(-1.f, -1.f);
+        wfft_store_z(v[l], v[l ^ 16], sgn, zb, l);
+    }
     int bad = 0;
-    for (int l = 0; l < 16; ++l) for (int j = 0; j < 8; ++j) {           // h = 0 lanes, bins k = k1 + 16 j
-        int k1 = l, k = k1 + 16 * j, partner = ((16 - k1) & 15) + 16;
-        if (k == 0) continue;
-        int mk = 512 - k;
-        float2 want = Z[(mk & 15) + 16 * (mk >= 256)][(mk % 256) / 16];
-        float2 got = (k1 == 0) ? Z[partner][8 + (8 - j)] : Z[partner][8 + (7 - j)];
-        if (got.x != want.x || got.y != want.y) ++bad;
+    for (int l = 0; l < 32; ++l) for (int s = 0; s < 16; ++s) {
+        int k = (l & 15) + 256 * (l >> 4) + 16 * s;
+        if (zb[wz_pos(k)].x != Z[l][s].x || zb[wz_pos(k)].y != Z[l][s].y) ++bad;
     }
-    for (int l = 16; l < 32; ++l) for (int j = 0; j < 8; ++j) {          // h = 1 lanes, bins of k1' = (16 - p) & 15, s = j + 8
-        int p = l & 15, k1 = (16 - p) & 15, k = k1 + 16 * (j + 8);
-        int mk = 512 - k;
-        float2 want = Z[(mk & 15) + 16 * (mk >= 256)][(mk % 256) / 16];
-        float2 got = (p == 0) ? Z[l][8 - j] : Z[l][7 - j];
-        float2 zz = Z[k1][8 + j];                                        // what the exchange delivers as Z[k]
-        float2 zw = Z[(k & 15) + 16 * (k >= 256)][(k % 256) / 16];
-        if (got.x != want.x || got.y != want.y || zz.x != zw.x || zz.y != zw.y) ++bad;
+    double maxsplit = 0;
+    for (int k = 1; k <= 256; ++k) {
+        float4 o = wfft_split2(zb[wz_pos(k)], zb[wz_pos(512 - k)]);
+        std::complex<double> X0 = 0, X1 = 0;
+        for (int n = 0; n < 512; ++n) {
+            double w = 0.5 - 0.5 * cos(2 * PI * n / 512);
+            std::complex<double> e = std::polar(1.0, -2 * PI * n * k / 512.0);
+            X0 += x0[n] * w * e; X1 += x1[n] * w * e;
+        }
+        maxsplit = fmax(maxsplit, fmax(fmax(fabs(0.5 * o.x - X0.real()), fabs(0.5 * o.z - X0.imag())), fmax(fabs(0.5 * o.y - X1.real()), fabs(0.5 * o.w - X1.imag()))));
     }
-    printf("warp fft: max abs err %.3e (max |Z| %.3f), mirror-map mismatches %d\n", maxerr, maxref, bad);
+    if (maxsplit > 1e-4 * maxref) ++bad;
+    printf("warp fft: max abs err %.3e (max |Z| %.3f), split err %.3e, mismatches %d\n", maxerr, maxref, maxsplit, bad);
     return (maxerr < 1e-4 * maxref && bad == 0) ? 0 : 1;
 }
 struct RunWarpCheck { RunWarpCheck() { if (check_warp_fft()) { fprintf(stderr, "warp fft check FAILED\n"); exit(2); } } } run_warp_check_instance;

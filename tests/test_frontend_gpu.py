@@ -46,12 +46,11 @@ def test_stft_matches_reference_fixture():
     assert (x - xr).abs().max() <= 1e-4 * xr.abs().max()
 
 
-@pytest.mark.parametrize("nb,nsample,nch,generic", [(1, 512, 2, 0), (3, 4352, 2, 0), (3, 4352, 2, 1), (3, 4352, 2, 2), (2, 65792, 2, 0),
-                                                    (2, 65792, 2, 1), (2, 65792, 2, 2), (4, 64000, 2, 0), (4, 64000, 2, 2), (2, 2 * 256 + 511, 2, 0),
-                                                    (2, 4352, 3, 0), (1, 3000, 4, 0), (1, 262400, 2, 0), (3, 10 * 256, 2, 0),
-                                                    (3, 4352, 2, 4), (2, 65792, 2, 4), (4, 64000, 2, 3), (2, 2 * 256 + 511, 2, 3), (1, 512, 2, 3),
-                                                    (5, 7 * 256 + 512, 2, 3), (1, 262400, 2, 4),
-                                                    (1, 512, 2, 5), (3, 4352, 2, 5), (2, 65792, 2, 5), (4, 64000, 2, 5), (1, 262400, 2, 5), (40, 65792, 2, 5)])
+@pytest.mark.parametrize("nb,nsample,nch,generic", [(1, 512, 2, 0), (3, 4352, 2, 0), (3, 4352, 2, 1), (2, 65792, 2, 0), (2, 65792, 2, 1), (4, 64000, 2, 0),
+                                                    (2, 2 * 256 + 511, 2, 0), (2, 4352, 3, 0), (1, 3000, 4, 0), (1, 262400, 2, 0), (3, 10 * 256, 2, 0),
+                                                    (3, 4352, 2, 4), (2, 65792, 2, 4), (4, 64000, 2, 4), (1, 262400, 2, 4), (1, 512, 2, 4), (5, 7 * 256 + 512, 2, 4),
+                                                    (1, 512, 2, 5), (3, 4352, 2, 5), (2, 65792, 2, 5), (4, 64000, 2, 5), (1, 262400, 2, 5), (40, 65792, 2, 5),
+                                                    (5, 7 * 256 + 512, 2, 5), (2, 2 * 256 + 511, 2, 5)])
 def test_frontend_matches_oracle(nb, nsample, nch, generic):
     sig = O.synthetic_waveforms(nb, nsample, nch, seed=17 + nsample % 97)
     want = O.preprocess(sig)                                   # (nb*(nch-1), 2, 256, nt, 2)
