@@ -163,22 +163,25 @@ __global__ void __launch_bounds__(kThreads) stft_frontend_fused_kernel(const flo
 // transpose, no block-level barrier after start-up): frame f = warp_id + r * warps of the clip-major frame list in round r.
 // The per-clip normalisation needs the clip's nt partial sums of |X_ch0| before anything can be written.  A warp that waited for its
 // clip right after publishing would meet the clip's other 256 warps after every frame and the SM would alternate between a compute
-// phase and a store phase (measured: 1.3 ms).  Instead the wait is software-pipelined: a warp transforms frame r, publishes its partial
-// sum, and only THEN finishes frame r - 1, whose spectrum waits in the second Z buffer - by then the clip's other warps have had a
-// whole transform's time to publish, nothing runs in lock step, and loads, butterflies and scaled stores of different warps overlap.
+// phase and a store phase (measured: 1.3 ms).  Instead the wait is software-pipelined kLag rounds deep: a warp transforms frame r,
+// publishes its partial sum, parks the frame's un-scaled bins in TENSOR MEMORY (tcgen05.st: the SM's 256 KB of TMEM are otherwise idle
+// in this kernel; 8 warps x 4 frames x 4 KB = 128 KB per CTA, two CTAs per SM) and only then finishes frame r - kLag (tcgen05.ld, scale,
+// streaming store).  With one round of slack (bins parked in shared memory: all that fits there) the clip's slowest warp still paced
+// all 257 of them (0.454 ms, 85 % of the polls had to wait); three rounds absorb the jitter.
 // The rendezvous carries no fence and no atomic: a partial sum is published as ONE 64-bit store {sum, launch epoch}; a clip is complete
 // when all nt of its words carry this launch's epoch (L2-coherent loads; the words are the only data exchanged, so nothing else has to
-// be ordered).
-// (__threadfence + atomicAdd + ld.acquire cost 48 % of the stall samples of the first version: profiles/r02_stft_frontend.txt.)
+// be ordered).  (__threadfence + atomicAdd + ld.acquire cost 48 % of the stall samples of the first version: profiles/r02_stft_frontend.txt.)
 // One 4 KB input buffer per warp: the next frame's bulk-TMA copy is issued as soon as this frame's samples are in registers.
-// Deadlock-free when every warp is resident and warps >= nt - 1: a warp publishes round r before it waits for round r - 1, and a clip
-// that holds a round r - 1 frame ends before frame (r + 1) * warps.
+// Deadlock-free when every warp is resident and warps >= nt - 1: a warp publishes round r before it waits for an earlier round, and a
+// clip that holds a round r - 1 frame ends before frame (r + 1) * warps.
 constexpr int kW2Warps = 8;
+constexpr int kLag = 3;                           // rounds between publishing a frame and storing it; kLag + 1 TMEM slots per warp
 struct Warp2Smem {
     float2 in[kW2Warps][kFftN];                   // 32 KB   per-warp staged samples (ch0, ch1)
-    float2 tb[kW2Warps][2][kWTransFloat2];        // 66 KB   per-warp transpose buffer, then the frame's Z in bin order; double buffered
+    float2 tb[kW2Warps][kWTransFloat2];           // 33 KB   per-warp transpose buffer, then the frame's Z in bin order
     float2 win2[kFftN];                           // 4 KB    periodic Hann window as (w, w) pairs (one packed multiply per sample pair)
     uint64_t bar[kW2Warps];
+    uint32_t tmem_slot;
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -191,10 +194,34 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// 32 lanes x 32 columns (one frame's 256 bins x float4, lane l holding bins 1 + l + 32 r) <-> tensor memory
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&o)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "f"(o[0].x), "f"(o[0].y), "f"(o[0].z), "f"(o[0].w), "f"(o[1].x), "f"(o[1].y), "f"(o[1].z), "f"(o[1].w), "f"(o[2].x), "f"(o[2].y),
+          "f"(o[2].z), "f"(o[2].w), "f"(o[3].x), "f"(o[3].y), "f"(o[3].z), "f"(o[3].w), "f"(o[4].x), "f"(o[4].y), "f"(o[4].z), "f"(o[4].w), "f"(o[5].x),
+          "f"(o[5].y), "f"(o[5].z), "f"(o[5].w), "f"(o[6].x), "f"(o[6].y), "f"(o[6].z), "f"(o[6].w), "f"(o[7].x), "f"(o[7].y), "f"(o[7].z), "f"(o[7].w)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&o)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(o[0].x), "=f"(o[0].y), "=f"(o[0].z), "=f"(o[0].w), "=f"(o[1].x), "=f"(o[1].y), "=f"(o[1].z), "=f"(o[1].w), "=f"(o[2].x), "=f"(o[2].y),
+          "=f"(o[2].z), "=f"(o[2].w), "=f"(o[3].x), "=f"(o[3].y), "=f"(o[3].z), "=f"(o[3].w), "=f"(o[4].x), "=f"(o[4].y), "=f"(o[4].z), "=f"(o[4].w),
+          "=f"(o[5].x), "=f"(o[5].y), "=f"(o[5].z), "=f"(o[5].w), "=f"(o[6].x), "=f"(o[6].y), "=f"(o[6].z), "=f"(o[6].w), "=f"(o[7].x), "=f"(o[7].y),
+          "=f"(o[7].z), "=f"(o[7].w)
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(const float* __restrict__ sig, float4* __restrict__ out,
-                                                                              unsigned long long* partials, unsigned* counters, unsigned epoch, int nb, long long nsample, int nt,
-                                                                              float eps) {
+                                                                              unsigned long long* partials, unsigned* counters, unsigned epoch, int nb,
+                                                                              long long nsample, int nt, float eps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Warp2Smem& sm = *reinterpret_cast<Warp2Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -208,23 +235,30 @@ __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(c
         mbar_init(&sm.bar[warp], 1);
         mbar_fence_init();
     }
+    if (warp == 0) {                                                 // half of the SM's tensor memory (two CTAs per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // a warp reaches the 32 TMEM lanes of its quarter (warp % 4); the two warps of a quarter split the CTA's 256 columns
+    const uint32_t tm = sm.tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 128;
     const unsigned total = (unsigned)nb * (unsigned)nt, unt = (unsigned)nt;
     const unsigned gw = blockIdx.x * kW2Warps + warp, G = gridDim.x * kW2Warps;
     const unsigned db = G / unt, dt = G - db * unt;                  // frame f + G = (b + db, t + dt) with one carry
     const float inv_bins = 1.0f / (float)((long long)kBins * nt);
     const float2 sgn = lane < 16 ? make_float2(1.f, 1.f) : make_float2(-1.f, -1.f);
     float2* in = sm.in[warp];
+    float2* tb = sm.tb[warp];
     auto issue = [&](unsigned b, unsigned t) {
         if (lane == 0) {
             mbar_expect_tx(&sm.bar[warp], kFftN * sizeof(float2));
             tma_bulk_g2s(in, sig + ((size_t)b * nsample + (size_t)t * kHop) * 2, kFftN * sizeof(float2), &sm.bar[warp]);
         }
     };
-    // scale and store the frame whose Z sits in `zb`, once its clip is complete
-    auto finish = [&](unsigned b, unsigned t, const float2* zb) {
-        // (a per-clip {scale, epoch} word published by the first finisher was tried: the clip's 257 warps arrive together, all miss it, and
-        //  their loads of the one hot word serialise on a single L2 slice - 3.5 ms instead of 0.47)
+    // scale and store the frame parked in TMEM slot `slot`, once its clip is complete
+    auto finish = [&](unsigned b, unsigned t, int slot) {
         const unsigned long long* pp = partials + (size_t)b * unt;
         float s;
         for (unsigned spins = 0;; ++spins) {
@@ -240,23 +274,22 @@ __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(c
             if (spins > (1u << 22)) { if (lane == 0) atomicExch(&counters[1], 1u); break; }      // never expected; report instead of hanging
         }
         s = warp_sum(s);
-        // the bins below are 2 X and the partial sums 2 sum|X_ch0| (the split's factor 1/2 is folded in here): out = 2 X * scale
+        // the parked bins are 2 X and the partial sums 2 sum|X_ch0| (the split's factor 1/2 is folded in here): out = 2 X * scale
         const float scale = 0.5f / (0.5f * s * inv_bins + eps);
         const float2 sc2 = make_float2(scale, scale);
+        float4 o[8];
+        tmem_ld32(tm + (uint32_t)slot * 32, o);
         float4* dst = out + ((size_t)b * unt + t) * kHop + lane;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int k = 1 + lane + 32 * r;
-            const float4 o = wfft_split2(zb[wz_pos(k)], zb[wz_pos(512 - k)]);
-            const float2 lo = cscale2(make_float2(o.x, o.y), sc2), hi = cscale2(make_float2(o.z, o.w), sc2);
+            const float2 lo = cscale2(make_float2(o[r].x, o[r].y), sc2), hi = cscale2(make_float2(o[r].z, o[r].w), sc2);
             st_stream_f4(dst + 32 * r, make_float4(lo.x, lo.y, hi.x, hi.y));
         }
     };
     uint32_t ph = 0;
-    int cur = 0;
     unsigned b = gw / unt, t = gw - b * unt;
-    unsigned pb = 0, pt = 0;
-    bool have_prev = false;                                          // published, not yet stored
+    unsigned hb = b, ht = t;                                         // oldest parked frame (frames of one warp advance by (db, dt) per round)
+    int nheld = 0, wslot = 0, rslot = 0;
     if (gw < total) issue(b, t);
     for (unsigned f = gw; f < total; f += G) {
         mbar_wait(&sm.bar[warp], ph);
@@ -268,35 +301,52 @@ __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(c
         unsigned nb_ = b + db, nt_ = t + dt;
         if (nt_ >= unt) { nt_ -= unt; ++nb_; }
         if (f + G < total) issue(nb_, nt_);
-        float2* tb = sm.tb[warp][cur];
         wfft_stage1(v, lc, tb, lane);
         __syncwarp();
         wfft_stage2(v, tb, lane);
-        float2 o[16];
+        {
+            float2 o[16];
 #pragma unroll
-        for (int s = 0; s < 16; ++s) o[s] = make_float2(__shfl_xor_sync(0xffffffffu, v[s].x, 16), __shfl_xor_sync(0xffffffffu, v[s].y, 16));
-        wfft_store_z(v, o, sgn, tb, lane);                           // (the shuffles above ordered every lane's transpose reads before this)
+            for (int s = 0; s < 16; ++s) o[s] = make_float2(__shfl_xor_sync(0xffffffffu, v[s].x, 16), __shfl_xor_sync(0xffffffffu, v[s].y, 16));
+            wfft_store_z(v, o, sgn, tb, lane);                       // (the shuffles above ordered every lane's transpose reads before this)
+        }
         __syncwarp();
+        float4 o[8];
         float part = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int k = 1 + lane + 32 * r;
-            const float2 z = tb[wz_pos(k)], p = tb[wz_pos(512 - k)];
-            const float a = z.x + p.x, c = z.y - p.y;
-            part += sqrt_approx(a * a + c * c);
+            o[r] = wfft_split2(tb[wz_pos(k)], tb[wz_pos(512 - k)]);
+            part += sqrt_approx(o[r].x * o[r].x + o[r].z * o[r].z);
         }
         {   // bin 0 (DC) is dropped from the patches but counts in the mean magnitude: X_ch0[0] = Re Z[0]
             const float z0 = tb[0].x;
             if (lane == 0) part += 2.f * fabsf(z0);
         }
+        __syncwarp();                                                // the Z buffer is read: the next frame's transpose may overwrite it
         part = warp_sum(part);
         if (lane == 0) __stcg(&partials[(size_t)b * unt + t], ((unsigned long long)epoch << 32) | __float_as_uint(part));
-        if (have_prev) finish(pb, pt, sm.tb[warp][cur ^ 1]);
-        pb = b; pt = t; have_prev = true;
+        tmem_st32(tm + (uint32_t)wslot * 32, o);
+        wslot = (wslot + 1) & kLag;
+        if (++nheld > kLag) {
+            finish(hb, ht, rslot);
+            rslot = (rslot + 1) & kLag;
+            --nheld;
+            hb += db; ht += dt;
+            if (ht >= unt) { ht -= unt; ++hb; }
+        }
         b = nb_; t = nt_;
-        cur ^= 1;
     }
-    if (have_prev) finish(pb, pt, sm.tb[warp][cur ^ 1]);
+    while (nheld > 0) {
+        finish(hb, ht, rslot);
+        rslot = (rslot + 1) & kLag;
+        --nheld;
+        hb += db; ht += dt;
+        if (ht >= unt) { ht -= unt; ++hb; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_slot), "r"(256) : "memory");
 }
 
 // ---------------- generic path ----------------
@@ -451,9 +501,22 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
         static int max_ctas_v5 = -1;
         if (max_ctas_v5 < 0) {
             SARSSL_CUDA(cudaFuncSetAttribute(stft_frontend_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Warp2Smem)));
-            int n = 0;
-            SARSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_frontend_warp2_kernel, kW2Warps * 32, sizeof(Warp2Smem)));
-            max_ctas_v5 = n;
+            // Residency from the kernel's own resource use: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel (measured on
+            // the B200s of this pool, CUDA 12.9; ncu's launch__occupancy_limit_{registers,shared_mem} both say 2 and two CTAs per SM do run: 0.39 ms
+            // against 0.54 ms with one).  If fewer CTAs than assumed were ever resident the rendezvous would time out and raise the sticky error flag.
+            cudaFuncAttributes fa;
+            SARSSL_CUDA(cudaFuncGetAttributes(&fa, stft_frontend_warp2_kernel));
+            int dev = 0, regs_sm = 0, smem_sm = 0, thr_sm = 0;
+            SARSSL_CUDA(cudaGetDevice(&dev));
+            SARSSL_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+            SARSSL_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+            SARSSL_CUDA(cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+            const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * kW2Warps * 32;
+            const int smem_cta = (int)sizeof(Warp2Smem) + (int)fa.sharedSizeBytes + 1024;          // + the driver's 1 KB per CTA
+            int n = regs_sm / regs_cta;
+            if (smem_sm / smem_cta < n) n = smem_sm / smem_cta;
+            if (thr_sm / (kW2Warps * 32) < n) n = thr_sm / (kW2Warps * 32);
+            max_ctas_v5 = n < 2 ? n : 2;                              // each CTA takes half of the SM's tensor memory
         }
         const long long resident5 = (long long)max_ctas_v5 * sm_count(), frames = (long long)nb * nt, ctas = (frames + kW2Warps - 1) / kW2Warps;
         if (max_ctas_v5 > 0 && (ctas <= resident5 || resident5 * kW2Warps >= nt)) {
