@@ -179,6 +179,47 @@ def run_frozen_case(name, nb, nt, sig_seed, sd_seed, mask_seed):
     print(name, "loss", out["loss"], "grads for", sorted(k[10:] for k in out if k.startswith("grad_norm/")))
 
 
+def run_multich_case(name, nb, nt, nmic_pair, task, sig_seed, sd_seed):
+    """SARSSL_MultiCH (model.py:793-821): forward + an MSE step on the head output; fixtures hold pred, embed and gradient samples."""
+    rm, rl, rops, ru = ref_shim.load_reference()
+    factor = nmic_pair if task == "TDOA" else 1
+    net = rm.SARSSL_MultiCH(sig_shape=(256, nt, 2, 2), nmic_pair=nmic_pair, task=task, device="cpu")
+    net.load_state_dict(O.synthetic_state_dict(sd_seed, pretrain=False, head="", prefix="model_sch.", nmic_pair=nmic_pair, factor=factor))
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    net.train()
+    sig = O.synthetic_waveforms(nb * nmic_pair, (nt + 1) * 256, 2, seed=sig_seed)
+    x = O.preprocess(sig)
+    pred, emb = net(x)
+    tar = torch.linspace(-1.0, 1.0, nb * factor).reshape(nb, factor)
+    loss = torch.nn.functional.mse_loss(pred, tar)
+    loss.backward()
+    out = {"nb": nb, "nt": nt, "nmic_pair": nmic_pair, "factor": factor, "sig_seed": sig_seed, "sd_seed": sd_seed, "pred": pred.detach().numpy(),
+           "embed": emb.detach().numpy(), "tar": tar.numpy(), "loss": float(loss), "keys": np.array(list(net.state_dict().keys()))}
+    for k, p in net.named_parameters():
+        g = (p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+        out["grad_rand/" + k] = g.numpy()[O.fixture_sample_idx(k, g.numel(), 256)].astype(np.float32)
+        out["grad_norm/" + k] = float(g.norm())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "pred", out["pred"].ravel()[:4])
+
+
+def run_mcconformer_case(name, nb, nt, sig_seed, sd_seed):
+    """MCConformer (model.py:824-912) in eval mode: data_pred of the un-masked input."""
+    rm, rl, rops, ru = ref_shim.load_reference()
+    net = rm.MCConformer(sig_shape=[256, nt, 2, 2], patch_shape=(256, 1), spec_model=["cnn", "conformer"], spat_model=["cnn", "conformer"],
+                         dembed={"spec": 512, "spat": 256})
+    net.load_state_dict(O.synthetic_state_dict(sd_seed))
+    net.eval()
+    x = O.preprocess(O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=sig_seed))
+    with torch.no_grad():
+        y = net(x)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), nb=nb, nt=nt, sig_seed=sig_seed, sd_seed=sd_seed, data_pred=y.numpy(),
+                        keys=np.array(list(net.state_dict().keys())))
+    print(name, "data_pred", tuple(y.shape), float(y.norm()))
+
+
 def mask_streams():
     """Known-answer vectors for the mask RNG: python `random` (CPython MT19937) under the reference's seeds."""
     out = {}
@@ -212,3 +253,5 @@ if __name__ == "__main__":
     run_downstream_case("downstream_nt16_b4", nb=4, nt=16, embed="spec_spat", sig_seed=8, sd_seed=9)
     run_downstream_case("downstream_spat_nt64_b2", nb=2, nt=64, embed="spat", sig_seed=10, sd_seed=9)
     run_frozen_case("frozen_nt16_b3", nb=3, nt=16, sig_seed=12, sd_seed=13, mask_seed=21)
+    run_multich_case("multich_nt16_b2x3", nb=2, nt=16, nmic_pair=3, task="TDOA", sig_seed=14, sd_seed=15)
+    run_mcconformer_case("mcconformer_nt16_b2", nb=2, nt=16, sig_seed=18, sd_seed=19)

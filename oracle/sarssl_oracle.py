@@ -321,6 +321,34 @@ def downstream_forward(x, sd, embed_use="spec_spat", training=True, dropout_p=0.
     return pred, pooled
 
 
+def multich_forward(x, sd, nmic_pair, training=True, dropout_p=0.0):
+    """SARSSL_MultiCH.forward (model.py:793-821): the spatial encoder's time-mean embedding of every microphone pair (the inner
+    SARSSL(pretrain=False, downstream_head='', downstream_embed='spat') runs both encoders, model.py:676-678), the pairs of one item
+    concatenated, LayerNorm + Linear + ReLU + Linear.  x (nb*nmic_pair, 2, nf, nt, 2) -> (pred (nb, factor), embed (nb, nmic_pair*256))."""
+    inner = {k[len("model_sch."):]: v for k, v in sd.items() if k.startswith("model_sch.")}
+    n, nmic, nf, nt, _ = x.shape
+    bn = BNState(training)
+    drop = (lambda t: F.dropout(t, dropout_p, True)) if (training and dropout_p > 0) else (lambda t: t)
+    tokens = x.permute(0, 3, 2, 4, 1).reshape(n, nt, -1)
+    embed_encoder(tokens, inner, "spec_encoder", SPEC_LAYERS, NHEAD, bn, drop)            # run for its BatchNorm side effects only, like the reference
+    e = embed_encoder(tokens, inner, "spat_encoder", SPAT_LAYERS, NHEAD, bn, drop) + 0.0
+    emb = e.mean(dim=1).reshape(-1, nmic_pair * e.shape[-1])
+    h = F.relu(_lin(_ln(emb, sd, "head_mch.0"), sd, "head_mch.1"))
+    return _lin(h, sd, "head_mch.3"), emb
+
+
+def mcconformer_forward(x, sd, training=False):
+    """MCConformer.forward (model.py:824-912, both encoders): un-masked input -> encoders -> decoder -> PatchRecover.
+    x (nb, 2, nf, nt, 2) -> data_pred (nb, nf, nt, 2, 2)."""
+    nb, nmic, nf, nt, _ = x.shape
+    bn = BNState(training)
+    tokens = x.permute(0, 3, 2, 4, 1).reshape(nb, nt, -1)
+    e = torch.cat([embed_encoder(tokens, sd, "spec_encoder", SPEC_LAYERS, NHEAD, bn, lambda t: t),
+                   embed_encoder(tokens, sd, "spat_encoder", SPAT_LAYERS, NHEAD, bn, lambda t: t)], dim=2)
+    pred = _lin(F.relu(_lin(e, sd, "decoder.proj.0")), sd, "decoder.proj.2").view(nb, nt, nf, 2, nmic)
+    return pred.permute(0, 2, 1, 3, 4)
+
+
 def masked_loss(pred, vec, pidx, cidx):
     """model.py:585-592,721-747.  pred/vec (nb, nt, nf, 2, nmic).
     loss = mean over (item, masked frame, bin, re/im) of (pred - target)^2 on the masked channel,
@@ -349,7 +377,7 @@ def positional_table(d_model, max_len=10000):
     return pe.unsqueeze(0)
 
 
-def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False):
+def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False, head="mlp", prefix="", nmic_pair=0, factor=1):
     """[(key, shape, kind)] for the 214 state_dict entries of SARSSL(pretrain=True).
     frozen=True: SARSSL(pretrain=False, pretrain_frozen_encoder=True) - three decoders instead of one (model.py:470-481; the spatial
     decoder is built with the SPECTRAL width, as the reference does).
@@ -408,18 +436,23 @@ def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False):
         decoder("spec_spat_decoder", 768)
         decoder("spec_decoder", 512)
         decoder("spat_decoder", 512)
-    else:       # downstream head (model.py:495-500)
+    elif head == "mlp":       # downstream head (model.py:495-500)
         out.extend([("mlp_head.0.weight", (dembed_ds,), "g"), ("mlp_head.0.bias", (dembed_ds,), "b"),
                     ("mlp_head.1.weight", (1, dembed_ds), "w"), ("mlp_head.1.bias", (1,), "b")])
+    out = [(prefix + k, shp, kind) for k, shp, kind in out]
+    if nmic_pair:             # SARSSL_MultiCH.head_mch (model.py:807-812): LayerNorm, Linear, ReLU, Linear over the concatenated pair embeddings
+        d = 256 * nmic_pair
+        out.extend([("head_mch.0.weight", (d,), "g"), ("head_mch.0.bias", (d,), "b"), ("head_mch.1.weight", (d, d), "w"), ("head_mch.1.bias", (d,), "b"),
+                    ("head_mch.3.weight", (factor, d), "w"), ("head_mch.3.bias", (factor,), "b")])
     return out
 
 
-def synthetic_state_dict(seed=7, nf=256, pretrain=True, dembed_ds=768, frozen=False):
+def synthetic_state_dict(seed=7, nf=256, pretrain=True, dembed_ds=768, frozen=False, **spec_kw):
     """Seeded, non-degenerate weights (non-zero biases, non-unit gains) for parity tests.  Generated
     key by key from one torch.Generator so reference, oracle and CUDA path can all be loaded with it."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for key, shape, kind in state_dict_spec(nf, pretrain, dembed_ds, frozen):
+    for key, shape, kind in state_dict_spec(nf, pretrain, dembed_ds, frozen, **spec_kw):
         if kind == "w":
             fan_in = 1
             for s in shape[1:]:

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(kW2Warps * 32, 2) stft_frontend_warp2_kernel(c
             float2 o[16];
 #pragma unroll
             for (int s = 0; s < 16; ++s) o[s] = make_float2(__shfl_xor_sync(0xffffffffu, v[s].x, 16), __shfl_xor_sync(0xffffffffu, v[s].y, 16));
-            wfft_store_z(v, o, sgn, tb, lane);                       // (the shuffles above ordered every lane's transpose reads before this)
+            __syncwarp();                                            // every lane's transpose reads are done before the buffer is re-written
+            wfft_store_z(v, o, sgn, tb, lane);
         }
         __syncwarp();
         float4 o[8];

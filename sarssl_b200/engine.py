@@ -92,9 +92,11 @@ class Engine:
         return self._pe_cache[ck]
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, patches, flag, ch, nmasked, training, want_grad, frozen=False):
+    def forward(self, patches, flag, ch, nmasked, training, want_grad, frozen=False, plain=False):
         """patches (B, T, F, 2, 2) f32; flag (B, T) uint8; ch (B,) int32.  Returns (out2 = [loss, diff], pred (B*T, F*4), saved).
-        frozen: the pretrain_frozen_encoder branch (model.py:603-666) - spectral input mode 4, `spec_spat_decoder` instead of `decoder`."""
+        frozen: the pretrain_frozen_encoder branch (model.py:603-666) - spectral input mode 4, `spec_spat_decoder` instead of `decoder`.
+        plain: MCConformer.forward (model.py:890-912) - un-masked input into both encoders, decoder, no masks and no loss (out2 is None;
+        backward() then takes the gradient of the prediction from the caller)."""
         k, st = self.k, self.store
         B, T, F = patches.shape[:3]
         M, P = B * T, B * T * F
@@ -111,6 +113,8 @@ class Engine:
         for enc, D, nl, mode, col in ENCODERS:
             if frozen and mode == 1:
                 mode = 4
+            if plain:
+                mode = 3
             e = self._stem_fwd(enc, D, mode, patches, flag, ch, B, T, F, training, enc_sv)
             for l in range(nl):
                 last = l == nl - 1
@@ -121,6 +125,10 @@ class Engine:
         k.linear(cat, self.w(dec + ".proj.0.weight"), hdec, M, dff, SPEC_D + SPAT_D, bias=st.p(dec + ".proj.0.bias"), act=ACT_RELU)
         pred = k.empty(M, 4 * F)
         k.linear(hdec, self.w(dec + ".proj.2.weight"), pred, M, 4 * F, dff, bias=st.p(dec + ".proj.2.bias"))
+        if plain:
+            if want_grad:
+                sv.update(cat=cat, hdec=hdec, dpred=None, plain=True)
+            return None, pred, sv
         # masked reconstruction loss (+ dpred in the same launch)                                  model.py:585-592,721-747
         from . import ops
         out2, dpred = ops.masked_loss(pred.view(B, T, 4 * F), patches, flag, ch, nmasked, want_grad=want_grad)
@@ -264,9 +272,10 @@ class Engine:
         return y
 
     # ------------------------------------------------------------------------------------------------ downstream branch
-    def forward_downstream(self, patches, embed_use, training, want_grad):
-        """model.py:667-719 (pretrain=False, head 'mlp', dlabel 1): both encoders on the UN-masked input, concatenate, mean over time,
-        LayerNorm + Linear(dembed, 1).  Returns (pred (B, 1) fp32, pooled (B, dembed) fp32, saved)."""
+    def forward_downstream(self, patches, embed_use, training, want_grad, head="mlp"):
+        """model.py:667-719 (pretrain=False): both encoders on the UN-masked input, concatenate, mean over time, then the head:
+        'mlp' = LayerNorm + Linear(dembed, 1) (dlabel 1), '' = none, an integer nmic_pair = SARSSL_MultiCH.head_mch (model.py:793-821).
+        Returns (pred fp32, pooled (B, dembed) fp32, saved)."""
         k, k32, st = self.k, self.k32, self.store
         B, T, F = patches.shape[:3]
         M = B * T
@@ -285,29 +294,70 @@ class Engine:
         col, Dd = {"spec_spat": (0, Dc), "spec": (0, SPEC_D), "spat": (SPEC_D, SPAT_D)}[embed_use]
         pooled = torch.empty(B, Dd, dtype=torch.float32, device=self.dev)
         k.mean_pool_fwd(cat, Dc, pooled, B, T, Dd, x_off=col)
-        hn, mean, rstd = torch.empty_like(pooled), torch.empty(B, dtype=torch.float32, device=self.dev), torch.empty(B, dtype=torch.float32, device=self.dev)
-        k32.layernorm_fwd(pooled, Dd, st.p("mlp_head.0.weight"), st.p("mlp_head.0.bias"), hn, Dd, mean, rstd, B, Dd)
-        pred = torch.empty(B, 1, dtype=torch.float32, device=self.dev)
         k32.use_tc = False
-        k32.linear(hn, st.p("mlp_head.1.weight"), pred, B, 1, Dd, bias=st.p("mlp_head.1.bias"))
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        if head == "":                               # SARSSL(downstream_head=''): the pooled embedding is the prediction   model.py:705-706
+            pred, hs = pooled, {}
+        elif head == "mlp":                          # LayerNorm + Linear(dembed, 1)                                       model.py:495-500
+            hn, mean, rstd = torch.empty_like(pooled), torch.empty(B, **f32), torch.empty(B, **f32)
+            k32.layernorm_fwd(pooled, Dd, st.p("mlp_head.0.weight"), st.p("mlp_head.0.bias"), hn, Dd, mean, rstd, B, Dd)
+            pred = torch.empty(B, 1, **f32)
+            k32.linear(hn, st.p("mlp_head.1.weight"), pred, B, 1, Dd, bias=st.p("mlp_head.1.bias"))
+            hs = dict(hn=hn, hmean=mean, hrstd=rstd)
+        else:                                        # SARSSL_MultiCH.head_mch over the pairs of an item                    model.py:807-820
+            P = int(head)
+            if B % P:
+                raise _lib.SarsslError(f"SARSSL_MultiCH: batch of {B} clips is not a multiple of nmic_pair = {P}")
+            nbm, Dh = B // P, P * Dd
+            emb = pooled.view(nbm, Dh)
+            factor = st.shapes["head_mch.3.weight"][0]
+            hn, mean, rstd = torch.empty_like(emb), torch.empty(nbm, **f32), torch.empty(nbm, **f32)
+            k32.layernorm_fwd(emb, Dh, st.p("head_mch.0.weight"), st.p("head_mch.0.bias"), hn, Dh, mean, rstd, nbm, Dh)
+            h1 = torch.empty(nbm, Dh, **f32)
+            k32.linear(hn, st.p("head_mch.1.weight"), h1, nbm, Dh, Dh, bias=st.p("head_mch.1.bias"), act=ACT_RELU)
+            pred = torch.empty(nbm, factor, **f32)
+            k32.linear(h1, st.p("head_mch.3.weight"), pred, nbm, factor, Dh, bias=st.p("head_mch.3.bias"))
+            hs = dict(hn=hn, hmean=mean, hrstd=rstd, h1=h1, nbm=nbm, Dh=Dh, factor=factor)
         if want_grad:
-            sv.update(pooled=pooled, hn=hn, hmean=mean, hrstd=rstd, col=col, Dd=Dd)
+            sv.update(pooled=pooled, col=col, Dd=Dd, head=head, **hs)
         return pred, pooled, sv
 
     def backward_downstream(self, sv, dpred, on_ready=None):
-        """dpred (B, 1) fp32 = d loss / d pred."""
+        """dpred fp32 = d loss / d pred ((B, 1) for the 'mlp' head, (B, dembed) without a head, (B / nmic_pair, factor) for head_mch)."""
         k, k32, st = self.k, self.k32, self.store
         B, T, F, col, Dd = sv["B"], sv["T"], sv["F"], sv["col"], sv["Dd"]
         M, Dc = B * T, SPEC_D + SPAT_D
         k32.use_tc = False
-        k32.linear_wgrad(dpred, sv["hn"], st.g("mlp_head.1.weight"), B, 1, Dd)
-        # bias gradient = sum_b dpred[b]: a 1 x 1 GEMM over K = B against a stride-0 "ones" operand
-        k32.gemm(dpred, torch.ones(1, 1, device=self.dev), st.g("mlp_head.1.bias").view(1, 1), 1, 1, B, (1, 1), (1, 0), 1, accumulate=True)
-        dhn = torch.empty(B, Dd, dtype=torch.float32, device=self.dev)
-        k32.linear_dgrad(dpred, st.p("mlp_head.1.weight"), dhn, B, 1, Dd)
-        dpool = torch.empty_like(dhn)
-        k32.layernorm_bwd(dhn, Dd, sv["pooled"], Dd, sv["hmean"], sv["hrstd"], st.p("mlp_head.0.weight"), None, dpool, st.g("mlp_head.0.weight"),
-                          st.g("mlp_head.0.bias"), B, Dd)
+        head = sv["head"]
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        if head == "":
+            dpool = dpred.reshape(B, Dd).contiguous()
+        elif head == "mlp":
+            k32.linear_wgrad(dpred, sv["hn"], st.g("mlp_head.1.weight"), B, 1, Dd)
+            # bias gradient = sum_b dpred[b]: a 1 x 1 GEMM over K = B against a stride-0 "ones" operand
+            k32.gemm(dpred, torch.ones(1, 1, device=self.dev), st.g("mlp_head.1.bias").view(1, 1), 1, 1, B, (1, 1), (1, 0), 1, accumulate=True)
+            dhn = torch.empty(B, Dd, **f32)
+            k32.linear_dgrad(dpred, st.p("mlp_head.1.weight"), dhn, B, 1, Dd)
+            dpool = torch.empty_like(dhn)
+            k32.layernorm_bwd(dhn, Dd, sv["pooled"], Dd, sv["hmean"], sv["hrstd"], st.p("mlp_head.0.weight"), None, dpool, st.g("mlp_head.0.weight"),
+                              st.g("mlp_head.0.bias"), B, Dd)
+        else:
+            nbm, Dh, factor = sv["nbm"], sv["Dh"], sv["factor"]
+            ones = torch.ones(1, 1, device=self.dev)
+            dpred = dpred.reshape(nbm, factor).contiguous()
+            k32.linear_wgrad(dpred, sv["h1"], st.g("head_mch.3.weight"), nbm, factor, Dh)
+            k32.gemm(dpred, ones, st.g("head_mch.3.bias").view(factor, 1), factor, 1, nbm, (1, factor), (1, 0), 1, accumulate=True)     # column sums of dpred
+            dh1 = torch.empty(nbm, Dh, **f32)
+            k32.linear_dgrad(dpred, st.p("head_mch.3.weight"), dh1, nbm, factor, Dh)
+            k32.relu_bwd(dh1, sv["h1"], dh1, nbm * Dh)
+            k32.linear_wgrad(dh1, sv["hn"], st.g("head_mch.1.weight"), nbm, Dh, Dh)
+            k32.gemm(dh1, ones, st.g("head_mch.1.bias").view(Dh, 1), Dh, 1, nbm, (1, Dh), (1, 0), 1, accumulate=True)
+            dhn = torch.empty(nbm, Dh, **f32)
+            k32.linear_dgrad(dh1, st.p("head_mch.1.weight"), dhn, nbm, Dh, Dh)
+            dpool = torch.empty(nbm, Dh, **f32)
+            k32.layernorm_bwd(dhn, Dh, sv["pooled"].view(nbm, Dh), Dh, sv["hmean"], sv["hrstd"], st.p("head_mch.0.weight"), None, dpool,
+                              st.g("head_mch.0.weight"), st.g("head_mch.0.bias"), nbm, Dh)
+            dpool = dpool.view(B, Dd)
         dcat = k.empty(M, Dc)
         k.mean_pool_bwd(dpool, dcat, Dc, B, T, Dd, dx_off=col)
         ready = on_ready if on_ready is not None else (lambda name: None)
@@ -334,7 +384,7 @@ class Engine:
         B, T, F = sv["B"], sv["T"], sv["F"]
         M = B * T
         dpred = sv["dpred"]
-        if gscale is not None:
+        if gscale is not None and not sv.get("plain"):
             _lib.check(_lib.lib().sarssl_scale_masked_rows(_lib.ptr(dpred), _lib.dtype_code(dpred), _lib.ptr(sv["flag"]), _lib.ptr(gscale), B, T, F,
                                                            k.stream), "scale_masked_rows")
         dec = sv["dec"]
@@ -360,6 +410,8 @@ class Engine:
         for enc, D, nl, mode, col in ENCODERS:
             if sv["frozen"] and mode == 1:
                 mode = 4
+            if sv.get("plain"):
+                mode = 3
             d = None
             for l in reversed(range(nl)):
                 last = l == nl - 1

@@ -70,13 +70,37 @@ class _PretrainFn(torch.autograd.Function):
         return None, None, None, None, None, None
 
 
+class _PlainFn(torch.autograd.Function):
+    """MCConformer: encoders + decoder on the un-masked input; the caller's loss supplies the gradient of the prediction."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, patches, want):
+        _, pred, saved = model._engine().forward(patches, None, None, 0, training=model.training, want_grad=want, plain=True)
+        ctx.model, ctx.saved = model, saved
+        return pred.float() if pred.dtype != torch.float32 else pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        if ctx.saved is None:
+            raise _lib.SarsslError("backward() through a forward that ran without gradient tracking (eval() or no_grad())")
+        ctx.model.store.reattach_grads()
+        ctx.saved["dpred"] = g_pred.to(ctx.model.compute_dtype).contiguous()
+        sync = getattr(ctx.model, "grad_sync", None)
+        ctx.model.engine.backward(ctx.saved, gscale=None, on_ready=sync.bucket_ready if sync is not None else None)
+        ctx.saved = None
+        return None, None, None, None
+
+
 class _DownstreamFn(torch.autograd.Function):
     """One autograd node for the downstream branch: (pred, pooled embedding); the loss is formed outside (Learner.loss)."""
 
     @staticmethod
     def forward(ctx, anchor, model, patches, want):
-        pred, pooled, saved = model._engine().forward_downstream(patches, model.embed_use4ds, training=model.training, want_grad=want)
+        pred, pooled, saved = model._engine().forward_downstream(patches, model.embed_use4ds, training=model.training, want_grad=want,
+                                                                 head=model.downstream_head)
         ctx.model, ctx.saved = model, saved
+        if pred is pooled:                       # head '': the embedding is the prediction (model.py:705-706); hand out two tensors
+            pred = pooled.clone()
         ctx.mark_non_differentiable(pooled)
         return pred, pooled
 
@@ -116,15 +140,15 @@ class SARSSL(nn.Module):
 
     def __init__(self, sig_shape=[256, 256, 2, 2], patch_shape=(256, 1), patch_mode="T", nmasked_patch=128 * 1, pretrain=True, use_cls=False,
                  downstream_token="all", downstream_head="mlp", downstream_embed="spec_spat", downstream_dlabel=1, device="cpu",
-                 pretrain_frozen_encoder=False):
+                 pretrain_frozen_encoder=False, _nmic_pair=0, _factor=1, _tree_prefix=""):
         super().__init__()
         nf, nt, nreim, nmic = sig_shape
         if use_cls:
             raise _lib.SarsslError("sarssl_b200.SARSSL implements pretrain=True, pretrain_frozen_encoder=True and the downstream branch; use_cls is not built")
         pretrain_frozen_encoder = bool(pretrain_frozen_encoder) and not pretrain            # model.py:463,469: `pretrain` wins
-        if not pretrain and not pretrain_frozen_encoder and (downstream_head != "mlp" or downstream_dlabel != 1 or downstream_token != "all" or
-                             downstream_embed not in ("spec_spat", "spec", "spat")):
-            raise _lib.SarsslError("downstream branch: only head 'mlp', dlabel 1, token 'all', embed in {spec_spat, spec, spat} (the shipped defaults)")
+        if not pretrain and not pretrain_frozen_encoder and (downstream_head not in ("mlp", "") or downstream_dlabel != 1 or downstream_token != "all" or
+                                                             downstream_embed not in ("spec_spat", "spec", "spat")):
+            raise _lib.SarsslError("downstream branch: heads 'mlp' / '' (none), dlabel 1, token 'all', embed in {spec_spat, spec, spat}")
         if tuple(patch_shape) != (nf, 1) or patch_mode != "T" or nreim != 2 or nmic != 2:
             raise _lib.SarsslError("only frame patches (patch_shape == (nf, 1), patch_mode 'T') of 2-microphone re/im spectrograms are on the hot path")
         npatch = nt
@@ -135,7 +159,9 @@ class SARSSL(nn.Module):
         self.device = torch.device(device if str(device) != "cpu" else ("cuda" if torch.cuda.is_available() else "cpu"))
         self.embed_use4ds = downstream_embed
         dembed_ds = {"spec_spat": 768, "spec": 512, "spat": 256}.get(downstream_embed, 768)
-        self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds, frozen=pretrain_frozen_encoder)
+        self.downstream_head = _nmic_pair if _nmic_pair else downstream_head         # an integer selects SARSSL_MultiCH.head_mch in the engine
+        self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds, frozen=pretrain_frozen_encoder,
+                                head=downstream_head, nmic_pair=_nmic_pair, factor=_factor, tree_prefix=_tree_prefix)
         # the rest are plain attributes (not sub-modules) so that state_dict() holds exactly the reference's 214 entries
         object.__setattr__(self, "patch_split", PatchSplit(patch_shape=patch_shape, f_first=False))
         object.__setattr__(self, "patch_recover", PatchRecover(output_shape=(nf, nt), patch_shape=patch_shape, f_first=False))
@@ -198,3 +224,44 @@ class SARSSL(nn.Module):
         if self.pretrain_frozen_encoder:
             return loss, loss * 0.0, vis                 # model.py:666
         return loss, diff, vis
+
+
+class SARSSL_MultiCH(SARSSL):
+    """model.py:793-821: the single-pair model (spatial encoder embedding, no head) applied to every microphone pair of an item and an MLP head
+    over the concatenated pair embeddings.  Same constructor, `forward(x) -> (pred (nb, factor), embed (nb, nmic_pair * 256))` and state_dict
+    keys (`model_sch.*`, `head_mch.*`) as the reference; everything runs on the fused engine (one parameter arena, one optimizer launch)."""
+
+    def __init__(self, sig_shape, nmic_pair, task, device):
+        factor = nmic_pair if task == "TDOA" else 1
+        super().__init__(sig_shape=sig_shape, pretrain=False, device=device, downstream_token="all", downstream_head="", downstream_embed="spat",
+                         downstream_dlabel=1, _nmic_pair=int(nmic_pair), _factor=factor, _tree_prefix="model_sch.")
+        self.nmic_pair = int(nmic_pair)
+
+    def forward(self, x):
+        """x (nb * nmic_pair, 2, nf, nt, 2): the pairs of an item are consecutive (model.py:816-819)."""
+        pred, pooled = super().forward(x)
+        return pred, pooled.reshape(-1, self.nmic_pair * pooled.shape[-1])
+
+
+class MCConformer(SARSSL):
+    """model.py:824-912 with its defaults (['cnn', 'conformer'] encoders of width 512 / 256, decoder ['', 'fc'], frame patches): spectrogram in,
+    reconstructed spectrogram out - `forward(x (nb, 2, nf, nt, 2)) -> data_pred (nb, nf, nt, 2, 2)`; no masking, no loss.  The state_dict
+    is the pre-training model's (spec_encoder.*, spat_encoder.*, decoder.*), so pre-trained checkpoints load directly."""
+
+    def __init__(self, sig_shape=[256, 256, 2, 2], patch_shape=(256, 1), spec_model=["cnn", "conformer"], spat_model=["cnn", "conformer"],
+                 dembed={"spec": 512, "spat": 256}, dec_model=["", "fc"], device="cpu"):
+        if list(spec_model) != ["cnn", "conformer"] or list(spat_model) != ["cnn", "conformer"] or list(dec_model) != ["", "fc"] or \
+                dict(dembed) != {"spec": 512, "spat": 256}:
+            raise _lib.SarsslError("MCConformer: only the shipped architecture (CNN + Conformer encoders of width 512 / 256, fc decoder) is on the hot path")
+        super().__init__(sig_shape=sig_shape, patch_shape=patch_shape, pretrain=True, device=device)
+        self.dembed = dict(dembed)
+
+    def forward(self, x):
+        self._engine()
+        patches = as_patch_layout(x)
+        nb, nt, nf = patches.shape[:3]
+        if (nf, nt) != tuple(self.sig_shape[:2]):
+            raise _lib.SarsslError(f"input is {nf} bins x {nt} frames but the model was built for {self.sig_shape[:2]}")
+        want = torch.is_grad_enabled() and self.training
+        pred = _PlainFn.apply(self._anchor, self, patches, want)
+        return pred.view(nb, nt, nf, 2, 2).permute(0, 2, 1, 3, 4)                 # PatchRecover (model.py:910) as a view

@@ -19,10 +19,12 @@ def bucket_ranges(store):
     """[(name, offset, numel)] in the order backward completes them: decoder, spec encoder, spat blocks 2..1, spat block 0 + stem."""
     def span(prefixes):
         ks = [k for k in store.order if any(k.startswith(p) for p in prefixes)]
+        if not ks:                                # a model without any head / decoder (SARSSL(downstream_head='')): an empty bucket
+            return store.total, 0
         lo = min(store.offsets[k][0] for k in ks)
         hi = max(store.offsets[k][0] + (store.offsets[k][1] + 3) // 4 * 4 for k in ks)
         return lo, hi - lo
-    out = [("decoder",) + span(["decoder.", "mlp_head.", "spec_spat_decoder.", "spec_decoder.", "spat_decoder."]), ("spec_encoder",) + span(["spec_encoder."]),
+    out = [("decoder",) + span(["decoder.", "mlp_head.", "head_mch.", "spec_spat_decoder.", "spec_decoder.", "spat_decoder."]), ("spec_encoder",) + span(["spec_encoder."]),
            ("spat_blocks_1_2",) + span(["spat_encoder.embed.layers.1.", "spat_encoder.embed.layers.2."]),
            ("spat_stem_block_0",) + span(["spat_encoder.patch_embed.", "spat_encoder.embed.layers.0."])]
     covered = sum(n for _, _, n in out)

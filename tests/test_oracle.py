@@ -191,3 +191,36 @@ def test_frozen_encoder_branch_matches_reference_fixture():
     for k in g.files:
         if k.startswith("bn/"):
             assert np.allclose(sd[k[3:]].numpy(), g[k], rtol=1e-4, atol=1e-6), k
+
+
+def test_multich_matches_reference_fixture():
+    """oracle.multich_forward vs the reference's SARSSL_MultiCH (model.py:793-821): prediction, embedding, gradients of an MSE step."""
+    g = np.load(os.path.join(GOLDEN, "multich_nt16_b2x3.npz"))
+    nb, nt, P, factor = int(g["nb"]), int(g["nt"]), int(g["nmic_pair"]), int(g["factor"])
+    sd = O.synthetic_state_dict(int(g["sd_seed"]), pretrain=False, head="", prefix="model_sch.", nmic_pair=P, factor=factor)
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    x = O.preprocess(O.synthetic_waveforms(nb * P, (nt + 1) * 256, 2, seed=int(g["sig_seed"])))
+    pred, emb = O.multich_forward(x, sd, P, training=True)
+    assert np.allclose(pred.detach().numpy(), g["pred"], rtol=1e-4, atol=1e-5) and np.allclose(emb.detach().numpy(), g["embed"], rtol=1e-4, atol=1e-5)
+    loss = torch.nn.functional.mse_loss(pred, torch.from_numpy(g["tar"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    gmax = max(float(g[k]) for k in g.files if k.startswith("grad_norm/"))
+    for k in names:
+        gr = (sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])).reshape(-1)
+        assert abs(float(gr.norm()) - float(g["grad_norm/" + k])) <= 2e-3 * float(g["grad_norm/" + k]) + 1e-6 * gmax, k
+
+
+def test_mcconformer_matches_reference_fixture():
+    """oracle.mcconformer_forward vs the reference's MCConformer (model.py:824-912), eval mode."""
+    g = np.load(os.path.join(GOLDEN, "mcconformer_nt16_b2.npz"))
+    nb, nt = int(g["nb"]), int(g["nt"])
+    sd = O.synthetic_state_dict(int(g["sd_seed"]))
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    x = O.preprocess(O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"])))
+    with torch.no_grad():
+        y = O.mcconformer_forward(x, sd, training=False)
+    assert y.shape == g["data_pred"].shape and np.allclose(y.numpy(), g["data_pred"], rtol=1e-4, atol=1e-5)
