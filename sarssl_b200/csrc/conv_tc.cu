@@ -19,10 +19,14 @@
 //
 // Weight gradient  (conv3x3_wgrad_tc_kernel, persistent, split over pixels):
 //   dWp[o, tap, ci] = sum_pixels dy[p, o] * in[p + tap, ci]; the contraction runs over pixels, so both operands are MN-major;
-//   the whole 576 x 64 result lives in TMEM (6 accumulators of 128 x 64: two taps of the same image row per UMMA).  Output rows are
-//   processed in pairs: the dy boxes of rows h and h+1 sit side by side in shared memory, so the input rows that feed both (h, h+1)
-//   run as N = 128 instructions into two neighbouring accumulators ([dh | dh-1]); rows h-1 and h+2 feed one tap row each (N = 64).
-//   The rolling ring of input row boxes is re-used across pairs; per-CTA partial sums are reduced in a fixed order by a second kernel.
+//   the whole result lives in TMEM.  Output rows are processed in pairs: the dy boxes of rows h and h+1 sit side by side in shared memory,
+//   so the input rows that feed both (h, h+1) run as N = 128 instructions ([dh | dh-1]); rows h-1 and h+2 feed one tap row each (N = 64).
+//   Taps dw = -1 / 0 fill the 128 lanes of an instruction through the pixel shift (the second 64-channel group starts one pixel later).
+//   Tap dw = +1 has no horizontal partner, so it is stacked VERTICALLY instead: input rows h and h+1 occupy neighbouring ring slots (the
+//   ring starts at an odd slot, so such a pair never wraps) and form one M = 128 operand whose two groups are a slot apart; against
+//   [dy(h) | dy(h+1)] one instruction yields (dh 0 | dh -1) in the lower and (dh +1 | dh 0) in the upper lanes.  Only rows h-1 / h+2 of that
+//   tap still issue half-empty instructions: 640 instead of 768 column-units per k-step.  A tap that receives contributions in two TMEM
+//   regions gets two slots in the per-CTA partial sums; the fixed-order reduction kernel adds them.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -314,13 +318,14 @@ constexpr int GDY = 4;                   // ring of dy boxes (8 KB each)
 constexpr int kWgradSmem = GSLOTS * GBOXB + GDY * 8192 + 1024 + 256;
 constexpr int GSEG = 32;
 
+constexpr int GTAPS = 12;                // partial-sum slots per CTA: taps 0..8 + a second slot for the three dw = +1 taps (9 + dh + 1)
 struct WgradP {
-    float* partials;                     // [gridDim.x][576][64]
+    float* partials;                     // [gridDim.x][GTAPS][64 ci][64 o]
     int B, H, W, tiles_w, nseg_h;
     long long nunits;
 };
 
-// accumulator g (0..5) holds taps (3*(g/2) + 2*(g%2)) and, in its upper 64 lanes, the next tap of the same image row (g even)
+// TMEM: 7 regions of 64 columns (see the MMA warp and the epilogue for the tap each lane half of a region holds)
 __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy,
                                                                       WgradP p) {
     extern __shared__ unsigned char raw[];
@@ -351,11 +356,23 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
     __syncthreads();
     cfence_after();
     const uint32_t tmem = *slot_tmem;
-    bool any = false;
+    if (warp >= 2) {                                            // all accumulators start at zero: every UMMA accumulates, whatever pair shape comes first
+        const uint32_t zero[1] = {0u};
+        for (int c = 0; c < 448; c += 32) {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                ::"r"(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c), "r"(zero[0]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    cfence_before();
+    __syncthreads();
+    cfence_after();
 
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0, sd = 0;
+            int s = 1, sd = 0;                                  // odd start: rows (h, h+1) of a pair always sit in slots (even, even + 1)
             uint32_t ephase = 0, dephase = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
@@ -392,7 +409,8 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
             constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t hi = cdesc_hi(1024);
             const uint32_t ring_lo = cdesc_lo(smem_u32(ring), 128), dy_lo0 = cdesc_lo(smem_u32(dyr), 8192);
-            int slot0 = 0, sd = 0;
+            const uint32_t stk_lo = cdesc_lo(smem_u32(ring), GBOXB);      // vertically stacked operand: the second 64-channel group is the next ring slot
+            int slot0 = 1, sd = 0;
             uint32_t fphase = 0, dphase = 0;
             for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
                 const int hs = (int)(u % p.nseg_h);
@@ -415,39 +433,51 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                     }
                     cfence_after();
                     const uint32_t dy_lo = dy_lo0 + (uint32_t)sd * (8192 >> 4);
-                    const uint32_t accf = any ? 1u : 0u;
                     const uint32_t a0 = ring_lo + (uint32_t)sl[0] * (GBOXB >> 4), a1 = ring_lo + (uint32_t)sl[1] * (GBOXB >> 4),
                                    a2 = ring_lo + (uint32_t)sl[2] * (GBOXB >> 4), a3 = ring_lo + (uint32_t)sl[3] * (GBOXB >> 4);
+                    const uint32_t a12 = stk_lo + (uint32_t)sl[1] * (GBOXB >> 4) + 16;        // [in(h) | in(h+1)] at dw = +1 (sl[1] is even: sl[2] = sl[1] + 1)
                     const bool last = t == npair - 1;
                     const bool full_pair = h0 + 2 * t + 1 < h1;  // a trailing half pair has only output row h
-                    // accumulator (tap group G, dh) lives at columns G*192 + (1-dh)*64: [dh=+1 | dh=0 | dh=-1], so an N = 128 instruction whose B is
-                    // [dy(h) | dy(h+1)] lands on (dh, dh-1).  The first instructions ever issued initialise every column exactly once.
+                    // TMEM columns.  Taps dw = -1 / 0 (lanes 0-63 / 64-127): [dh=+1 | dh=0 | dh=-1] at 0 / 64 / 128, so an N = 128 instruction whose B is
+                    // [dy(h) | dy(h+1)] lands on (dh, dh-1).  Tap dw = +1: X at 192 (lanes 0-63 = in(h): [dh=0 | dh=-1], lanes 64-127 = in(h+1):
+                    // [dh=+1 | dh=0]), Y1 at 320 (in(h-1) x dy(h): dh=-1), Y2 at 384 (in(h+2) x dy(h+1): dh=+1).  Everything accumulates (zeroed above).
                     if (celect_one()) {
+                        if (full_pair) {
 #pragma unroll
-                        for (int G = 0; G < 2; ++G) {            // G = 0: taps dw = -1, 0;  G = 1: tap dw = +1 (upper 64 lanes unused)
-                            const uint32_t d = tmem + G * 192, ao = G * 16;
-                            if (full_pair) {
+                            for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for dy(h), dh = 0 for dy(h+1)
+                                cumma2(tmem, a2 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)     // input row h+1: dh = +1 for dy(h), dh = 0 for dy(h+1)
-                                    cumma2(d, a2 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc128, k == 0 ? accf : 1u);
+                            for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1 for dy(h)
+                                cumma2(tmem + 128, a0 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)     // input row h-1: dh = -1 for dy(h)
-                                    cumma2(d + 128, a0 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc64, k == 0 ? accf : 1u);
+                            for (int k = 0; k < 4; ++k)         // input row h:   dh = 0 for dy(h), dh = -1 for dy(h+1)
+                                cumma2(tmem + 64, a1 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)     // input row h:   dh = 0 for dy(h), dh = -1 for dy(h+1)
-                                    cumma2(d + 64, a1 + ao + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
+                            for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1 for dy(h+1)
+                                cumma2(tmem, a3 + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)     // input row h+2: dh = +1 for dy(h+1)
-                                    cumma2(d, a3 + ao + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
-                            } else {
+                            for (int k = 0; k < 4; ++k)         // dw = +1, rows h | h+1 stacked against both dy rows
+                                cumma2(tmem + 192, a12 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
 #pragma unroll
-                                for (int dh = 0; dh < 3; ++dh) {                  // single output row: input rows h-1, h, h+1 against dy(h)
-                                    const uint32_t a = dh == 0 ? a0 : (dh == 1 ? a1 : a2);
+                            for (int k = 0; k < 4; ++k)         // dw = +1, row h-1 (upper lanes unused)
+                                cumma2(tmem + 320, a0 + 16 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        cumma2(d + (2 - dh) * 64, a + ao + k * 128, hi, dy_lo + k * 128, hi, idesc64, k == 0 ? accf : 1u);
-                                }
+                            for (int k = 0; k < 4; ++k)         // dw = +1, row h+2 (upper lanes unused)
+                                cumma2(tmem + 384, a3 + 16 + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
+                        } else {
+#pragma unroll
+                            for (int dh = 0; dh < 3; ++dh) {                      // single output row: input rows h-1, h, h+1 against dy(h)
+                                const uint32_t a = dh == 0 ? a0 : (dh == 1 ? a1 : a2);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    cumma2(tmem + (2 - dh) * 64, a + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
                             }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)         // dw = +1: rows h | h+1 stacked against dy(h) -> (dh = 0 | dh = +1) in X's first column block
+                                cumma2(tmem + 192, a12 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                cumma2(tmem + 320, a0 + 16 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
                         }
                         ccommit(&empty[sl[0]]);
                         ccommit(&empty[sl[1]]);
@@ -456,7 +486,6 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                         ccommit(&dempty[sd + 1]);
                     }
                     __syncwarp();
-                    any = true;
                     slot0 += last ? 4 : 2; if (slot0 >= GSLOTS) slot0 -= GSLOTS;
                     sd += 2; if (sd >= GDY) sd = 0;
                 }
@@ -465,33 +494,36 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
             __syncwarp();
         }
     }
-    // every CTA writes its partial (zeros if it had no work) so the reduction can read a fixed number of partials
+    // every CTA writes its partial (zeros if it had no work: the accumulators were zeroed) so the reduction can read a fixed number of partials
     const bool has_work = (long long)blockIdx.x < p.nunits;
     if (warp >= 2) {
         const int q = warp & 3;
-        float* dst = p.partials + (size_t)blockIdx.x * 576 * 64;
+        float* dst = p.partials + (size_t)blockIdx.x * GTAPS * 64 * 64;
         if (has_work) {
             mbar_wait(done, 0);
             cfence_after();
         }
-        // accumulator g = G*3 + (1-dh) at columns g*64: lanes l < 64 -> tap (dh, dw = 2G-1), ci = l;  l >= 64 (G = 0 only) -> tap (dh, dw = 0), ci = l - 64
-        for (int g = 0; g < 6; ++g) {
-            const int l = q * 32 + lane;
-            const int G = g / 3, dhi = 2 - (g % 3);              // dhi = dh + 1
-            const int tap = dhi * 3 + 2 * G + (l >> 6);
-            const bool valid = (l < 64) || (G == 0);
-            const int ci = l & 63;
+        const int l = q * 32 + lane, up = l >> 6, ci = l & 63;
+        // region r at TMEM columns r*64 -> partial slot of this lane (-1: nothing useful in this lane)
+        //   0..2: taps dw = -1 (lanes 0-63) / dw = 0 (lanes 64-127), dh + 1 = 2 - r
+        //   3: X first block  (in(h) x dy(h): dh 0 | in(h+1) x dy(h): dh +1)        4: X second block (in(h) x dy(h+1): dh -1 | in(h+1) x dy(h+1): dh 0, 2nd slot)
+        //   5: Y1 (in(h-1) x dy(h): dh -1, 2nd slot)                                 6: Y2 (in(h+2) x dy(h+1): dh +1, 2nd slot)
+        for (int r = 0; r < 7; ++r) {
+            int slot;
+            if (r < 3) slot = (2 - r) * 3 + up;
+            else if (r == 3) slot = up ? 8 : 5;
+            else if (r == 4) slot = up ? 10 : 2;
+            else if (r == 5) slot = up ? -1 : 9;
+            else slot = up ? -1 : 11;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
-                if (has_work) ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 64 + c0, v);
-                if (valid) {
-                    float* o = dst + ((size_t)tap * 64 + ci) * 64 + c0;
+                ctmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + r * 64 + c0, v);
+                if (slot >= 0) {
+                    float* o = dst + ((size_t)slot * 64 + ci) * 64 + c0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(o + j) = has_work ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                                                                   __uint_as_float(v[j + 3]))
-                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 }
             }
         }
@@ -501,13 +533,18 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-// partials [nparts][tap][ci][o] -> dWp[o][tap][ci] (+)=
+// partials [nparts][GTAPS][ci][o] -> dWp[o][tap][ci] (+)=; slot 9 + dh + 1 holds the second contribution to tap (dh, dw = +1)
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ out, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;          // index into [tap][ci][o]
     if (i >= 576 * 64) return;
+    const int o = i & 63, tc = i >> 6, tap = tc >> 6, ci = tc & 63;
+    const int second = (tap % 3 == 2) ? (((9 + tap / 3) * 64 + ci) * 64 + o) : -1;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)partials[(size_t)p * 576 * 64 + i];
-    const int o = i & 63, tc = i >> 6;
+    for (int p = 0; p < nparts; ++p) {
+        const float* base = partials + (size_t)p * GTAPS * 64 * 64;
+        s += (double)base[i];
+        if (second >= 0) s += (double)base[second];
+    }
     float* d = out + (size_t)o * 576 + tc;
     *d = accumulate ? *d + (float)s : (float)s;
 }
@@ -575,7 +612,7 @@ extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void
     return SARSSL_OK;
 }
 
-extern "C" size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void) { return (size_t)sm_count() * 576 * 64 * sizeof(float); }
+extern "C" size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void) { return (size_t)sm_count() * GTAPS * 64 * 64 * sizeof(float); }
 
 extern "C" int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
                                        size_t workspace_bytes, cudaStream_t stream) {

@@ -524,8 +524,8 @@ class Engine:
         r = sv[pe]
         M, P = B * T, B * T * F
         # patch conv (F x 1, stride F x 1) = GEMM over K = F*4
-        dwp = torch.empty(D, 4 * F, dtype=torch.float32, device=self.dev)
-        k.gemm(de, r["z4"], dwp, D, 4 * F, M, (1, D), (1, 4 * F), 4 * F)
+        dwp = torch.zeros(D, 4 * F, dtype=torch.float32, device=self.dev)               # accumulate=True selects the split-K path: 16-32 output tiles, K = B*T
+        k.gemm(de, r["z4"], dwp, D, 4 * F, M, (1, D), (1, 4 * F), 4 * F, accumulate=True)
         k.permute4(dwp, st.g(f"{pe}.12.weight"), (D, 4, F, 1), (4 * F, 1, 4, 0), accumulate=True)
         dz4 = k.empty(M, 4 * F)
         k.linear_dgrad(de, self.W[f"{pe}.12.packed"], dz4, M, D, 4 * F)
