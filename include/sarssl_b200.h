@@ -305,15 +305,18 @@ int sarssl_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, 
                          int B, int H, int W, int dtype, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* Tensor-core versions (bf16 only): tcgen05 implicit GEMM, TMA row boxes shared by the three horizontal taps, weights
- * resident in shared memory, persistent CTAs.  `in` must already be the post-BatchNorm/ReLU activation (or dy for the data
+ * resident in shared memory, persistent CTAs.  in_scale / in_shift (both nullable, 64 floats each): `in` is the PRE-BatchNorm tensor and
+ * the operand is relu(in_scale * in + in_shift) (model.py:52-56), applied to the landed row boxes in shared memory by transform warps, so
+ * the post-BatchNorm/ReLU activation never exists in HBM; null: `in` is used as it is (already activated input, or dy for the data
  * gradient, with the mirrored weight pack).  wgrad workspace: sarssl_conv3x3_wgrad_tc_workspace_bytes(). */
 /*   bn_partials (nullable): sarssl_conv3x3_tc_grid(B,H,W) x 2 x 64 floats receive per-CTA sums of out / out^2 (fused BatchNorm batch
  *   statistics of the conv output); turn them into stats with sarssl_batchnorm_finalize. */
 int sarssl_conv3x3_tc_grid(int B, int H, int W);
-int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, int B, int H, int W, cudaStream_t stream);
+int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, const float* in_scale, const float* in_shift,
+                      int B, int H, int W, cudaStream_t stream);
 size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void);
-int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
-                            size_t workspace_bytes, cudaStream_t stream);
+int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dweight_packed, int accumulate,
+                            int B, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A14  optimizer: torch.optim.Adam(betas (0.9, 0.999), eps 1e-8, wd 0) over flat fp32 arenas      learner.py:83,111-113

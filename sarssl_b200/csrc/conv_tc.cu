@@ -84,6 +84,57 @@ __device__ __forceinline__ void ctmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- operand transform: BatchNorm + ReLU applied to a TMA-landed row box in place -------------------------------------------------
+// The stem's second 3x3 convolution consumes z = relu(scale * y + shift) (model.py:52-56).  Round 1 materialised z with a separate pass
+// (read y, write z: 0.66 ms per encoder at 256 clips) because TMA feeds the UMMA directly.  Here four extra warps sit between the
+// TMA's `full` barrier and the `ready` barrier the MMA warp waits on: they rewrite the box (pixels x 64 channels bf16, 128-byte swizzled
+// rows) in shared memory - smem -> registers -> fma + max -> bf16 -> smem, same arithmetic and rounding as bn_act_fwd_kernel - so z never
+// exists in HBM.  Zero padding must stay zero: whole out-of-image rows are skipped, out-of-image pixels of a row are masked.
+// Thread t of the 128 owns the logical 16-byte chunk t & 7 (= 8 fixed channels: their scale / shift live in registers) of pixels
+// (t >> 3) + 16 i; the physical chunk is (t & 7) ^ (pixel & 7).
+struct XfConst {
+    float sc[8], sh[8];
+    __device__ __forceinline__ void load(const float* scale, const float* shift, int t) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[(t & 7) * 8 + j]; sh[j] = shift[(t & 7) * 8 + j]; }
+    }
+};
+// NITER = ceil(npix / 16) chunks per thread: all loads first, then the arithmetic, then the stores (one shared-memory round trip of latency
+// per box instead of NITER: the transform sits on the TMA -> MMA path of a ring that cannot be made deeper in the forward kernel).
+template <int NITER>
+__device__ __forceinline__ void xf_box(unsigned char* box, int npix, int w_first, int W, int t, const XfConst& c) {
+    const int ch = t & 7, r0 = t >> 3;
+    uint4 u[NITER];
+    bool ok[NITER];
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+        const int r = r0 + 16 * i, w = w_first + r;
+        ok[i] = r < npix && w >= 0 && w < W;
+        if (ok[i]) u[i] = *reinterpret_cast<const uint4*>(box + r * 128 + ((ch ^ (r & 7)) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&u[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = __uint_as_float(pw[j] << 16), hi = __uint_as_float(pw[j] & 0xFFFF0000u);
+            const float a = fmaxf(fmaf(lo, c.sc[2 * j], c.sh[2 * j]), 0.f), b = fmaxf(fmaf(hi, c.sc[2 * j + 1], c.sh[2 * j + 1]), 0.f);
+            const __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+            pw[j] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+        const int r = r0 + 16 * i;
+        if (ok[i]) *reinterpret_cast<uint4*>(box + r * 128 + ((ch ^ (r & 7)) << 4)) = u[i];
+    }
+}
+__device__ __forceinline__ void xf_publish(uint64_t* bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
 // ============================================================================================================================
 // forward / data gradient
 // ============================================================================================================================
@@ -97,16 +148,21 @@ constexpr int COUTB = CW * 128;           // 16 KB output staging tile (x2)
 constexpr int kConvSmem = CSLOTS * CBOXB + CWB + 2 * COUTB + 1024 + 256;
 constexpr int kConvThreads = 192;          // weight-gradient kernel: 2 control + 4 epilogue warps
 constexpr int kConvFwdThreads = 320;       // forward kernel: 2 control + 8 epilogue warps (the epilogue paces the tile rate)
+constexpr int kConvXfThreads = 448;        // + 4 operand-transform warps (fused BatchNorm + ReLU of the input)
 
 struct ConvP {
+    const float* in_scale;               // XF: per-channel scale / shift of the input's BatchNorm (the input is y, the operand relu(scale * y + shift))
+    const float* in_shift;
     __nv_bfloat16* out;
     float* bn_partials;                  // nullable: [gridDim.x][2][64] per-CTA sums of out and out^2 (BatchNorm batch statistics of the conv output)
     int B, H, W, tiles_w, nseg_h;
     long long nunits;
 };
 
-__global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
-                                                                const __grid_constant__ CUtensorMap tmOut, ConvP p) {
+template <bool XF>
+__global__ void __launch_bounds__(XF ? kConvXfThreads : kConvFwdThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn,
+                                                                                      const __grid_constant__ CUtensorMap tmW,
+                                                                                      const __grid_constant__ CUtensorMap tmOut, ConvP p) {
     extern __shared__ unsigned char raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     unsigned char* ring = smem;
@@ -117,14 +173,15 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
     uint64_t* wbar = empty + CSLOTS;
     uint64_t* tfull = wbar + 1;          // [2]
     uint64_t* tempty = tfull + 2;        // [2]
-    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* ready = tempty + 2;        // [CSLOTS] XF: box transformed (one arrival per transform warp)
+    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(ready + CSLOTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
-        for (int s = 0; s < CSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
         mbar_init(wbar, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
@@ -183,7 +240,7 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {               // (unrolled: a run-time index would push sl[] into local memory)
                         if (j < 2 && t != 0) continue;
-                        mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
+                        mbar_wait(XF ? &ready[sl[j]] : &full[sl[j]], (fphase >> sl[j]) & 1u);
                         fphase ^= 1u << sl[j];
                     }
                     const uint32_t acc = it & 1u;
@@ -194,7 +251,9 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
                                    a2 = ring_lo + (uint32_t)sl[2] * (CBOXB >> 4), a3 = ring_lo + (uint32_t)sl[3] * (CBOXB >> 4);
                     const bool last = t == npair - 1;
                     if (celect_one()) {
-                        // weight slot (dw, dh) = dw*3 + (1 - dh) (dw, dh as 0..2 / -1..1); the first instruction initialises all 128 columns
+                        // weight slot (dw, dh) = dw*3 + (1 - dh) (dw, dh as 0..2 / -1..1); the first instruction initialises all 128 columns.
+                        // Rows h-1 and h die with this pair: their instructions go first and their slots are released half a pair early, which
+                        // is the lead the producer (and, with XF, the operand transform behind it) needs on a ring that cannot be deeper.
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
@@ -203,26 +262,47 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
+                            for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1, output row h only (columns 0-63)
+                                cumma2(d, a0 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 2) * 512 + k * 2, hi, idesc64, 1u);
+                        ccommit(&empty[sl[0]]);
+                        ccommit(&empty[sl[1]]);
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for output row h | dh = 0 for output row h+1
                                 cumma2(d, a2 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc128, 1u);
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1, output row h only (columns 0-63)
-                                cumma2(d, a0 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 2) * 512 + k * 2, hi, idesc64, 1u);
-#pragma unroll
-                        for (int dw = 0; dw < 3; ++dw)
-#pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1, output row h+1 only (columns 64-127)
                                 cumma2(d + 64, a3 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc64, 1u);
-                        ccommit(&empty[sl[0]]);                 // rows h-1 and h are dead after this pair
-                        ccommit(&empty[sl[1]]);
                         if (last) { ccommit(&empty[sl[2]]); ccommit(&empty[sl[3]]); }
                         ccommit(&tfull[acc]);
                     }
                     __syncwarp();
                     slot0 += last ? 4 : 2; if (slot0 >= CSLOTS) slot0 -= CSLOTS;
                 }
+            }
+        }
+    } else if (XF && warp >= 10) {
+        // operand-transform warps: walk the producer's box sequence, rewrite each landed row box, hand it to the MMA warp
+        const int t = threadIdx.x - 320;
+        XfConst xc;
+        xc.load(p.in_scale, p.in_shift, t);
+        int s = 0;
+        uint32_t fph = 0;
+        for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+            const int hs = (int)(u % p.nseg_h);
+            const long long r = u / p.nseg_h;
+            const int wt = (int)(r % p.tiles_w);
+            const int h0 = hs * CSEG, h1 = min(p.H, h0 + CSEG), w0 = wt * CW;
+            const int npair = (h1 - h0 + 1) >> 1;
+            for (int row = h0 - 1; row <= h0 + 2 * npair; ++row) {
+                mbar_wait(&full[s], (fph >> s) & 1u);
+                fph ^= 1u << s;
+                if (row >= 0 && row < p.H) xf_box<(CBOXR + 15) / 16>(ring + s * CBOXB, CBOXR, w0 - 1, p.W, t, xc);
+                xf_publish(&ready[s], lane);
+                if (++s == CSLOTS) s = 0;
             }
         }
     } else {
@@ -313,19 +393,22 @@ __global__ void __launch_bounds__(kConvFwdThreads) conv3x3_tc_kernel(const __gri
 constexpr int GK = 64;                   // pixels per k-block
 constexpr int GBOXR = 72;                // input rows per box: GK + 2 halo, rounded up to 8
 constexpr int GBOXB = 10240;             // 72 * 128 = 9216, padded to a multiple of 1024
-constexpr int GSLOTS = 8;                // ring of input row boxes
-constexpr int GDY = 4;                   // ring of dy boxes (8 KB each)
-constexpr int kWgradSmem = GSLOTS * GBOXB + GDY * 8192 + 1024 + 256;
+constexpr int GSLOTS = 12;               // ring of input row boxes (even; deep enough to hide TMA latency + the operand transform: a pair lasts ~1.3 us)
+constexpr int GDY = 8;                   // ring of dy boxes (8 KB each)
+constexpr int kWgradSmem = GSLOTS * GBOXB + GDY * 8192 + 1024 + 512;          // data + alignment slack + 53 mbarriers and the TMEM slot
 constexpr int GSEG = 32;
 
 constexpr int GTAPS = 12;                // partial-sum slots per CTA: taps 0..8 + a second slot for the three dw = +1 taps (9 + dh + 1)
 struct WgradP {
+    const float* in_scale;               // XF: the `in` operand is relu(scale * in + shift), applied to the landed boxes by the (otherwise idle) epilogue warps
+    const float* in_shift;
     float* partials;                     // [gridDim.x][GTAPS][64 ci][64 o]
     int B, H, W, tiles_w, nseg_h;
     long long nunits;
 };
 
 // TMEM: 7 regions of 64 columns (see the MMA warp and the epilogue for the tap each lane half of a region holds)
+template <bool XF>
 __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy,
                                                                       WgradP p) {
     extern __shared__ unsigned char raw[];
@@ -337,13 +420,14 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
     uint64_t* dfull = empty + GSLOTS;
     uint64_t* dempty = dfull + GDY;
     uint64_t* done = dempty + GDY;
-    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(done + 1);
+    uint64_t* ready = done + 1;          // [GSLOTS] XF: box transformed
+    uint32_t* slot_tmem = reinterpret_cast<uint32_t*>(ready + GSLOTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDy) : "memory");
-        for (int s = 0; s < GSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < GSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
         for (int s = 0; s < GDY; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 1); }
         mbar_init(done, 1);
         mbar_fence_init();
@@ -423,7 +507,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {               // (unrolled: a run-time index would push sl[] into local memory)
                         if (j < 2 && t != 0) continue;
-                        mbar_wait(&full[sl[j]], (fphase >> sl[j]) & 1u);
+                        mbar_wait(XF ? &ready[sl[j]] : &full[sl[j]], (fphase >> sl[j]) & 1u);
                         fphase ^= 1u << sl[j];
                     }
 #pragma unroll
@@ -443,24 +527,27 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                     // [dh=+1 | dh=0]), Y1 at 320 (in(h-1) x dy(h): dh=-1), Y2 at 384 (in(h+2) x dy(h+1): dh=+1).  Everything accumulates (zeroed above).
                     if (celect_one()) {
                         if (full_pair) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for dy(h), dh = 0 for dy(h+1)
-                                cumma2(tmem, a2 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
+                            // rows h-1 and h die with this pair: everything that reads them first, then their slots are released half a pair early
 #pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1 for dy(h)
                                 cumma2(tmem + 128, a0 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
 #pragma unroll
+                            for (int k = 0; k < 4; ++k)         // dw = +1, row h-1 (upper lanes unused)
+                                cumma2(tmem + 320, a0 + 16 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
+#pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h:   dh = 0 for dy(h), dh = -1 for dy(h+1)
                                 cumma2(tmem + 64, a1 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1 for dy(h+1)
-                                cumma2(tmem, a3 + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
-#pragma unroll
                             for (int k = 0; k < 4; ++k)         // dw = +1, rows h | h+1 stacked against both dy rows
                                 cumma2(tmem + 192, a12 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
+                            ccommit(&empty[sl[0]]);
+                            ccommit(&empty[sl[1]]);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)         // dw = +1, row h-1 (upper lanes unused)
-                                cumma2(tmem + 320, a0 + 16 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
+                            for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for dy(h), dh = 0 for dy(h+1)
+                                cumma2(tmem, a2 + k * 128, hi, dy_lo + k * 128, hi, idesc128, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1 for dy(h+1)
+                                cumma2(tmem, a3 + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)         // dw = +1, row h+2 (upper lanes unused)
                                 cumma2(tmem + 384, a3 + 16 + k * 128, hi, dy_lo + 512 + k * 128, hi, idesc64, 1u);
@@ -479,8 +566,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
                             for (int k = 0; k < 4; ++k)
                                 cumma2(tmem + 320, a0 + 16 + k * 128, hi, dy_lo + k * 128, hi, idesc64, 1u);
                         }
-                        ccommit(&empty[sl[0]]);
-                        ccommit(&empty[sl[1]]);
+                        if (!full_pair) { ccommit(&empty[sl[0]]); ccommit(&empty[sl[1]]); }
                         if (last) { ccommit(&empty[sl[2]]); ccommit(&empty[sl[3]]); }
                         ccommit(&dempty[sd]);
                         ccommit(&dempty[sd + 1]);
@@ -499,6 +585,27 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_tc_kernel(const __
     if (warp >= 2) {
         const int q = warp & 3;
         float* dst = p.partials + (size_t)blockIdx.x * GTAPS * 64 * 64;
+        if (XF) {                                               // main loop: these warps are the operand transform (they only drain TMEM at the very end)
+            const int t = threadIdx.x - 64;
+            XfConst xc;
+            xc.load(p.in_scale, p.in_shift, t);
+            int s = 1;
+            uint32_t fph = 0;
+            for (long long u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+                const int hs = (int)(u % p.nseg_h);
+                const long long r = u / p.nseg_h;
+                const int wt = (int)(r % p.tiles_w);
+                const int h0 = hs * GSEG, h1 = min(p.H, h0 + GSEG), w0 = wt * GK;
+                const int npair = (h1 - h0 + 1) >> 1;
+                for (int row = h0 - 1; row <= h0 + 2 * npair; ++row) {
+                    mbar_wait(&full[s], (fph >> s) & 1u);
+                    fph ^= 1u << s;
+                    if (row >= 0 && row < p.H) xf_box<(GBOXR + 15) / 16>(ring + s * GBOXB, GBOXR, w0 - 1, p.W, t, xc);
+                    xf_publish(&ready[s], lane);
+                    if (++s == GSLOTS) s = 0;
+                }
+            }
+        }
         if (has_work) {
             mbar_wait(done, 0);
             cfence_after();
@@ -583,7 +690,8 @@ extern "C" int sarssl_conv3x3_tc_grid(int B, int H, int W) {
     return (int)(nunits < sm_count() ? nunits : sm_count());
 }
 
-extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, int B, int H, int W, cudaStream_t stream) {
+extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void* out, float* bn_partials, const float* in_scale, const float* in_shift,
+                                 int B, int H, int W, cudaStream_t stream) {
     SARSSL_CHECK_ARG(in && weight_packed && out && B > 0 && H > 0 && W > 0, "conv3x3_tc: bad arguments");
     SARSSL_CHECK_ARG(aligned16(in) && aligned16(weight_packed) && aligned16(out), "conv3x3_tc: buffers must be 16-byte aligned");
     CUtensorMap mi, mw, mo;
@@ -600,36 +708,50 @@ extern "C" int sarssl_conv3x3_tc(const void* in, const void* weight_packed, void
             return SARSSL_ERR_ARG;
         }
     }
+    SARSSL_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_tc: in_scale and in_shift come together");
     static bool configured = false;
-    if (!configured) { SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem)); configured = true; }
+    if (!configured) {
+        SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        configured = true;
+    }
     ConvP p;
+    p.in_scale = in_scale; p.in_shift = in_shift;
     p.out = static_cast<__nv_bfloat16*>(out); p.bn_partials = bn_partials; p.B = B; p.H = H; p.W = W;
     p.tiles_w = (W + CW - 1) / CW; p.nseg_h = (H + CSEG - 1) / CSEG;
     p.nunits = (long long)B * p.tiles_w * p.nseg_h;
     const int grid = sarssl_conv3x3_tc_grid(B, H, W);
-    conv3x3_tc_kernel<<<grid, kConvFwdThreads, kConvSmem, stream>>>(mi, mw, mo, p);
+    if (in_scale) conv3x3_tc_kernel<true><<<grid, kConvXfThreads, kConvSmem, stream>>>(mi, mw, mo, p);
+    else conv3x3_tc_kernel<false><<<grid, kConvFwdThreads, kConvSmem, stream>>>(mi, mw, mo, p);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 extern "C" size_t sarssl_conv3x3_wgrad_tc_workspace_bytes(void) { return (size_t)sm_count() * GTAPS * 64 * 64 * sizeof(float); }
 
-extern "C" int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, float* dweight_packed, int accumulate, int B, int H, int W, void* workspace,
-                                       size_t workspace_bytes, cudaStream_t stream) {
+extern "C" int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dweight_packed, int accumulate,
+                                       int B, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     SARSSL_CHECK_ARG(dy && in && dweight_packed && workspace && B > 0 && H > 0 && W > 0, "conv3x3_wgrad_tc: bad arguments");
     if (workspace_bytes < sarssl_conv3x3_wgrad_tc_workspace_bytes()) { set_last_error("conv3x3_wgrad_tc: workspace too small"); return SARSSL_ERR_WORKSPACE; }
     CUtensorMap mi, md;
     int rc;
     if ((rc = image_map(&mi, in, B, H, W, GBOXR))) return rc;
     if ((rc = image_map(&md, dy, B, H, W, GK))) return rc;
+    SARSSL_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "conv3x3_wgrad_tc: in_scale and in_shift come together");
     static bool configured = false;
-    if (!configured) { SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem)); configured = true; }
+    if (!configured) {
+        SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem));
+        SARSSL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem));
+        configured = true;
+    }
     WgradP p;
+    p.in_scale = in_scale; p.in_shift = in_shift;
     p.partials = static_cast<float*>(workspace); p.B = B; p.H = H; p.W = W;
     p.tiles_w = (W + GK - 1) / GK; p.nseg_h = (H + GSEG - 1) / GSEG;
     p.nunits = (long long)B * p.tiles_w * p.nseg_h;
     const int grid = (int)(p.nunits < sm_count() ? p.nunits : sm_count());
-    conv3x3_wgrad_tc_kernel<<<grid, kConvThreads, kWgradSmem, stream>>>(mi, md, p);
+    if (in_scale) conv3x3_wgrad_tc_kernel<true><<<grid, kConvThreads, kWgradSmem, stream>>>(mi, md, p);
+    else conv3x3_wgrad_tc_kernel<false><<<grid, kConvThreads, kWgradSmem, stream>>>(mi, md, p);
     SARSSL_LAUNCH_CHECK();
     conv_wgrad_reduce_kernel<<<(576 * 64 + 255) / 256, 256, 0, stream>>>(p.partials, grid, dweight_packed, accumulate);
     SARSSL_LAUNCH_CHECK();

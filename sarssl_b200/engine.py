@@ -170,10 +170,8 @@ class Engine:
             s2 = None
         if s2 is None:
             s2 = self._bn(f"{pe}.4", y2, P, CNN_CH, training)
-        if k.conv_tc:
-            z2 = k.empty(P, CNN_CH)
-            k.bn_act_fwd(y2, s2, ACT_RELU, z2, P, CNN_CH)
-            s3 = k.conv3x3_tc(z2, self.W[f"{pe}.6.fwd"], y3, B, T, F, bn=self._bn_args(f"{pe}.7") if training else None)
+        if k.conv_tc:            # BatchNorm + ReLU of y2 is applied to the conv's operand tiles in shared memory: z2 is never stored
+            s3 = k.conv3x3_tc(y2, self.W[f"{pe}.6.fwd"], y3, B, T, F, bn=self._bn_args(f"{pe}.7") if training else None, in_stats=s2)
         else:
             k.conv3x3(y2, s2, self.W[f"{pe}.6.fwd"], y3, B, T, F)
             s3 = None
@@ -544,8 +542,8 @@ class Engine:
         dz_prev = k.empty(P, CNN_CH)
         for i, y_in, s_in, y_bn, bn_key, z_in in ((6, r["y2"], r["s2"], r["y2"], f"{pe}.4", r["z2"]), (3, r["y1"], r["s1"], r["y1"], f"{pe}.1", r["z1"])):
             dwpk = torch.empty(CNN_CH, 9, CNN_CH, dtype=torch.float32, device=self.dev)
-            if k.conv_tc:
-                k.conv3x3_wgrad_tc(dz, z_in, dwpk, B, T, F)
+            if k.conv_tc:        # layer 6 reads y2 and applies BatchNorm + ReLU on the fly (z_in is None there); layer 3 reads the stored z1
+                k.conv3x3_wgrad_tc(dz, z_in if z_in is not None else y_in, dwpk, B, T, F, in_stats=s_in if z_in is None else None)
             else:
                 k.conv3x3_wgrad(dz, y_in, s_in, dwpk, B, T, F)
             k.permute4(dwpk, st.g(f"{pe}.{i}.weight"), (CNN_CH, CNN_CH, 3, 3), (576, 1, 64, 192), accumulate=True)

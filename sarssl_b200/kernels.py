@@ -219,14 +219,17 @@ class KernelSet:
     def conv_tc(self):
         return self.use_tc and self.dtype == torch.bfloat16
 
-    def conv3x3_tc(self, x, wpacked, out, B, H, W, bn=None):
+    def conv3x3_tc(self, x, wpacked, out, B, H, W, bn=None, in_stats=None):
         """bn = (gamma, beta, running_mean, running_var, num_batches_tracked): also returns the BatchNorm batch statistics of `out`,
-        reduced inside the conv epilogue (no extra pass over the tensor)."""
+        reduced inside the conv epilogue (no extra pass over the tensor).  in_stats: BatchNorm statistics of `x`; the operand becomes
+        relu(bn(x)), applied to the landed tiles in shared memory (the activated tensor is never stored)."""
+        sc = _addr(in_stats, 2 * 64) if in_stats is not None else None
+        sh = _addr(in_stats, 3 * 64) if in_stats is not None else None
         partials = None
         if bn is not None:
             nparts = self.L.sarssl_conv3x3_tc_grid(B, H, W)
             partials = torch.empty(nparts * 128, dtype=torch.float32, device=self.dev)
-        self._ok(self.L.sarssl_conv3x3_tc(ptr(x), ptr(wpacked), ptr(out), ptr(partials), B, H, W, self.stream), "conv3x3_tc")
+        self._ok(self.L.sarssl_conv3x3_tc(ptr(x), ptr(wpacked), ptr(out), ptr(partials), sc, sh, B, H, W, self.stream), "conv3x3_tc")
         self.tc_launches += 1
         if bn is None:
             return None
@@ -235,8 +238,11 @@ class KernelSet:
                                                   ptr(stats), self.stream), "batchnorm_finalize")
         return stats
 
-    def conv3x3_wgrad_tc(self, dy, x, dwpacked, B, H, W):
-        self._ok(self.L.sarssl_conv3x3_wgrad_tc(ptr(dy), ptr(x), ptr(dwpacked), 0, B, H, W, ptr(self.ws), self.ws.numel(), self.stream), "conv3x3_wgrad_tc")
+    def conv3x3_wgrad_tc(self, dy, x, dwpacked, B, H, W, in_stats=None):
+        sc = _addr(in_stats, 2 * 64) if in_stats is not None else None
+        sh = _addr(in_stats, 3 * 64) if in_stats is not None else None
+        self._ok(self.L.sarssl_conv3x3_wgrad_tc(ptr(dy), ptr(x), sc, sh, ptr(dwpacked), 0, B, H, W, ptr(self.ws), self.ws.numel(), self.stream),
+                 "conv3x3_wgrad_tc")
         self.launches += 1
         self.tc_launches += 1
 

@@ -92,6 +92,36 @@ def test_tc_conv3x3_wgrad_vs_torch_fp32(B, H, W):
     assert rel(out, pack(w.grad)) < 1e-4, rel(out, pack(w.grad))
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 1, 64), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 70, 64), (1, 5, 130), (8, 256, 256)])
+def test_tc_conv3x3_fused_input_batchnorm_relu_is_bit_identical_to_the_materialised_route(B, H, W):
+    """in_stats: the operand relu(scale * y + shift) is produced from the landed TMA boxes in shared memory (transform warps).  Forward conv,
+    its fused output statistics and the weight gradient must equal - bit for bit - what the same kernels give on a materialised z (the
+    arithmetic and rounding of bn_act_fwd_kernel), including the zero padding at the image borders (out-of-image pixels stay zero, they do
+    NOT become relu(shift)) and ragged widths."""
+    k = KernelSet(DEV, torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(B * 11 + H + W)
+    y = torch.randn(B, H, W, 64, device=DEV, generator=g).bfloat16()
+    scale, shift = torch.rand(64, device=DEV, generator=g) + 0.5, torch.randn(64, device=DEV, generator=g) * 0.5 + 0.3     # shift > 0 mostly: padding bugs show
+    stats = torch.cat([torch.zeros(128, device=DEV), scale, shift])
+    z = torch.empty_like(y)
+    k.bn_act_fwd(y, stats, 1, z, B * H * W, 64)
+    wp = (torch.randn(64, 9, 64, device=DEV, generator=g) / 24).bfloat16()
+    bn = lambda: (torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV), torch.zeros(64, device=DEV), torch.ones(64, device=DEV),
+                  torch.zeros((), dtype=torch.int64, device=DEV))
+    out_a, out_b = torch.empty_like(y), torch.empty_like(y)
+    st_a = k.conv3x3_tc(z, wp, out_a, B, H, W, bn=bn())
+    st_b = k.conv3x3_tc(y, wp, out_b, B, H, W, bn=bn(), in_stats=stats)
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b) and torch.equal(st_a[:128], st_b[:128])
+    assert rel(out_b.float(), conv_ref_fp32(z, wp)) < 3e-3
+    dy = (torch.randn(B, H, W, 64, device=DEV, generator=g) / (B * H * W) ** 0.5).bfloat16()
+    dw_a, dw_b = torch.empty(64, 9, 64, device=DEV), torch.empty(64, 9, 64, device=DEV)
+    k.conv3x3_wgrad_tc(dy, z, dw_a, B, H, W)
+    k.conv3x3_wgrad_tc(dy, y, dw_b, B, H, W, in_stats=stats)
+    torch.cuda.synchronize()
+    assert torch.equal(dw_a, dw_b)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,mode", [(2, 16, 256, 0), (3, 5, 130, 0), (1, 3, 37, 0), (2, 16, 256, 1), (2, 16, 256, 2), (2, 7, 64, 3), (16, 64, 256, 1)])
 def test_stem_pointwise_wgrad_vs_torch(dtype, B, H, W, mode):
