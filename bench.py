@@ -274,7 +274,8 @@ def run_ours(args):
     learner = STFTLearner(model, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
     learner.device = dev
     if world > 1:
-        learner.mul_gpu()
+        with stdout_to_stderr():
+            learner.mul_gpu()
     sync = getattr(learner, "grad_sync", None)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     sig = 0.1 * torch.randn(nb, NSAMPLE, 2, device=dev, generator=g)
@@ -464,6 +465,21 @@ FT_NT = 64                                  # TDOA fine-tuning uses 1.04 s clips
 FT_NSAMPLE = (FT_NT + 1) * 256
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on STDOUT when the communicator is created (NCCL_DEBUG=VERSION on these boxes); the bench's stdout is
+    one JSON line, so file descriptor 1 points at stderr while the communicator comes up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def make_timed(world, dev):
     import torch
     import torch.distributed as dist
@@ -507,7 +523,8 @@ def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, 
     L = STFTLearner(model, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
     L.device = dev
     if world > 1:
-        L.mul_gpu()
+        with stdout_to_stderr():
+            L.mul_gpu()
     sync = getattr(L, "grad_sync", None)
     sig = 0.1 * torch.randn(nb, (nt + 1) * 256, 2, device=dev)
     host_sig = sig.cpu().pin_memory()
@@ -581,7 +598,8 @@ def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype):
     L = STFTLearner(model, 512, 0.5, 512, 1, 16000, task="TDOA")
     L.device = dev
     if world > 1:
-        L.mul_gpu()
+        with stdout_to_stderr():
+            L.mul_gpu()
     sync = getattr(L, "grad_sync", None)
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     sig = 0.1 * torch.randn(nb, FT_NSAMPLE, 2, device=dev, generator=g)

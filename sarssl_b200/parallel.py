@@ -50,7 +50,10 @@ class GradientSync:
         self.pending = {name for name, _, _ in self.buckets}
         self.stream = None
         self.defer = False                  # True while accumulating micro-batches: backward must not start the exchange yet
-        if backend == "nccl":
+        if backend == "nccl" and lib().sarssl_comm_world_size() == self.world:
+            # the library's communicator is process-global (one process per GPU): a second model / learner in the same process shares it
+            self.stream = torch.cuda.Stream(device=model.store.flat.device)
+        elif backend == "nccl":
             L = lib()
             nbytes = L.sarssl_comm_unique_id_bytes()
             buf = (C.c_ubyte * nbytes)()

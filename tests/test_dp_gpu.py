@@ -74,6 +74,23 @@ def _worker(rank, world, port, out):
         ref = [random.sample(range(nt), nt // 2) + [random.randint(0, 1)] for _ in range(nb * world)]
         got = torch.cat(masks).cpu().tolist()
         assert got == [r[:-1] for r in ref]
+        # a second model / learner in the same process shares the library's process-global communicator (bench.py's sub-runs do this)
+        m2 = SARSSL(sig_shape=(256, nt, 2, 2), device=dev)
+        m2.load_state_dict(O.synthetic_state_dict(7))
+        m2.to(dev)
+        m2.set_dropout(0.0)
+        m2.train()
+        L2 = STFTLearner(m2, 512, 0.5, 512, 1, 16000)
+        L2.device = dev
+        L2.mul_gpu()
+        x, = L2.data_preprocess(sig.to(dev))
+        random.seed(400000001)
+        l3, _, _ = m2(x)
+        l3.backward()
+        L2.grad_sync.all_reduce()
+        torch.cuda.synchronize()
+        err2 = float((m2.store.grad - want).norm() / want.norm())
+        assert err2 < 1e-5, err2
         keep.close()
         out[rank] = 1
     finally:
