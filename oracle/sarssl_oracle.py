@@ -317,7 +317,10 @@ def downstream_forward(x, sd, embed_use="spec_spat", training=True, dropout_p=0.
     e_spat = embed_encoder(tokens, sd, "spat_encoder", SPAT_LAYERS, NHEAD, bn, drop)
     e = {"spec_spat": torch.cat([e_spec, e_spat], dim=2), "spec": e_spec + 0.0, "spat": e_spat + 0.0}[embed_use]
     pooled = e.mean(dim=1)
-    pred = _lin(_ln(pooled, sd, "mlp_head.0"), sd, "mlp_head.1")
+    if "joint_head.0.weight" in sd:                # dlabel > 1 (model.py:501-507,709-710)
+        pred = _lin(F.relu(_lin(_ln(pooled, sd, "joint_head.0"), sd, "joint_head.1")), sd, "joint_head.3")
+    else:
+        pred = _lin(_ln(pooled, sd, "mlp_head.0"), sd, "mlp_head.1")
     return pred, pooled
 
 
@@ -377,7 +380,7 @@ def positional_table(d_model, max_len=10000):
     return pe.unsqueeze(0)
 
 
-def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False, head="mlp", prefix="", nmic_pair=0, factor=1):
+def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False, head="mlp", prefix="", nmic_pair=0, factor=1, dlabel=1):
     """[(key, shape, kind)] for the 214 state_dict entries of SARSSL(pretrain=True).
     frozen=True: SARSSL(pretrain=False, pretrain_frozen_encoder=True) - three decoders instead of one (model.py:470-481; the spatial
     decoder is built with the SPECTRAL width, as the reference does).
@@ -436,9 +439,13 @@ def state_dict_spec(nf=256, pretrain=True, dembed_ds=768, frozen=False, head="ml
         decoder("spec_spat_decoder", 768)
         decoder("spec_decoder", 512)
         decoder("spat_decoder", 512)
-    elif head == "mlp":       # downstream head (model.py:495-500)
+    elif head == "mlp" and dlabel == 1:       # downstream head (model.py:495-500)
         out.extend([("mlp_head.0.weight", (dembed_ds,), "g"), ("mlp_head.0.bias", (dembed_ds,), "b"),
                     ("mlp_head.1.weight", (1, dembed_ds), "w"), ("mlp_head.1.bias", (1,), "b")])
+    elif head == "mlp":                       # joint_head (model.py:501-507)
+        d = dembed_ds
+        out.extend([("joint_head.0.weight", (d,), "g"), ("joint_head.0.bias", (d,), "b"), ("joint_head.1.weight", (d, d), "w"), ("joint_head.1.bias", (d,), "b"),
+                    ("joint_head.3.weight", (dlabel, d), "w"), ("joint_head.3.bias", (dlabel,), "b")])
     out = [(prefix + k, shp, kind) for k, shp, kind in out]
     if nmic_pair:             # SARSSL_MultiCH.head_mch (model.py:807-812): LayerNorm, Linear, ReLU, Linear over the concatenated pair embeddings
         d = 256 * nmic_pair

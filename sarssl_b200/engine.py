@@ -272,7 +272,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ downstream branch
     def forward_downstream(self, patches, embed_use, training, want_grad, head="mlp"):
         """model.py:667-719 (pretrain=False): both encoders on the UN-masked input, concatenate, mean over time, then the head:
-        'mlp' = LayerNorm + Linear(dembed, 1) (dlabel 1), '' = none, an integer nmic_pair = SARSSL_MultiCH.head_mch (model.py:793-821).
+        'mlp' = LayerNorm + Linear(dembed, 1) (dlabel 1), 'joint' = joint_head (dlabel > 1, model.py:501-507), '' = none, an integer nmic_pair =
+        SARSSL_MultiCH.head_mch (model.py:793-821).
         Returns (pred fp32, pooled (B, dembed) fp32, saved)."""
         k, k32, st = self.k, self.k32, self.store
         B, T, F = patches.shape[:3]
@@ -302,20 +303,20 @@ class Engine:
             pred = torch.empty(B, 1, **f32)
             k32.linear(hn, st.p("mlp_head.1.weight"), pred, B, 1, Dd, bias=st.p("mlp_head.1.bias"))
             hs = dict(hn=hn, hmean=mean, hrstd=rstd)
-        else:                                        # SARSSL_MultiCH.head_mch over the pairs of an item                    model.py:807-820
-            P = int(head)
+        else:   # LayerNorm, Linear, ReLU, Linear: SARSSL_MultiCH.head_mch over the P pairs of an item (model.py:807-820) or joint_head, P = 1 (model.py:501-507)
+            hk, P = ("joint_head", 1) if head == "joint" else ("head_mch", int(head))
             if B % P:
                 raise _lib.SarsslError(f"SARSSL_MultiCH: batch of {B} clips is not a multiple of nmic_pair = {P}")
             nbm, Dh = B // P, P * Dd
             emb = pooled.view(nbm, Dh)
-            factor = st.shapes["head_mch.3.weight"][0]
+            factor = st.shapes[hk + ".3.weight"][0]
             hn, mean, rstd = torch.empty_like(emb), torch.empty(nbm, **f32), torch.empty(nbm, **f32)
-            k32.layernorm_fwd(emb, Dh, st.p("head_mch.0.weight"), st.p("head_mch.0.bias"), hn, Dh, mean, rstd, nbm, Dh)
+            k32.layernorm_fwd(emb, Dh, st.p(hk + ".0.weight"), st.p(hk + ".0.bias"), hn, Dh, mean, rstd, nbm, Dh)
             h1 = torch.empty(nbm, Dh, **f32)
-            k32.linear(hn, st.p("head_mch.1.weight"), h1, nbm, Dh, Dh, bias=st.p("head_mch.1.bias"), act=ACT_RELU)
+            k32.linear(hn, st.p(hk + ".1.weight"), h1, nbm, Dh, Dh, bias=st.p(hk + ".1.bias"), act=ACT_RELU)
             pred = torch.empty(nbm, factor, **f32)
-            k32.linear(h1, st.p("head_mch.3.weight"), pred, nbm, factor, Dh, bias=st.p("head_mch.3.bias"))
-            hs = dict(hn=hn, hmean=mean, hrstd=rstd, h1=h1, nbm=nbm, Dh=Dh, factor=factor)
+            k32.linear(h1, st.p(hk + ".3.weight"), pred, nbm, factor, Dh, bias=st.p(hk + ".3.bias"))
+            hs = dict(hn=hn, hmean=mean, hrstd=rstd, h1=h1, nbm=nbm, Dh=Dh, factor=factor, hk=hk)
         if want_grad:
             sv.update(pooled=pooled, col=col, Dd=Dd, head=head, **hs)
         return pred, pooled, sv
@@ -340,21 +341,21 @@ class Engine:
             k32.layernorm_bwd(dhn, Dd, sv["pooled"], Dd, sv["hmean"], sv["hrstd"], st.p("mlp_head.0.weight"), None, dpool, st.g("mlp_head.0.weight"),
                               st.g("mlp_head.0.bias"), B, Dd)
         else:
-            nbm, Dh, factor = sv["nbm"], sv["Dh"], sv["factor"]
+            nbm, Dh, factor, hk = sv["nbm"], sv["Dh"], sv["factor"], sv["hk"]
             ones = torch.ones(1, 1, device=self.dev)
             dpred = dpred.reshape(nbm, factor).contiguous()
-            k32.linear_wgrad(dpred, sv["h1"], st.g("head_mch.3.weight"), nbm, factor, Dh)
-            k32.gemm(dpred, ones, st.g("head_mch.3.bias").view(factor, 1), factor, 1, nbm, (1, factor), (1, 0), 1, accumulate=True)     # column sums of dpred
+            k32.linear_wgrad(dpred, sv["h1"], st.g(hk + ".3.weight"), nbm, factor, Dh)
+            k32.gemm(dpred, ones, st.g(hk + ".3.bias").view(factor, 1), factor, 1, nbm, (1, factor), (1, 0), 1, accumulate=True)     # column sums of dpred
             dh1 = torch.empty(nbm, Dh, **f32)
-            k32.linear_dgrad(dpred, st.p("head_mch.3.weight"), dh1, nbm, factor, Dh)
+            k32.linear_dgrad(dpred, st.p(hk + ".3.weight"), dh1, nbm, factor, Dh)
             k32.relu_bwd(dh1, sv["h1"], dh1, nbm * Dh)
-            k32.linear_wgrad(dh1, sv["hn"], st.g("head_mch.1.weight"), nbm, Dh, Dh)
-            k32.gemm(dh1, ones, st.g("head_mch.1.bias").view(Dh, 1), Dh, 1, nbm, (1, Dh), (1, 0), 1, accumulate=True)
+            k32.linear_wgrad(dh1, sv["hn"], st.g(hk + ".1.weight"), nbm, Dh, Dh)
+            k32.gemm(dh1, ones, st.g(hk + ".1.bias").view(Dh, 1), Dh, 1, nbm, (1, Dh), (1, 0), 1, accumulate=True)
             dhn = torch.empty(nbm, Dh, **f32)
-            k32.linear_dgrad(dh1, st.p("head_mch.1.weight"), dhn, nbm, Dh, Dh)
+            k32.linear_dgrad(dh1, st.p(hk + ".1.weight"), dhn, nbm, Dh, Dh)
             dpool = torch.empty(nbm, Dh, **f32)
-            k32.layernorm_bwd(dhn, Dh, sv["pooled"].view(nbm, Dh), Dh, sv["hmean"], sv["hrstd"], st.p("head_mch.0.weight"), None, dpool,
-                              st.g("head_mch.0.weight"), st.g("head_mch.0.bias"), nbm, Dh)
+            k32.layernorm_bwd(dhn, Dh, sv["pooled"].view(nbm, Dh), Dh, sv["hmean"], sv["hrstd"], st.p(hk + ".0.weight"), None, dpool,
+                              st.g(hk + ".0.weight"), st.g(hk + ".0.bias"), nbm, Dh)
             dpool = dpool.view(B, Dd)
         dcat = k.empty(M, Dc)
         k.mean_pool_bwd(dpool, dcat, Dc, B, T, Dd, dx_off=col)

@@ -146,9 +146,10 @@ class SARSSL(nn.Module):
         if use_cls:
             raise _lib.SarsslError("sarssl_b200.SARSSL implements pretrain=True, pretrain_frozen_encoder=True and the downstream branch; use_cls is not built")
         pretrain_frozen_encoder = bool(pretrain_frozen_encoder) and not pretrain            # model.py:463,469: `pretrain` wins
-        if not pretrain and not pretrain_frozen_encoder and (downstream_head not in ("mlp", "") or downstream_dlabel != 1 or downstream_token != "all" or
+        if not pretrain and not pretrain_frozen_encoder and (downstream_head not in ("mlp", "") or downstream_dlabel < 1 or downstream_token != "all" or
                                                              downstream_embed not in ("spec_spat", "spec", "spat")):
-            raise _lib.SarsslError("downstream branch: heads 'mlp' / '' (none), dlabel 1, token 'all', embed in {spec_spat, spec, spat}")
+            raise _lib.SarsslError("downstream branch: heads 'mlp' (mlp_head for dlabel 1, joint_head for dlabel > 1) / '' (none), token 'all', "
+                                   "embed in {spec_spat, spec, spat}; the crnn_* heads of model.py:508-517 are commented out in the reference too")
         if tuple(patch_shape) != (nf, 1) or patch_mode != "T" or nreim != 2 or nmic != 2:
             raise _lib.SarsslError("only frame patches (patch_shape == (nf, 1), patch_mode 'T') of 2-microphone re/im spectrograms are on the hot path")
         npatch = nt
@@ -159,9 +160,11 @@ class SARSSL(nn.Module):
         self.device = torch.device(device if str(device) != "cpu" else ("cuda" if torch.cuda.is_available() else "cpu"))
         self.embed_use4ds = downstream_embed
         dembed_ds = {"spec_spat": 768, "spec": 512, "spat": 256}.get(downstream_embed, 768)
-        self.downstream_head = _nmic_pair if _nmic_pair else downstream_head         # an integer selects SARSSL_MultiCH.head_mch in the engine
+        # what the engine runs after the time-mean pooling: 'mlp', 'joint' (dlabel > 1), '' or an integer (SARSSL_MultiCH.head_mch over that many pairs)
+        self.downstream_head = _nmic_pair if _nmic_pair else ("joint" if (downstream_head == "mlp" and downstream_dlabel > 1) else downstream_head)
+        self.downstream_dlabel = downstream_dlabel
         self.store = ParamStore(self, nf=nf, device=self.device, pretrain=pretrain, dembed_ds=dembed_ds, frozen=pretrain_frozen_encoder,
-                                head=downstream_head, nmic_pair=_nmic_pair, factor=_factor, tree_prefix=_tree_prefix)
+                                head=downstream_head, nmic_pair=_nmic_pair, factor=_factor, tree_prefix=_tree_prefix, dlabel=downstream_dlabel)
         # the rest are plain attributes (not sub-modules) so that state_dict() holds exactly the reference's 214 entries
         object.__setattr__(self, "patch_split", PatchSplit(patch_shape=patch_shape, f_first=False))
         object.__setattr__(self, "patch_recover", PatchRecover(output_shape=(nf, nt), patch_shape=patch_shape, f_first=False))

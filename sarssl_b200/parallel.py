@@ -24,7 +24,7 @@ def bucket_ranges(store):
         lo = min(store.offsets[k][0] for k in ks)
         hi = max(store.offsets[k][0] + (store.offsets[k][1] + 3) // 4 * 4 for k in ks)
         return lo, hi - lo
-    out = [("decoder",) + span(["decoder.", "mlp_head.", "head_mch.", "spec_spat_decoder.", "spec_decoder.", "spat_decoder."]), ("spec_encoder",) + span(["spec_encoder."]),
+    out = [("decoder",) + span(["decoder.", "mlp_head.", "joint_head.", "head_mch.", "spec_spat_decoder.", "spec_decoder.", "spat_decoder."]), ("spec_encoder",) + span(["spec_encoder."]),
            ("spat_blocks_1_2",) + span(["spat_encoder.embed.layers.1.", "spat_encoder.embed.layers.2."]),
            ("spat_stem_block_0",) + span(["spat_encoder.patch_embed.", "spat_encoder.embed.layers.0."])]
     covered = sum(n for _, _, n in out)

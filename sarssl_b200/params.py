@@ -15,7 +15,7 @@ import torch.nn as nn
 SPEC_D, SPAT_D, SPEC_LAYERS, SPAT_LAYERS, NHEAD, CNN_CH, DW_K = 512, 256, 1, 3, 4, 64, 31
 
 
-def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=False, head="mlp", nmic_pair=0, factor=1):
+def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=False, head="mlp", nmic_pair=0, factor=1, dlabel=1):
     """[(key, shape, kind)] in the reference's state_dict order.  pretrain: one `decoder`; frozen (pretrain_frozen_encoder, model.py:470-481):
     `spec_spat_decoder`, `spec_decoder`, `spat_decoder` (the last one built with the spectral width, as the reference does); otherwise the
     downstream head (`mlp_head`, or nothing for head '').  kind: conv / lin_x (xavier Linear wrapper,
@@ -73,9 +73,13 @@ def state_dict_layout(nf=256, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=F
         decoder("spec_spat_decoder", SPEC_D + SPAT_D)
         decoder("spec_decoder", SPEC_D)
         decoder("spat_decoder", SPEC_D)
-    elif head == "mlp":        # downstream head: nn.Sequential(LayerNorm(dembed_ds), Linear(dembed_ds, 1))   model.py:495-500
+    elif head == "mlp" and dlabel == 1:        # downstream head: nn.Sequential(LayerNorm(dembed_ds), Linear(dembed_ds, 1))   model.py:495-500
         out.extend([("mlp_head.0.weight", (dembed_ds,), "gain"), ("mlp_head.0.bias", (dembed_ds,), "beta"),
                     ("mlp_head.1.weight", (1, dembed_ds), "lin_k"), ("mlp_head.1.bias", (1,), "bias_k")])
+    elif head == "mlp":                        # joint_head: LayerNorm, Linear(d, d), ReLU, Linear(d, dlabel)               model.py:501-507
+        d = dembed_ds
+        out.extend([("joint_head.0.weight", (d,), "gain"), ("joint_head.0.bias", (d,), "beta"), ("joint_head.1.weight", (d, d), "lin_k"),
+                    ("joint_head.1.bias", (d,), "bias_k"), ("joint_head.3.weight", (dlabel, d), "lin_k"), ("joint_head.3.bias", (dlabel,), "bias_k")])
     if nmic_pair:              # SARSSL_MultiCH.head_mch: LayerNorm, Linear, ReLU, Linear over the concatenated pair embeddings   model.py:807-812
         d = SPAT_D * nmic_pair
         out.extend([("head_mch.0.weight", (d,), "gain"), ("head_mch.0.bias", (d,), "beta"), ("head_mch.1.weight", (d, d), "lin_k"),
@@ -130,10 +134,10 @@ class ParamStore:
     """Builds the tree under `root`, owns the arenas, and resolves keys to tensors for the engine."""
 
     def __init__(self, root, nf=256, device="cpu", seed_generator=None, pretrain=True, dembed_ds=SPEC_D + SPAT_D, frozen=False, head="mlp",
-                 nmic_pair=0, factor=1, tree_prefix=""):
+                 nmic_pair=0, factor=1, tree_prefix="", dlabel=1):
         """tree_prefix: where the encoder / decoder / mlp_head keys hang in the module tree (SARSSL_MultiCH keeps them under `model_sch.`, so its
         state_dict reads `model_sch.spec_encoder...` like the reference's); the engine-facing keys stay un-prefixed."""
-        self.layout = state_dict_layout(nf, pretrain, dembed_ds, frozen, head, nmic_pair, factor)
+        self.layout = state_dict_layout(nf, pretrain, dembed_ds, frozen, head, nmic_pair, factor, dlabel)
         self.tree_prefix = tree_prefix
         self.shapes = {k: tuple(s) for k, s, _ in self.layout}
         self.kinds = {k: kind for k, _, kind in self.layout}

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--nt", type=int, default=256, help="frames per clip (1024 = the long-clip configuration)")
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--out", default=None)
     ap.add_argument("--graph", action="store_true", help="replay the step as a CUDA graph when the engine supports it")
@@ -33,7 +34,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     torch.manual_seed(1)
-    model = SARSSL(sig_shape=(256, 256, 2, 2), device=dev)
+    model = SARSSL(sig_shape=(256, args.nt, 2, 2), device=dev)
     model.to(dev)
     model.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     model.set_dropout(0.1)
@@ -41,7 +42,7 @@ def main():
     model.train()
     learner = STFTLearner(model, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=1, fs=16000, task=None, ch_mode="M")
     learner.device = dev
-    sig = 0.1 * torch.randn(args.batch, 65792, 2, device=dev)
+    sig = 0.1 * torch.randn(args.batch, (args.nt + 1) * 256, 2, device=dev)
     opt = FusedAdam(model, lr=1e-3)
 
     def step():

@@ -104,3 +104,31 @@ def test_mcconformer_backward_matches_oracle_autograd():
     gmax = max(float(sd[k].grad.norm()) for k in names)
     worst = max((float((m.store.p(k).grad.cpu().double() - sd[k].grad.double()).norm() / (sd[k].grad.double().norm() + 1e-4 * gmax)), k) for k in names)
     assert worst[0] < 1e-2, worst
+
+
+def test_joint_head_dlabel3_matches_reference_and_oracle_autograd():
+    """SARSSL(pretrain=False, downstream_dlabel=3): joint_head = LayerNorm, Linear, ReLU, Linear (model.py:501-507,709-710).  Forward against the
+    real reference's output (fixture), gradients against oracle autograd."""
+    g = np.load(os.path.join(GOLDEN, "joint_head_nt16_b2.npz"))
+    nb, nt, dl = int(g["nb"]), int(g["nt"]), int(g["dlabel"])
+    sd = O.synthetic_state_dict(int(g["sd_seed"]), pretrain=False, dembed_ds=768, dlabel=dl)
+    m = SARSSL(sig_shape=(256, nt, 2, 2), pretrain=False, downstream_dlabel=dl, device=DEV)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m.to(DEV)
+    m.set_dropout(0.0)
+    m.train()
+    x = O.preprocess(O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=int(g["sig_seed"])))
+    pred, emb = m(x.to(DEV))
+    assert pred.shape == (nb, dl) and np.allclose(pred.detach().cpu().numpy(), g["pred"], rtol=2e-4, atol=2e-4)
+    assert np.allclose(emb.cpu().numpy(), g["embed"], rtol=2e-4, atol=2e-4)
+    tar = torch.linspace(-1, 1, nb * dl).reshape(nb, dl)
+    torch.nn.functional.mse_loss(pred, tar.to(DEV)).backward()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    po, _ = O.downstream_forward(x, sd, "spec_spat", training=True)
+    torch.nn.functional.mse_loss(po, tar).backward()
+    gmax = max(float(sd[k].grad.norm()) for k in names)
+    worst = max((float((m.store.p(k).grad.cpu().double() - sd[k].grad.double()).norm() / (sd[k].grad.double().norm() + 1e-4 * gmax)), k) for k in names)
+    assert worst[0] < 1e-2, worst
