@@ -69,6 +69,12 @@ int sarssl_stft_spectrum(const float* sig, float* spec, int nb, long long nsampl
 size_t sarssl_stft_workspace_bytes(int nb, long long nsample, int nch, int generic);
 int sarssl_stft_frontend(const float* sig, float* patches, int nb, long long nsample, int nch, int win_len, int hop, int nfft,
                          float eps, int force_generic, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* The variants of data_preprocess off the pre-training hot path (three-kernel generic route; workspace: generic = 1):
+ *   all_pairs != 0: ch_mode 'MM' - every channel pair a < b in AddChToBatch's order (utils_module.py:136-143), nb * nch (nch - 1) / 2 output items;
+ *   bins [first_bin, first_bin + nbins) of the 257: fre_used_ratio 1 -> (1, 256), 0.5 -> (0, 128) (learner.py:514-517).
+ *   patches (items, nt, nbins, 2, 2). */
+int sarssl_stft_frontend_ex(const float* sig, float* patches, int nb, long long nsample, int nch, int win_len, int hop, int nfft, float eps,
+                            int all_pairs, int first_bin, int nbins, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* Synchronises `stream`; *flag_host != 0 means the fused kernel's clip rendezvous timed out (never expected) in some launch
  * on this workspace: the flag is sticky (only a fresh zeroed workspace clears it), so one check per epoch covers every step.
  * The workspace must be zero-initialised when it is first handed to sarssl_stft_frontend. */

@@ -86,7 +86,7 @@ def add_ch_to_batch(x, ch_mode="M"):
     return out.reshape((nb * len(pairs), 2) + tuple(x.shape[2:])).contiguous()
 
 
-def preprocess(signal, win_len=512, win_shift_ratio=0.5, nfft=512, eps=1e-6, ch_mode="M"):
+def preprocess(signal, win_len=512, win_shift_ratio=0.5, nfft=512, eps=1e-6, ch_mode="M", fre_used_ratio=1):
     """(nb, nsample, nch) f32 -> (nb*(nch-1), 2, nfft/2, nt, 2) f32.
 
     STFT, divide every channel by (mean over all 257 x nt bins of |X_ch0| + eps) (learner.py:539-542),
@@ -95,7 +95,8 @@ def preprocess(signal, win_len=512, win_shift_ratio=0.5, nfft=512, eps=1e-6, ch_
     mean_mag = X[:, 0].abs().reshape(X.shape[0], -1).mean(dim=1)
     X = X / (mean_mag + eps)[:, None, None, None]
     X = add_ch_to_batch(X, ch_mode)
-    return torch.view_as_real(X)[:, :, 1:nfft // 2 + 1].contiguous()
+    bins = slice(1, nfft // 2 + 1) if fre_used_ratio == 1 else slice(0, int(nfft / 2 * fre_used_ratio))     # learner.py:514-517
+    return torch.view_as_real(X)[:, :, bins].contiguous()
 
 
 # ----------------------------------------------------------------------------------------------

@@ -422,6 +422,31 @@ __global__ void pair_normalize_kernel(const float2* __restrict__ spec, const flo
     }
 }
 
+// generalised pairing for the off-hot-path variants of data_preprocess: ch_mode 'MM' (all channel pairs a < b in AddChToBatch's order,
+// utils_module.py:136-143) and fre_used_ratio 0.5 (bins 0..127, learner.py:516-517).  spec [nb][nt][257][nch] -> [(b, pair)][nt][nbins] float4
+__global__ void pair_normalize_ex_kernel(const float2* __restrict__ spec, const float* __restrict__ scale, float4* __restrict__ out, int nb, int nt,
+                                         int nch, int all_pairs, int first_bin, int nbins) {
+    const int npair = all_pairs ? nch * (nch - 1) / 2 : nch - 1;
+    const size_t total = (size_t)nb * npair * nt * nbins;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % nbins);
+        size_t r = i / nbins;
+        const int t = (int)(r % nt); r /= nt;
+        int pr = (int)(r % npair);
+        const int b = (int)(r / npair);
+        int ca = 0, cb = pr + 1;
+        if (all_pairs) {                                             // pairs (0,1) (0,2) .. (0,nch-1) (1,2) ..
+            ca = 0;
+            while (pr >= nch - 1 - ca) { pr -= nch - 1 - ca; ++ca; }
+            cb = ca + 1 + pr;
+        }
+        const float s = scale[b];
+        const float2* row = spec + (((size_t)b * nt + t) * kBins + (first_bin + f)) * nch;
+        const float2 a = row[ca], c = row[cb];
+        st_stream_f4(out + i, make_float4(a.x * s, c.x * s, a.y * s, c.y * s));
+    }
+}
+
 static int items_per_clip(int nt) { return (nt + kFPI - 1) / kFPI; }
 
 // Clears the work-queue head and the per-clip arrival counters; counters[1], the rendezvous-timeout flag, is STICKY: it is only ever
@@ -562,6 +587,37 @@ extern "C" int sarssl_stft_frontend(const float* sig, float* patches, int nb, lo
     const size_t total = (size_t)nb * (nch - 1) * nt * 256;
     const int blocks = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
     pair_normalize_kernel<<<blocks, 256, 0, stream>>>(spec, scale, reinterpret_cast<float4*>(patches), nb, nt, nch);
+    SARSSL_LAUNCH_CHECK();
+    return SARSSL_OK;
+}
+
+extern "C" int sarssl_stft_frontend_ex(const float* sig, float* patches, int nb, long long nsample, int nch, int win_len, int hop, int nfft, float eps,
+                                       int all_pairs, int first_bin, int nbins, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    int rc = check_stft_args(sig, patches, nb, nsample, nch, win_len, hop, nfft);
+    if (rc) return rc;
+    SARSSL_CHECK_ARG(nch >= 2 && workspace != nullptr, "stft_frontend_ex: needs at least 2 microphones and a workspace");
+    SARSSL_CHECK_ARG(first_bin >= 0 && nbins > 0 && first_bin + nbins <= kBins, "stft_frontend_ex: bins [%d, %d) outside [0, 257)", first_bin, first_bin + nbins);
+    if (workspace_bytes < sarssl_stft_workspace_bytes(nb, nsample, nch, 1)) {
+        set_last_error("stft_frontend_ex: workspace %zu < required %zu (query with generic=1)", workspace_bytes, sarssl_stft_workspace_bytes(nb, nsample, nch, 1));
+        return SARSSL_ERR_WORKSPACE;
+    }
+    SARSSL_CHECK_ARG(aligned16(sig) && aligned16(patches) && aligned16(workspace), "stft_frontend_ex: buffers must be 16-byte aligned");
+    const int nt = sarssl_stft_num_frames(nsample, win_len, hop), ipc = items_per_clip(nt), npair_ch = (nch + 1) / 2;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    size_t off = 256 + ((size_t)nb * sizeof(unsigned) + 255) / 256 * 256;
+    float* partials = reinterpret_cast<float*>(ws + off);
+    off += ((size_t)nb * nt * sizeof(unsigned long long) + 255) / 256 * 256;
+    float* scale = reinterpret_cast<float*>(ws + off);
+    off += ((size_t)nb * sizeof(unsigned long long) + 255) / 256 * 256;
+    float2* spec = reinterpret_cast<float2*>(ws + off);
+    stft_spectrum_kernel<<<nb * ipc * npair_ch, kThreads, 0, stream>>>(sig, spec, partials, nb, nsample, nch, nt, ipc, npair_ch);
+    SARSSL_LAUNCH_CHECK();
+    clip_scale_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(partials, scale, nb, ipc, nt, eps);
+    SARSSL_LAUNCH_CHECK();
+    const int npair = all_pairs ? nch * (nch - 1) / 2 : nch - 1;
+    const size_t total = (size_t)nb * npair * nt * nbins;
+    const int blocks = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
+    pair_normalize_ex_kernel<<<blocks, 256, 0, stream>>>(spec, scale, reinterpret_cast<float4*>(patches), nb, nt, nch, all_pairs, first_bin, nbins);
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -179,15 +179,17 @@ class STFTLearner(Learner):
 
     def __init__(self, model, win_len, win_shift_ratio, nfft, fre_used_ratio, fs, mel_scale=False, task=None, ch_mode="M"):
         super().__init__(model)
-        if mel_scale or fre_used_ratio != 1 or ch_mode != "M":
-            raise SarsslError("STFTLearner: only mel_scale=False, fre_used_ratio=1, ch_mode='M' (the pre-training configuration, "
-                              "run_pretrain.py:67-72,208) are on the hot path")
+        if mel_scale:
+            raise SarsslError("STFTLearner: mel_scale=True (torchaudio MelScale on the CPU, learner.py:506-513,548) is not built")
+        if fre_used_ratio not in (1, 0.5) or ch_mode not in ("M", "MM"):
+            raise SarsslError("STFTLearner: fre_used_ratio in {1, 0.5} and ch_mode in {'M', 'MM'} (learner.py:514-520, utils_module.py:124-148)")
+        self.fre_used_ratio = fre_used_ratio
         self.win_len, self.win_shift_ratio, self.nfft, self.fs = win_len, win_shift_ratio, nfft, fs
         self.ch_mode, self.task = ch_mode, task
         from .modules import STFT, ISTFT
         self.stft = STFT(win_len=win_len, win_shift_ratio=win_shift_ratio, nfft=nfft)
         self.istft = ISTFT(win_len=win_len, win_shift_ratio=win_shift_ratio, nfft=nfft, inv=False)
-        self.fre_range_used = range(1, int(nfft / 2 * fre_used_ratio) + 1, 1)
+        self.fre_range_used = range(1, int(nfft / 2 * fre_used_ratio) + 1, 1) if fre_used_ratio == 1 else range(0, int(nfft / 2 * fre_used_ratio), 1)
 
     def data_preprocess(self, mic_sig_batch=None, gt_batch=None, eps=1e-6):
         """learner.py:525-572.  mic_sig_batch (nb, nsample, nch) (host or device) -> [ (nb*(nch-1), 2, nf, nt, 2) f32 ].
@@ -195,7 +197,12 @@ class STFTLearner(Learner):
         data = []
         if mic_sig_batch is not None:
             sig = mic_sig_batch.to(self.device, non_blocking=True)
-            patches = ops.stft_frontend(sig, eps=eps, win_len=self.win_len, hop=int(self.win_len * self.win_shift_ratio), nfft=self.nfft)
+            if self.fre_used_ratio == 1 and (self.ch_mode == "M" or sig.shape[-1] == 2):          # the pre-training configuration: fused kernel
+                patches = ops.stft_frontend(sig, eps=eps, win_len=self.win_len, hop=int(self.win_len * self.win_shift_ratio), nfft=self.nfft)
+            else:                                                    # ch_mode 'MM' with > 2 microphones / lower half of the spectrum: generic route
+                first, nbins = (1, self.nfft // 2) if self.fre_used_ratio == 1 else (0, self.nfft // 4)
+                patches = ops.stft_frontend_ex(sig, eps=eps, win_len=self.win_len, hop=int(self.win_len * self.win_shift_ratio), nfft=self.nfft,
+                                               all_pairs=self.ch_mode == "MM", first_bin=first, nbins=nbins)
             data += [patches.permute(0, 4, 2, 1, 3)]
         if gt_batch is not None:
             gt = gt_batch[self.task].to(self.device, non_blocking=True)

@@ -70,6 +70,20 @@ def stft_frontend(signal, eps=1e-6, win_len=WIN, hop=HOP, nfft=NFFT, force_gener
     return out
 
 
+def stft_frontend_ex(signal, eps=1e-6, win_len=WIN, hop=HOP, nfft=NFFT, all_pairs=False, first_bin=1, nbins=256):
+    """data_preprocess variants off the hot path (ch_mode 'MM', fre_used_ratio 0.5): (nb, nsample, nch) -> (items, nt, nbins, 2, 2) f32."""
+    signal = _f32c(signal, "signal")
+    nb, nsample, nch = signal.shape
+    nt = num_frames(nsample, win_len, hop)
+    items = nb * (nch * (nch - 1) // 2 if all_pairs else nch - 1)
+    out = torch.empty((items, nt, nbins, 2, 2), dtype=torch.float32, device=signal.device)
+    L = lib()
+    ws = _workspace(signal.device, L.sarssl_stft_workspace_bytes(nb, nsample, nch, 1), "stft")
+    check(L.sarssl_stft_frontend_ex(ptr(signal), ptr(out), nb, nsample, nch, win_len, hop, nfft, float(eps), int(all_pairs), int(first_bin), int(nbins),
+                                    ptr(ws), ws.numel(), stream_ptr(signal.device)), "sarssl_stft_frontend_ex")
+    return out
+
+
 def stft_frontend_check(device):
     """Synchronises and raises if the fused kernel's clip rendezvous timed out in ANY launch since the workspace was created (the
     flag is sticky).  Learner checks it once per epoch, at the loss read-back."""

@@ -125,3 +125,21 @@ def test_masked_loss_bf16():
     loss, diff, grad, out2, dpred = _loss_case(4, 32, 256, 9, torch.bfloat16)
     assert abs(float(out2[0]) - float(loss)) <= 1e-4 * float(loss)
     assert rel(dpred, grad) < 1e-2                                   # bf16 rounding of the stored gradient
+
+
+@pytest.mark.parametrize("ch_mode,ratio,nch,nb,nsample", [("MM", 1, 4, 2, 9 * 256), ("M", 0.5, 3, 2, 9 * 256), ("MM", 0.5, 3, 3, 4352), ("MM", 1, 2, 2, 4352),
+                                                           ("M", 0.5, 2, 2, 65792)])
+def test_learner_preprocess_variants_match_oracle(ch_mode, ratio, nch, nb, nsample):
+    """STFTLearner.data_preprocess off the pre-training configuration: ch_mode 'MM' (all microphone pairs, utils_module.py:136-143) and
+    fre_used_ratio 0.5 (bins 0..127, learner.py:516-517); the oracle's versions are checked against the real reference in
+    tests/test_oracle_vs_reference.py."""
+    from sarssl_b200.learner import STFTLearner
+    from sarssl_b200.model import SARSSL
+    m = SARSSL(sig_shape=(256, 16, 2, 2), device=DEV)
+    L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=ratio, fs=16000, task=None, ch_mode=ch_mode)
+    L.device = DEV
+    sig = O.synthetic_waveforms(nb, nsample, nch, seed=41)
+    got, = L.data_preprocess(sig)
+    want = O.preprocess(sig, ch_mode=ch_mode, fre_used_ratio=ratio)
+    assert got.shape == want.shape
+    assert rel(got.cpu(), want) < 1e-5 and (got.cpu() - want).abs().max() <= 1e-4 * want.abs().max()

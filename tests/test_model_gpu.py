@@ -255,3 +255,36 @@ def test_long_clip_config5(nt):
     assert abs(float(loss16) - float(rl)) < 2e-2 * float(rl)
     for k, p in mb.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+
+
+def test_half_spectrum_model_nf128_matches_oracle():
+    """fre_used_ratio 0.5 (learner.py:516-517): 128-bin spectrograms, SARSSL(sig_shape=(128, nt, 2, 2)) - loss and gradients against oracle autograd."""
+    import random
+    from sarssl_b200.learner import STFTLearner
+    nb, nt, nf = 2, 16, 128
+    sd = O.synthetic_state_dict(11, nf=nf)
+    m = SARSSL(sig_shape=(nf, nt, 2, 2), patch_shape=(nf, 1), device=DEV)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m.to(DEV)
+    m.set_dropout(0.0)
+    m.train()
+    L = STFTLearner(m, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=0.5, fs=16000, task=None, ch_mode="M")
+    L.device = DEV
+    sig = O.synthetic_waveforms(nb, (nt + 1) * 256, 2, seed=8)
+    x, = L.data_preprocess(sig)
+    assert x.shape == (nb, 2, nf, nt, 2)
+    random.seed(3)
+    loss, diff, vis = m(x)
+    loss.backward()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")]
+    for k in names:
+        sd[k].requires_grad_(True)
+    random.seed(3)
+    pidx, cidx = O.draw_masks(nb, nt, nt // 2, 2)
+    lo, do_, _ = O.pretrain_forward(O.preprocess(sig, fre_used_ratio=0.5), sd, pidx, cidx, training=True)
+    lo.backward()
+    assert abs(float(loss) - float(lo)) <= 1e-4 * float(lo) and abs(float(diff) - float(do_)) <= 1e-4 * float(do_)
+    gmax = max(float(sd[k].grad.norm()) for k in names)
+    worst = max((float((m.store.p(k).grad.cpu().double() - sd[k].grad.double()).norm() / (sd[k].grad.double().norm() + 1e-4 * gmax)), k) for k in names)
+    assert worst[0] < 1e-2, worst

@@ -45,3 +45,16 @@ def test_oracle_matches_live_reference():
     for k, v in net.state_dict().items():
         if "running_" in k:
             assert torch.allclose(v, sd[k].detach(), rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("ch_mode,ratio,nch", [("MM", 1, 4), ("M", 0.5, 3), ("MM", 0.5, 3)])
+def test_preprocess_variants_match_live_reference(ch_mode, ratio, nch):
+    """data_preprocess with ch_mode 'MM' (all microphone pairs) and fre_used_ratio 0.5 (bins 0..127): oracle vs the real STFTLearner."""
+    rm, rl, _, _ = ref_shim.load_reference()
+    sig = O.synthetic_waveforms(2, 9 * 256, nch, seed=31)
+    net = rm.SARSSL(sig_shape=(256, 8, 2, 2), pretrain=True, device="cpu")
+    L = rl.STFTLearner(net, win_len=512, win_shift_ratio=0.5, nfft=512, fre_used_ratio=ratio, fs=16000, task=None, ch_mode=ch_mode)
+    L.cpu()
+    want, = L.data_preprocess(sig)
+    got = O.preprocess(sig, ch_mode=ch_mode, fre_used_ratio=ratio)
+    assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-5, atol=1e-6)
