@@ -285,7 +285,7 @@ def run_ours(args):
 
     accum = max(args.accum_steps, 1)
 
-    def step_resident():
+    def step_eager():
         """One optimizer step = `accum` micro-batches (forward + backward each), then one all-reduce + Adam."""
         for a in range(accum):
             if sync is not None:
@@ -297,6 +297,21 @@ def run_ours(args):
         opt.step(1e-3, grad_scale=scale, zero_grad=True)
         losses.append(loss.detach())
 
+    graph_state = {"step": None}
+
+    def step_resident():
+        """The same step as the library runs it inside pretrain_epoch: replayed as one CUDA graph after the first eager step (--no-graph: eager)."""
+        g = graph_state["step"]
+        if g is None:
+            return step_eager()
+        loss, _, _ = g.run(sig, 1e-3)
+        losses.append(loss)
+
+    step_eager()
+    if accum == 1 and not args.no_graph:
+        learner._eager_pretrain_steps = 1
+        graph_state["step"] = learner.graphed_pretrain_step(sig, opt)
+
     for _ in range(warmup):
         step_resident()
     eng = model.engine
@@ -306,7 +321,8 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=10)              # an nvidia-smi query still in flight would stall the end-to-end region that follows
-    launches = eng.k.launches + opt.k.launches - l0 + args.steps       # + the front-end kernel
+    gstep = graph_state["step"]
+    launches = (eng.k.launches + opt.k.launches - l0 + args.steps) if gstep is None else args.steps * (gstep.launches_per_replay + 1)       # + the front-end kernel
     ops.stft_frontend_check(dev)
     value = nb * world * accum * args.steps / (ms * 1e-3)
     loss_first, loss_last = float(losses[0]), float(losses[-1])
@@ -363,7 +379,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extras["longclip"] = bench_pretrain_shape(dev, world, timed, nt=LC_NT, nb=args.longclip_batch, steps=3, dtype=dtype, sync_learner=None,
                                                   label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step")
-        extras["finetune"] = bench_finetune_core(dev, world, rank, timed, nb=64, steps=10, dtype=dtype)
+        extras["finetune"] = bench_finetune_core(dev, world, rank, timed, nb=64, steps=10, dtype=dtype, use_graph=not args.no_graph)
 
     if rank == 0:
         step_tflops = value * FLOP_PER_CLIP / 1e12 / world
@@ -373,6 +389,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * NT + nb * 4) * accum,
                         "d2h_bytes_per_step": 8},
                 "gpu_launches": int(launches), "tensor_core_gemm_launches": int(eng.k.tc_launches),
+                "cuda_graph": gstep is not None,
                 "loss_first_step": loss_first, "loss_last_step": loss_last,
                 "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / pk["bf16_tflops_sustained"],
                 "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (3x3 conv 64->64 implicit GEMM, forward)" if dtype == torch.bfloat16 else "conv3x3_kernel (CUDA cores, fp32)", "achieved": conv_tflops,
@@ -569,7 +586,7 @@ def cpu_finetune_clips_per_s(nb, steps, warmup, threads):
     return nb * len(times) / sum(times)
 
 
-def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype):
+def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype, use_graph=True):
     """configs[3]: downstream fine-tuning step (TDOA head, MSE, Adam) on 1.04 s clips."""
     import torch
     from sarssl_b200.learner import STFTLearner
@@ -590,17 +607,27 @@ def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype):
     host_sig, host_lab = sig.cpu().pin_memory(), labels.cpu().pin_memory()
     opt = FusedAdam(model, lr=1e-5)
 
-    def step():
+    def step_eager():
         x, tar = L.data_preprocess(sig, {"TDOA": labels})
         pred, _ = model(x)
         L.loss(pred_batch=pred, gt_batch=tar).backward()
         opt.step(1e-5, grad_scale=sync.all_reduce() if sync is not None else 1.0)
 
     for _ in range(3):
-        step()
+        step_eager()
+    L._eager_finetune_steps = 1
+    gstep = L.graphed_finetune_step(sig, opt) if use_graph else None          # the step as train_epoch runs it: one CUDA graph after the first eager step
+    tar_dev = L.get_tar_batch(labels)
+
+    def step():
+        if gstep is None:
+            return step_eager()
+        gstep.run(sig, tar_dev, 1e-5)
+
+    step()
     l0 = model.engine.k.launches + opt.k.launches
     ms = timed(step, steps)
-    launches = model.engine.k.launches + opt.k.launches - l0 + steps      # + the front-end kernel
+    launches = (model.engine.k.launches + opt.k.launches - l0 + steps) if gstep is None else steps * (gstep.launches_per_replay + 1)      # + the front-end kernel
     # end to end through the reference-facing call with host buffers; an epoch re-creates Adam (like the reference), so it is warmed up once
     # and timed over enough steps that this per-epoch cost does not dominate a 7 ms step
     e2e_steps = max(steps, 20)
@@ -611,7 +638,7 @@ def bench_finetune_core(dev, world, rank, timed, nb, steps, dtype):
             "ms_per_step": ms / steps, "per_gpu_batch": nb, "nt": FT_NT, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
             "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * 4),
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches), "cuda_graph": gstep is not None}
 
 
 def run_sub_workload(args):
@@ -634,7 +661,7 @@ def run_sub_workload(args):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     timed = make_timed(world, dev)
     if args.workload == "finetune":
-        line = bench_finetune_core(dev, world, rank, timed, nb=args.batch if args.batch != 256 else 64, steps=args.steps, dtype=dtype)   # configs[3]: batch 512 over 8 GPUs
+        line = bench_finetune_core(dev, world, rank, timed, nb=args.batch if args.batch != 256 else 64, steps=args.steps, dtype=dtype, use_graph=not args.no_graph)   # configs[3]: batch 512 over 8 GPUs
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = {"value": cpu_finetune_clips_per_s(8, 2, 1, cores), "unit": "clips/s", "cores": cores, "kind": "port",
@@ -676,6 +703,7 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-input-pipeline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly (one launch per kernel) instead of replaying it as a CUDA graph")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune", "longclip"],
                     help="pretrain = headline (configs[2]); finetune = configs[3]; longclip = configs[4]")
     args = ap.parse_args()

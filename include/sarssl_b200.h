@@ -165,6 +165,8 @@ typedef struct sarssl_gemm_args {
     float alpha, beta;
     float drop_p; unsigned long long drop_seed;
     float a_drop_p; unsigned long long a_drop_seed;
+    const unsigned long long* seed_dev;   /* nullable device word ADDED to both seeds inside the kernel: the per-step part of the dropout seed
+                                           * when the step is replayed as a CUDA graph (launch arguments are frozen in a graph) */
 } sarssl_gemm_args;
 /* CUDA-core kernel (exact fp32 when ab_dtype is F32): any shape / stride. */
 int sarssl_gemm(const sarssl_gemm_args* args, cudaStream_t stream);
@@ -213,10 +215,10 @@ int sarssl_batchnorm_act_bwd(const void* dz, const void* y, const float* stats, 
 
 /* Swish / ReLU / GLU gradients and GLU forward                              conformer/activation.py:19-42
  *   swish_bwd: du = ds * dropout_mask(offset)/(1-p) * swish'(u)  (regenerates the FFN dropout mask, feed_forward.py:51) */
-int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, int dtype,
+int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, const unsigned long long* seed_dev, int dtype,
                      cudaStream_t stream);
 /*   dst = alpha * src * dropout_mask(offset)/(1-p): gradient of `x + alpha*Dropout(v)` w.r.t. v (modules.py:33 + the Dropout sites) */
-int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, int dtype,
+int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, const unsigned long long* seed_dev, int dtype,
                          cudaStream_t stream);
 int sarssl_relu_bwd(const void* dz, const void* z, void* dy, long long n, int dtype, cudaStream_t stream);
 int sarssl_glu_fwd(const void* g, void* a, long long rows, int D, int dtype, cudaStream_t stream);
@@ -230,9 +232,10 @@ int sarssl_glu_bwd(const void* da, const void* g, void* dg, long long rows, int 
 int sarssl_add_head_bias(const void* q, long long ld, const float* u_bias, const float* v_bias, void* qu, void* qv, long long rows, int D,
                          int dtype, cudaStream_t stream);
 int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, void* attn_dropped, int B, int H, int T, float scale,
-                            float drop_p, unsigned long long seed, int dtype, cudaStream_t stream);
+                            float drop_p, unsigned long long seed, const unsigned long long* seed_dev, int dtype, cudaStream_t stream);
 int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void* dpos, int B, int H, int T, float scale, float drop_p,
-                            unsigned long long seed, int dtype, cudaStream_t stream);
+                            unsigned long long seed, const unsigned long long* seed_dev, int dtype, cudaStream_t stream);
+/* (seed_dev, nullable, everywhere it appears: a device word added to `seed` inside the kernel - see sarssl_gemm_args.seed_dev) */
 int sarssl_add2(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows, int cols, int dtype,
                 cudaStream_t stream);
 
@@ -331,7 +334,10 @@ int sarssl_conv3x3_wgrad_tc(const void* dy, const void* in, const float* in_scal
  * Hyper-parameters are doubles: 1 - beta, the bias corrections and lr / (1 - beta1^step) are formed in double on the host and rounded
  * to fp32 once, exactly as torch.optim.Adam does with its Python floats. */
 int sarssl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, long long n, int step, double lr,
-                     double beta1, double beta2, double eps, float grad_scale, int zero_grad, cudaStream_t stream);
+                     double beta1, double beta2, double eps, float grad_scale, int zero_grad, const float* hyper_dev, cudaStream_t stream);
+/* hyper_dev (nullable): two device floats {lr / (1 - beta1^step), sqrt(1 - beta2^step)} that replace the values derived from `step` and `lr`
+ * (a step replayed as a CUDA graph cannot change launch arguments); sarssl_adam_hyper_host fills them on the host exactly as above. */
+int sarssl_adam_hyper_host(float* hyper2_host, int step, double lr, double beta1, double beta2);
 
 /* ------------------------------------------------------------------------------------------------------------
  * A15  data-parallel gradient exchange (replaces nn.DataParallel, learner.py:25-31): NCCL sum all-reduce of contiguous buckets

@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
                 ("ab_dtype", C.c_int), ("c_dtype", C.c_int), ("act", C.c_int), ("accumulate", C.c_int),
                 ("alpha", C.c_float), ("beta", C.c_float),
                 ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
-                ("a_drop_p", C.c_float), ("a_drop_seed", C.c_ulonglong)]
+                ("a_drop_p", C.c_float), ("a_drop_seed", C.c_ulonglong), ("seed_dev", C.c_void_p)]
 
 
 _SCALARS = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t,

@@ -24,12 +24,14 @@ struct GemmP {
     int act, accumulate, has_resid;
     float drop_p; unsigned long long drop_seed;        // epilogue dropout (index = C element offset)
     float a_drop_p; unsigned long long a_drop_seed;    // A-operand dropout mask (index = A element offset)
+    const unsigned long long* seed_dev;                // nullable: device word added to both seeds
 };
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p) { return to_f32(*p); }
 
 template <typename TA, typename TC, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(TPB) gemm_simt_kernel(GemmP p) {
+    if (p.seed_dev) { const unsigned long long so = *p.seed_dev; p.drop_seed += so; p.a_drop_seed += so; }
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -141,7 +143,7 @@ extern "C" int sarssl_gemm(const sarssl_gemm_args* a, cudaStream_t stream) {
     p.ldc = a->ldc; p.sCb1 = a->sCb1; p.sCb2 = a->sCb2; p.ldr = a->ldr ? a->ldr : a->ldc;
     p.M = a->M; p.N = a->N; p.K = a->K; p.nb2 = a->nb2;
     p.alpha = a->alpha; p.beta = a->beta; p.act = a->act; p.accumulate = a->accumulate; p.has_resid = a->resid != nullptr;
-    p.drop_p = a->drop_p; p.drop_seed = a->drop_seed; p.a_drop_p = a->a_drop_p; p.a_drop_seed = a->a_drop_seed;
+    p.drop_p = a->drop_p; p.drop_seed = a->drop_seed; p.a_drop_p = a->a_drop_p; p.a_drop_seed = a->a_drop_seed; p.seed_dev = a->seed_dev;
     const int nbatch = a->nb1 * a->nb2;
     if (a->ab_dtype == SARSSL_F32 && a->c_dtype == SARSSL_F32) launch<float, float>(p, nbatch, stream);
     else if (a->ab_dtype == SARSSL_BF16 && a->c_dtype == SARSSL_BF16) launch<__nv_bfloat16, __nv_bfloat16>(p, nbatch, stream);

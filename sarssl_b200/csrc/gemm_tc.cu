@@ -30,6 +30,7 @@ struct TcEpi {
     float alpha, beta;
     int act, accumulate, c_is_bf16, vec_ok, tma_store;
     float drop_p; unsigned long long drop_seed;
+    const unsigned long long* seed_dev;  // nullable: device word added to drop_seed
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------------
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const int cpart = (warp - 2) >> 2;              // warps sharing a lane quarter interleave the tile's 32-column chunks
         const bool drop = FAST ? ((EPI & 16) != 0) : (p.drop_p > 0.f);
+        const unsigned long long drop_seed = p.drop_seed + ((drop && p.seed_dev) ? *p.seed_dev : 0ull);
         const uint32_t thr = drop_threshold(p.drop_p);
         const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
         const bool atomic = FAST ? false : (p.splitk > 1);
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     if (drop) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {              // off is even here (ldc % 8 == 0, nb % 32 == 0)
-                            const uint32_t kp = keep_pair(p.drop_seed, (unsigned long long)(off + j) >> 1, thr);
+                            const uint32_t kp = keep_pair(drop_seed, (unsigned long long)(off + j) >> 1, thr);
                             v[j] = (kp & 1u) ? v[j] * keep_scale : 0.f;
                             v[j + 1] = (kp & 2u) ? v[j + 1] * keep_scale : 0.f;
                         }
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     }
                     if (f_act == 1) v = fmaxf(v, 0.f);
                     else if (f_act == 2) v = __fdividef(v, 1.0f + __expf(-v));
-                    if (drop) v = keep_mask(p.drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
+                    if (drop) v = keep_mask(drop_seed, (unsigned long long)(off + j), p.drop_p) ? v * keep_scale : 0.f;
                     if (f_resid) {
                         const float rv = f_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[roff + j]) : static_cast<const float*>(p.resid)[roff + j];
                         v = rv + p.beta * v;
@@ -492,7 +494,7 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     e.C = a->C; e.pre = a->pre_out; e.resid = a->resid; e.bias = a->bias; e.ldc = a->ldc; e.ldr = a->ldr ? a->ldr : a->ldc;
     e.sCb1 = a->sCb1; e.sCb2 = a->sCb2; e.nb2 = a->nb2;
     e.M = a->M; e.N = a->N; e.K = a->K; e.alpha = a->alpha; e.beta = a->beta; e.act = a->act; e.accumulate = a->accumulate;
-    e.c_is_bf16 = a->c_dtype == SARSSL_BF16; e.drop_p = a->drop_p; e.drop_seed = a->drop_seed;
+    e.c_is_bf16 = a->c_dtype == SARSSL_BF16; e.drop_p = a->drop_p; e.drop_seed = a->drop_seed; e.seed_dev = a->seed_dev;
     e.a_z1 = (a->nb1 > 1 && a->sAb1 != 0); e.a_z2 = (a->nb2 > 1 && a->sAb2 != 0); e.b_z1 = (a->nb1 > 1 && a->sBb1 != 0); e.b_z2 = (a->nb2 > 1 && a->sBb2 != 0);
     if (e.accumulate && e.c_is_bf16) { set_last_error("gemm_tc: accumulate needs an fp32 C"); return SARSSL_ERR_UNSUPPORTED; }
     const size_t esz = e.c_is_bf16 ? 2 : 4;

@@ -16,7 +16,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // du = ds * dropmask(idx)/(1-p) * swish'(u)      (FFN: s = Dropout(Swish(u)), feed_forward.py:49-51)
 template <typename T>
 __global__ void __launch_bounds__(256) swish_bwd_kernel(const T* __restrict__ ds, const T* __restrict__ u, T* __restrict__ du, long long n, float drop_p,
-                                                      unsigned long long seed) {
+                                                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     const uint32_t thr = drop_threshold(drop_p);
     for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < n; g += (long long)gridDim.x * 256) {
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(256) add2_kernel(const T* __restrict__ a, long
 template <typename T>
 __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const T* __restrict__ content, const T* __restrict__ pos, T* __restrict__ prob,
                                                              T* __restrict__ attn, int B, int H, int Tn, float scale, float drop_p,
-                                                             unsigned long long seed) {
+                                                             unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= (long long)B * H * Tn) return;
@@ -163,7 +165,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const T* __restri
 // dscore = scale * P * (dP - sum_j dP*P),  dP = dattn * dropmask/(1-p);  in place over dattn
 template <typename T>
 __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(T* __restrict__ dattn, const T* __restrict__ prob, long long rows, int Tn,
-                                                             float scale, float drop_p, unsigned long long seed) {
+                                                             float scale, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -213,7 +216,8 @@ static inline int score_row_floats(int Tn) { return Tn + Tn / 8 + 8; }
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __restrict__ content, const T* __restrict__ pos, T* __restrict__ prob,
                                                                  T* __restrict__ attn, int B, int H, int Tn, float scale, float drop_p,
-                                                                 unsigned long long seed) {
+                                                                 unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     extern __shared__ float score_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rowf = Tn + Tn / 8 + 8;
@@ -292,7 +296,8 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __re
 
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256) attn_softmax_bwd_vec_kernel(T* __restrict__ dattn, const T* __restrict__ prob, long long rows, int Tn,
-                                                                 float scale, float drop_p, unsigned long long seed) {
+                                                                 float scale, float drop_p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -432,11 +437,12 @@ using namespace sarssl;
         else { set_last_error("bad dtype %d", (int)(dtype)); return SARSSL_ERR_ARG; }  \
     } while (0)
 
-extern "C" int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed, int dtype,
+extern "C" int sarssl_swish_bwd(const void* ds, const void* u, void* du, long long n, float drop_p, unsigned long long seed,
+                                const unsigned long long* seed_dev, int dtype,
                                 cudaStream_t stream) {
     SARSSL_CHECK_ARG(ds && u && du && n > 0 && n % 8 == 0, "swish_bwd: bad arguments (n must be a multiple of 8)");
     DISPATCH_T(dtype, (swish_bwd_kernel<T><<<ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(ds), static_cast<const T*>(u), static_cast<T*>(du), n,
-                                                                          drop_p, seed)));
+                                                                          drop_p, seed, seed_dev)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
@@ -482,7 +488,7 @@ extern "C" int sarssl_add2(const void* a, long long lda, const void* b, long lon
 }
 
 extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, void* prob, void* attn_dropped, int B, int H, int T_, float scale,
-                                       float drop_p, unsigned long long seed, int dtype, cudaStream_t stream) {
+                                       float drop_p, unsigned long long seed, const unsigned long long* seed_dev, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(content && pos && prob && B > 0 && H > 0 && T_ > 0, "attn_softmax_fwd: bad arguments");
     const long long rows = (long long)B * H * T_;
     if (T_ % 8 == 0 && T_ <= kScoreMaxT) {
@@ -498,7 +504,7 @@ extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, voi
             }                                                                                                                                    \
             DISPATCH_T(dtype, (attn_softmax_fwd_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, smem, stream>>>(                           \
                                    static_cast<const T*>(content), static_cast<const T*>(pos), static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_, \
-                                   scale, drop_p, seed)));                                                                                       \
+                                   scale, drop_p, seed, seed_dev)));                                                                                       \
         } while (0)
         if (T_ <= 256) SCORE_FWD(1);
         else if (T_ <= 512) SCORE_FWD(2);
@@ -507,13 +513,13 @@ extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, voi
     } else
         DISPATCH_T(dtype, (attn_softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<const T*>(content), static_cast<const T*>(pos),
                                                                                                     static_cast<T*>(prob), static_cast<T*>(attn_dropped), B, H, T_, scale,
-                                                                                                    drop_p, seed)));
+                                                                                                    drop_p, seed, seed_dev)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }
 
 extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void* dpos, int B, int H, int T_, float scale, float drop_p,
-                                       unsigned long long seed, int dtype, cudaStream_t stream) {
+                                       unsigned long long seed, const unsigned long long* seed_dev, int dtype, cudaStream_t stream) {
     SARSSL_CHECK_ARG(dattn_inout && prob && dpos && B > 0 && H > 0 && T_ > 0, "attn_softmax_bwd: bad arguments");
     const long long rows = (long long)B * H * T_;
     const bool vec = T_ % 8 == 0 && T_ <= kScoreMaxT;
@@ -528,7 +534,7 @@ extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void
             set = true;                                                                                                                          \
         }                                                                                                                                        \
         DISPATCH_T(dtype, (attn_softmax_bwd_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout),     \
-                               static_cast<const T*>(prob), rows, T_, scale, drop_p, seed)));                                                    \
+                               static_cast<const T*>(prob), rows, T_, scale, drop_p, seed, seed_dev)));                                                    \
         SARSSL_LAUNCH_CHECK();                                                                                                                   \
         DISPATCH_T(dtype, (attn_unshift_vec_kernel<T, NCH><<<(unsigned)((rows + 7) / 8), 256, smem, stream>>>(static_cast<const T*>(dattn_inout), \
                                static_cast<T*>(dpos), B, H, T_)));                                                                               \
@@ -539,7 +545,7 @@ extern "C" int sarssl_attn_softmax_bwd(void* dattn_inout, const void* prob, void
         else SCORE_BWD(4);
     } else {
         DISPATCH_T(dtype, (attn_softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(static_cast<T*>(dattn_inout), static_cast<const T*>(prob),
-                                                                                                    rows, T_, scale, drop_p, seed)));
+                                                                                                    rows, T_, scale, drop_p, seed, seed_dev)));
         SARSSL_LAUNCH_CHECK();
         DISPATCH_T(dtype, (attn_unshift_kernel<T><<<ew_grid(rows * T_), 256, 0, stream>>>(static_cast<const T*>(dattn_inout), static_cast<T*>(dpos), B, H, T_)));
     }
@@ -604,7 +610,8 @@ namespace sarssl {
 // dst = alpha * src * dropout_mask(offset)/(1-p): re-applies a forward dropout mask to the incoming gradient
 template <typename T>
 __global__ void __launch_bounds__(256) scale_dropout_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n, float alpha, float drop_p,
-                                                          unsigned long long seed) {
+                                                          unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) seed += *seed_dev;
     const float ks = drop_p > 0.f ? alpha / (1.0f - drop_p) : alpha;
     const uint32_t thr = drop_threshold(drop_p);
     for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g * 8 < n; g += (long long)gridDim.x * 256) {
@@ -621,11 +628,12 @@ __global__ void __launch_bounds__(256) scale_dropout_kernel(const T* __restrict_
 }
 }  // namespace sarssl
 
-extern "C" int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed, int dtype,
+extern "C" int sarssl_scale_dropout(const void* src, void* dst, long long n, float alpha, float drop_p, unsigned long long seed,
+                                    const unsigned long long* seed_dev, int dtype,
                                     cudaStream_t stream) {
     SARSSL_CHECK_ARG(src && dst && n > 0 && n % 8 == 0, "scale_dropout: bad arguments (n must be a multiple of 8)");
     DISPATCH_T(dtype, (sarssl::scale_dropout_kernel<T><<<sarssl::ew_grid(n), 256, 0, stream>>>(static_cast<const T*>(src), static_cast<T*>(dst), n, alpha,
-                                                                                             drop_p, seed)));
+                                                                                             drop_p, seed, seed_dev)));
     SARSSL_LAUNCH_CHECK();
     return SARSSL_OK;
 }

@@ -22,7 +22,15 @@ ENCODERS = (("spec_encoder", SPEC_D, SPEC_LAYERS, 1, 0), ("spat_encoder", SPAT_D
 
 
 def _site_seed(step_seed, site):
+    """Dropout seed of call site `site` in step `step_seed`.  step_seed None (CUDA-graph replay): only the site part - the kernels add the step
+    part, step_part(step_seed), from a device word, so a replayed graph draws fresh masks every step and eager / replayed steps agree bit for bit."""
+    if step_seed is None:
+        return site * 7919 + 12345
     return (step_seed * 1000003 + site * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF
+
+
+def step_part(step_seed):
+    return step_seed * 1000003
 
 
 class Engine:
@@ -33,6 +41,16 @@ class Engine:
         self.set_dtype(dtype)
         self.step_seed = 0
         self._pe_cache = {}
+
+    def _seed(self):
+        """The step's dropout seed as the kernels' by-value argument: the running step number, or None while the step part lives on the device."""
+        return None if self.k.seed_dev is not None else self.step_seed
+
+    def use_device_seed(self, seed_dev):
+        """seed_dev: a uint64 device tensor holding step_part(step number) (written before every replay), or None for by-value seeds."""
+        self.k.seed_dev = seed_dev
+        if self.k32 is not self.k:
+            self.k32.seed_dev = seed_dev
 
     def set_dtype(self, dtype):
         self.dtype = dtype
@@ -104,7 +122,7 @@ class Engine:
         p_drop = self.dropout_p if training else 0.0
         self._prepare_weights(F)
         dec = "spec_spat_decoder" if frozen else "decoder"
-        sv = {"B": B, "T": T, "F": F, "p_drop": p_drop, "seed": self.step_seed, "flag": flag, "ch": ch, "patches": patches, "dec": dec,
+        sv = {"B": B, "T": T, "F": F, "p_drop": p_drop, "seed": self._seed(), "flag": flag, "ch": ch, "patches": patches, "dec": dec,
               "frozen": frozen} if want_grad else None
         cat = k.empty(M, SPEC_D + SPAT_D)
         site = [0]
@@ -207,8 +225,8 @@ class Engine:
         k, st = self.k, self.store
         M, H, dh = B * T, NHEAD, D // NHEAD
         s = pre + ".sequential"
-        rec = {"seed": self.step_seed}
-        f1 = {"seed": self.step_seed}
+        rec = {"seed": self._seed()}
+        f1 = {"seed": self._seed()}
         x1 = self._ffn_fwd(s + ".0.module.sequential", D, x, M, p_drop, site, f1)
         # ---- relative-position MHSA                                                              attention.py:72-103,143-151
         m = s + ".1.module"
@@ -225,8 +243,8 @@ class Engine:
         content, pos, prob = k.empty(B, H, T, T), k.empty(H, B, T, T), k.empty(B, H, T, T)
         k.gemm(qu, qkv, content, T, T, dh, (D, 1), (3 * D, 1), T, b_off=D, batch=(B, H), sAb=(T * D, dh), sBb=(T * 3 * D, dh), sCb=(H * T * T, T * T))
         k.gemm(qv, pp, pos, T, T, dh, (D, 1), (D, 1), T, batch=(B, H), sAb=(T * D, dh), sBb=(0, dh), sCb=(T * T, B * T * T))
-        dp = (p_drop, _site_seed(self.step_seed, site[0])); site[0] += 1
-        do = (p_drop, _site_seed(self.step_seed, site[0])); site[0] += 1
+        dp = (p_drop, _site_seed(self._seed(), site[0])); site[0] += 1
+        do = (p_drop, _site_seed(self._seed(), site[0])); site[0] += 1
         attn = k.empty(B, H, T, T) if p_drop > 0 else None            # Dropout(prob), materialised so the context GEMMs run on tensor cores
         k.attn_softmax_fwd(content, pos, prob, attn, B, H, T, 1.0 / math.sqrt(D), dp)
         del content, pos
@@ -249,11 +267,11 @@ class Engine:
         sbn = self._bn(c + ".5", cv, M, D, training)
         z = k.empty(M, D)
         k.bn_act_fwd(cv, sbn, ACT_SWISH, z, M, D)
-        dc = (p_drop, _site_seed(self.step_seed, site[0])); site[0] += 1
+        dc = (p_drop, _site_seed(self._seed(), site[0])); site[0] += 1
         x3 = k.empty(M, D)
         k.linear(z, self.w(c + ".7.conv.weight", (D, D)), x3, M, D, D, bias=st.p(c + ".7.conv.bias"), resid=x2, ldr=D, beta=1.0, drop=dc)
         # ---- second half-step FFN + final LayerNorm
-        f2 = {"seed": self.step_seed}
+        f2 = {"seed": self._seed()}
         x4 = self._ffn_fwd(s + ".3.module.sequential", D, x3, M, p_drop, site, f2)
         mean5, rstd5 = k.empty(M, dtype=torch.float32), k.empty(M, dtype=torch.float32)
         if out is None:
@@ -281,7 +299,7 @@ class Engine:
         self.step_seed += 1
         p_drop = self.dropout_p if training else 0.0
         self._prepare_weights(F)
-        sv = {"B": B, "T": T, "F": F, "seed": self.step_seed, "patches": patches, "flag": None, "ch": None, "embed_use": embed_use} if want_grad else None
+        sv = {"B": B, "T": T, "F": F, "seed": self._seed(), "patches": patches, "flag": None, "ch": None, "embed_use": embed_use} if want_grad else None
         Dc = SPEC_D + SPAT_D
         cat = k.empty(M, Dc)
         site = [0]

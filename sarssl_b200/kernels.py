@@ -21,6 +21,7 @@ class KernelSet:
         self.launches = 0
         self.tc_launches = 0
         self.use_tc = True
+        self.seed_dev = None                     # device uint64 added to every dropout seed inside the kernels (CUDA-graph replay: engine.py)
         nbytes = max(self.L.sarssl_reduce_workspace_bytes(4096), self.L.sarssl_stem_workspace_bytes(),
                      self.L.sarssl_dwconv_wgrad_workspace_bytes(512, 31), self.L.sarssl_conv3x3_wgrad_tc_workspace_bytes())
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
@@ -29,6 +30,10 @@ class KernelSet:
     @property
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @property
+    def _sd(self):
+        return C.c_void_p(self.seed_dev.data_ptr()) if self.seed_dev is not None else None
 
     def empty(self, *shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.dtype, device=self.dev)
@@ -61,6 +66,7 @@ class KernelSet:
         g.alpha, g.beta = alpha, beta
         g.drop_p, g.drop_seed = drop
         g.a_drop_p, g.a_drop_seed = a_drop
+        g.seed_dev = self.seed_dev.data_ptr() if (self.seed_dev is not None and (drop[0] > 0 or a_drop[0] > 0)) else None
         if self.use_tc and A.dtype == torch.bfloat16 and a_drop[0] == 0.0:
             rc = self.L.sarssl_gemm_tc(C.byref(g), self.stream)      # tcgen05 path; -3 = shape/stride it does not take
             if rc == 0:
@@ -115,10 +121,10 @@ class KernelSet:
 
     # ------------------------------------------------------------------ pointwise
     def swish_bwd(self, ds, u, du, n, drop):
-        self._ok(self.L.sarssl_swish_bwd(ptr(ds), ptr(u), ptr(du), n, drop[0], drop[1], self.dt, self.stream), "swish_bwd")
+        self._ok(self.L.sarssl_swish_bwd(ptr(ds), ptr(u), ptr(du), n, drop[0], drop[1], self._sd, self.dt, self.stream), "swish_bwd")
 
     def scale_dropout(self, src, dst, n, alpha, drop):
-        self._ok(self.L.sarssl_scale_dropout(ptr(src), ptr(dst), n, alpha, drop[0], drop[1], self.dt, self.stream), "scale_dropout")
+        self._ok(self.L.sarssl_scale_dropout(ptr(src), ptr(dst), n, alpha, drop[0], drop[1], self._sd, self.dt, self.stream), "scale_dropout")
 
     def relu_bwd(self, dz, z, dy, n):
         self._ok(self.L.sarssl_relu_bwd(ptr(dz), ptr(z), ptr(dy), n, self.dt, self.stream), "relu_bwd")
@@ -136,11 +142,11 @@ class KernelSet:
         self._ok(self.L.sarssl_add2(ptr(a), lda, ptr(b), ldb, _addr(out, out_off), ldo, rows, cols, self.dt, self.stream), "add2")
 
     def attn_softmax_fwd(self, content, pos, prob, attn, B, H, T, scale, drop):
-        self._ok(self.L.sarssl_attn_softmax_fwd(ptr(content), ptr(pos), ptr(prob), ptr(attn), B, H, T, scale, drop[0], drop[1], self.dt, self.stream),
-                 "attn_softmax_fwd")
+        self._ok(self.L.sarssl_attn_softmax_fwd(ptr(content), ptr(pos), ptr(prob), ptr(attn), B, H, T, scale, drop[0], drop[1], self._sd, self.dt,
+                                                self.stream), "attn_softmax_fwd")
 
     def attn_softmax_bwd(self, dattn, prob, dpos, B, H, T, scale, drop):
-        self._ok(self.L.sarssl_attn_softmax_bwd(ptr(dattn), ptr(prob), ptr(dpos), B, H, T, scale, drop[0], drop[1], self.dt, self.stream),
+        self._ok(self.L.sarssl_attn_softmax_bwd(ptr(dattn), ptr(prob), ptr(dpos), B, H, T, scale, drop[0], drop[1], self._sd, self.dt, self.stream),
                  "attn_softmax_bwd")
         self.launches += 1
 
@@ -258,6 +264,6 @@ class KernelSet:
                  "conv3x3_wgrad")
         self.launches += 1
 
-    def adam(self, p, g, m, v, p_bf16, n, step, lr, grad_scale=1.0, zero_grad=True):
+    def adam(self, p, g, m, v, p_bf16, n, step, lr, grad_scale=1.0, zero_grad=True, hyper_dev=None):
         self._ok(self.L.sarssl_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), n, step, lr, 0.9, 0.999, 1e-8, grad_scale, int(zero_grad),
-                                         self.stream), "adam_step")
+                                         ptr(hyper_dev), self.stream), "adam_step")

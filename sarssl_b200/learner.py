@@ -103,7 +103,7 @@ class Learner(CheckpointMixin, ABC):
                 t.record_stream(compute)         # allocated on the copy stream, consumed on the compute stream
             yield out
 
-    def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True, accum_steps=1):
+    def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True, accum_steps=1, use_graph=None):
         """learner.py:76-131: one epoch of pre-training.  A fresh Adam (moments reset) per epoch like the reference; loss / diff
         of every step are kept on the device and read back once at the end of the epoch (the reference syncs 3x per step).
 
@@ -111,10 +111,16 @@ class Learner(CheckpointMixin, ABC):
         add up in the flat gradient arena, 1/accum_steps is folded into the Adam kernel, and under data parallelism the all-reduce
         runs once per optimizer step instead of once per micro-batch).  This is how 1 / 2 / 4 GPUs reach BASELINE.json's global batch
         of 2048 with 256-clip micro-batches; BatchNorm statistics stay per micro-batch, as under the reference's
-        DataParallel replicas.  A trailing partial group is applied with its real count."""
+        DataParallel replicas.  A trailing partial group is applied with its real count.
+
+        use_graph (None = automatic, False = never): after the first (eager) step, batches of an unchanged shape are replayed as ONE CUDA graph
+        (graph.py) - same arithmetic, same masks, same dropout stream as the eager step, without the ~450 per-step launches."""
         from .optim import FusedAdam
         self.model.train()
-        optimizer = FusedAdam(self.model, lr=lr)
+        optimizer = getattr(self, "_epoch_optimizer", None)
+        if optimizer is None or optimizer.model is not self.model or optimizer.m.device != self.model.store.flat.device:
+            optimizer = self._epoch_optimizer = FusedAdam(self.model, lr=lr)      # one set of moment buffers, reset every epoch: a captured graph keeps their addresses
+        optimizer.reset()
         optimizer.zero_grad()
         sync = getattr(self, "grad_sync", None)
         accum_steps = max(int(accum_steps), 1)
@@ -127,6 +133,20 @@ class Learner(CheckpointMixin, ABC):
             optimizer.step(lr, grad_scale=scale, zero_grad=True)
 
         for batch_idx, (mic_sig_batch,) in enumerate(self.device_batches(dataset)):
+            if accum_steps == 1 and use_graph is not False:
+                step = self.graphed_pretrain_step(mic_sig_batch, optimizer)
+                if step is not None:
+                    try:
+                        loss_batch, diff_batch, vis_batch = step.run(mic_sig_batch.to(self.device, non_blocking=True), lr)
+                    except RuntimeError as e:            # a capture that cannot be recorded: remember it and stay eager (nothing has executed)
+                        if step.graph is not None:
+                            raise
+                        self._graph_failed = True
+                        import warnings
+                        warnings.warn(f"sarssl_b200: CUDA-graph capture of the training step failed, running eagerly ({e})")
+                    else:
+                        log.append(torch.stack([loss_batch, diff_batch]))
+                        continue
             in_batch, = self.data_preprocess(mic_sig_batch, None)
             if sync is not None:
                 sync.defer = pending + 1 < accum_steps      # only the last micro-batch of a group announces its buckets
@@ -136,6 +156,7 @@ class Learner(CheckpointMixin, ABC):
             if pending == accum_steps:
                 apply(pending)
                 pending = 0
+            self._eager_pretrain_steps = getattr(self, "_eager_pretrain_steps", 0) + 1
             log.append(torch.stack([loss_batch.detach(), diff_batch.detach()]))
         if pending:
             apply(pending)
@@ -144,6 +165,54 @@ class Learner(CheckpointMixin, ABC):
         if return_diff:
             return vals[0], vals[1], vis_batch
         return vals[0]
+
+    def graphed_pretrain_step(self, sig, optimizer):
+        """The CUDA-graph runner (graph.py) for waveform batches shaped like `sig`, or None when this step must run eagerly: the very first
+        step (lazy initialisation - cached tables, kernel attributes - must happen outside a capture), a model outside the pre-training
+        configuration the graph covers, or a capture that failed once."""
+        m = self.model
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or not getattr(m, "pretrain", False) and not getattr(m, "pretrain_frozen_encoder", False):
+            return None
+        if not torch.is_tensor(sig) or sig.dim() != 3 or sig.shape[-1] != 2 or getattr(self, "fre_used_ratio", 1) != 1 or not m.training:
+            return None
+        if getattr(self, "_eager_pretrain_steps", 0) < 1 or getattr(self, "_graph_failed", False):
+            return None
+        eng = m._engine()
+        key = (tuple(sig.shape), id(eng), id(optimizer), m.compute_dtype, m.dropout_p, getattr(self, "grad_sync", None) is not None,
+               tuple(not p.requires_grad for p in m.store.params.values()))
+        cache = self.__dict__.setdefault("_graph_steps", {})
+        step = cache.get(key)
+        if step is None:
+            from .graph import GraphedPretrainStep
+            for old in cache.values():           # one live graph: its private pool holds a whole step's activations
+                old.release()
+            cache.clear()
+            step = cache[key] = GraphedPretrainStep(self, optimizer, sig.shape[0], sig.shape[1])
+        return step
+
+    def graphed_finetune_step(self, sig, optimizer):
+        """The CUDA-graph runner of the fine-tuning step for batches shaped like `sig`, or None when the step must run eagerly."""
+        m = self.model
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or getattr(m, "pretrain", True) or getattr(m, "pretrain_frozen_encoder", False) or not m.training:
+            return None
+        if not torch.is_tensor(sig) or sig.dim() != 3 or sig.shape[-1] != 2 or getattr(self, "fre_used_ratio", 1) != 1:
+            return None
+        if getattr(self, "_eager_finetune_steps", 0) < 1 or getattr(self, "_graph_failed", False):
+            return None
+        eng = m._engine()
+        key = ("ft", tuple(sig.shape), id(eng), id(optimizer), m.compute_dtype, m.dropout_p, getattr(self, "grad_sync", None) is not None,
+               tuple(not p.requires_grad for p in m.store.params.values()))
+        cache = self.__dict__.setdefault("_graph_steps", {})
+        step = cache.get(key)
+        if step is None:
+            from .graph import GraphedFinetuneStep
+            for old in cache.values():
+                old.release()
+            cache.clear()
+            step = cache[key] = GraphedFinetuneStep(self, optimizer, sig.shape[0], (sig.shape[0], 1))
+        return step
 
     def check_frontend(self):
         """Raise if the fused front-end kernel's per-clip rendezvous ever timed out during the epoch (it would have written
@@ -226,21 +295,42 @@ class STFTLearner(Learner):
         """learner.py:644-653: mean absolute error."""
         return torch.mean(torch.abs(pred_batch.contiguous().detach() - gt_batch.contiguous().detach()))
 
-    def train_epoch(self, dataset, lr=0.0001, epoch=None, return_metric=False):
-        """learner.py:170-222: one fine-tuning epoch; dataset yields (mic_sig_batch, {task: labels})."""
+    def train_epoch(self, dataset, lr=0.0001, epoch=None, return_metric=False, use_graph=None):
+        """learner.py:170-222: one fine-tuning epoch; dataset yields (mic_sig_batch, {task: labels}).  After the first (eager) step, batches of an
+        unchanged shape are replayed as one CUDA graph (graph.py; use_graph=False: never)."""
         from .optim import FusedAdam
         self.model.train()
-        optimizer = FusedAdam(self.model, lr=lr)
+        optimizer = getattr(self, "_epoch_optimizer", None)
+        if optimizer is None or optimizer.model is not self.model or optimizer.m.device != self.model.store.flat.device:
+            optimizer = self._epoch_optimizer = FusedAdam(self.model, lr=lr)      # one set of moment buffers, reset every epoch (a captured graph keeps their addresses)
+        optimizer.reset()
         optimizer.zero_grad()
         sync = getattr(self, "grad_sync", None)
         losses, metrics = [], []
         for mic_sig_batch, gt_batch in self.device_batches(dataset):
+            step = self.graphed_finetune_step(mic_sig_batch, optimizer) if use_graph is not False else None
+            if step is not None:
+                tar_batch = self.get_tar_batch(gt_batch=gt_batch[self.task].to(self.device))
+                try:
+                    loss_batch, pred_batch, embed_batch = step.run(mic_sig_batch.to(self.device, non_blocking=True), tar_batch, lr)
+                except RuntimeError as e:
+                    if step.graph is not None:
+                        raise
+                    self._graph_failed = True
+                    import warnings
+                    warnings.warn(f"sarssl_b200: CUDA-graph capture of the fine-tuning step failed, running eagerly ({e})")
+                else:
+                    losses.append(loss_batch)
+                    if return_metric:
+                        metrics.append(self.evaluate(pred_batch=pred_batch, gt_batch=tar_batch))
+                    continue
             in_batch, tar_batch = self.data_preprocess(mic_sig_batch, gt_batch)
             pred_batch, embed_batch = self.model(in_batch)
             loss_batch = self.loss(pred_batch=pred_batch, gt_batch=tar_batch)
             loss_batch.backward()
             scale = sync.all_reduce() if sync is not None else 1.0
             optimizer.step(lr, grad_scale=scale, zero_grad=True)
+            self._eager_finetune_steps = getattr(self, "_eager_finetune_steps", 0) + 1
             losses.append(loss_batch.detach())
             if return_metric:
                 metrics.append(self.evaluate(pred_batch=pred_batch, gt_batch=tar_batch))

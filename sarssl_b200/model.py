@@ -206,7 +206,7 @@ class SARSSL(nn.Module):
         return self.engine
 
     # ---- forward
-    def forward(self, x):
+    def forward(self, x, _static_masks=None):
         """pretrain=True : x (nb, 2, nf, nt, 2) -> (loss, diff, {'mask': (nb,nf,nt,2), 'pred': (nb,nf,nt,2,2), 'tar': (nb,nf,nt,2,2)})   model.py:519-601
         pretrain=False: x -> (pred (nb, 1), time-mean embedding (nb, dembed))                                                       model.py:667-719
         pretrain_frozen_encoder=True (with pretrain=False): x -> (loss, loss * 0, data_vis): un-masked channel of the masked frames into the spectral
@@ -219,7 +219,11 @@ class SARSSL(nn.Module):
         if not self.pretrain and not self.pretrain_frozen_encoder:
             want = torch.is_grad_enabled() and self.training
             return _DownstreamFn.apply(self._anchor, self, patches, want)
-        pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state, dp=self.dp)
+        if _static_masks is not None:            # CUDA-graph replay (graph.py): the masks already sit in static device buffers
+            flag, cidx = _static_masks
+            pidx = None
+        else:
+            pidx, cidx, flag = self.patch_mask.draw(nb, nt, 2, self.rng_state, dp=self.dp)
         want = torch.is_grad_enabled() and self.training
         loss, diff = _PretrainFn.apply(self._anchor, self, patches, flag, cidx, want)
         vis = VisDict(self._last["pred"], patches, flag, cidx)

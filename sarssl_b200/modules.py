@@ -80,8 +80,8 @@ class PatchMask(nn.Module):
             raise SarsslError("PatchMask: only patch_mode 'T' (frame masking, the shipped default) is implemented")
         self.patch_mode, self.nmasked_patch, self.npatch_shape, self.device = patch_mode, nmasked_patch, npatch_shape, device
 
-    def draw(self, nbatch, npatch, nmic, rng_state=None, dp=None):
-        """Compact masks: (patch_idx int64 (nb, nmasked), ch_idx int32 (nb,), frame_flag uint8 (nb, npatch)) on device.
+    def draw_host(self, nbatch, npatch, nmic, rng_state=None, dp=None):
+        """Compact masks as numpy arrays: (patch_idx int64 (nb, nmasked), ch_idx int64 (nb, 1), frame_flag uint8 (nb, npatch)).
         dp = (rank, world): every rank draws the masks of the GLOBAL batch (nbatch * world items, same seed everywhere) and keeps
         rows [rank*nbatch, (rank+1)*nbatch) - bit-exact with the single-process reference on the concatenated batch."""
         rank, world = dp if dp is not None else (0, 1)
@@ -93,6 +93,11 @@ class PatchMask(nn.Module):
         if world > 1:
             sl = slice(rank * nbatch, (rank + 1) * nbatch)
             pidx, cidx, flag = pidx[sl].copy(), cidx[sl].copy(), flag[sl].copy()
+        return pidx, cidx, flag
+
+    def draw(self, nbatch, npatch, nmic, rng_state=None, dp=None):
+        """draw_host on the device: (patch_idx int64 (nb, nmasked), ch_idx int32 (nb,), frame_flag uint8 (nb, npatch))."""
+        pidx, cidx, flag = self.draw_host(nbatch, npatch, nmic, rng_state, dp)
         dev = self.device
         to = lambda a: torch.from_numpy(a).pin_memory().to(dev, non_blocking=True) if str(dev) != "cpu" else torch.from_numpy(a)
         return to(pidx), to(cidx.astype("int32")), to(flag)

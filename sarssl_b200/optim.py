@@ -36,12 +36,27 @@ class FusedAdam:
             self._frozen_sig, self._frozen_ranges = sig, [(o, n) for o, n in merged]
         return self._frozen_ranges
 
-    def step(self, lr=None, grad_scale=1.0, zero_grad=True):
+    def step(self, lr=None, grad_scale=1.0, zero_grad=True, hyper_dev=None):
+        """hyper_dev: two device floats {lr / (1 - beta1^t), sqrt(1 - beta2^t)} (hyper_host fills their host image) used INSTEAD of the values
+        derived from `lr` and the step count - the form a step replayed as a CUDA graph needs (its launch arguments are frozen)."""
         st = self.model.store
         self.t += 1
         for o, n in self.frozen_ranges():
             self.k.fill(st.grad[o:o + n], 0.0)
-        self.k.adam(st.flat, st.grad, self.m, self.v, None, st.total, self.t, float(self.lr if lr is None else lr), grad_scale, zero_grad)
+        self.k.adam(st.flat, st.grad, self.m, self.v, None, st.total, self.t, float(self.lr if lr is None else lr), grad_scale, zero_grad,
+                    hyper_dev=hyper_dev)
+
+    def hyper_host(self, out2, step, lr):
+        """out2: float32 CPU tensor of 2 elements <- the bias-corrected step size and sqrt(1 - beta2^step) of `step`, rounded like the kernel's."""
+        from ._lib import check
+        import ctypes as C
+        check(self.k.L.sarssl_adam_hyper_host(C.c_void_p(out2.data_ptr()), int(step), float(lr), 0.9, 0.999), "sarssl_adam_hyper_host")
+
+    def reset(self):
+        """A fresh optimizer (the reference creates a new Adam every epoch, learner.py:83) in the same buffers (a captured graph keeps their addresses)."""
+        self.m.zero_()
+        self.v.zero_()
+        self.t = 0
 
     def zero_grad(self):
         self.k.fill(self.model.store.grad, 0.0)
