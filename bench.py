@@ -378,7 +378,7 @@ def run_ours(args):
         del fsig, fpred, patches, dpred
         torch.cuda.empty_cache()
         extras["longclip"] = bench_pretrain_shape(dev, world, timed, nt=LC_NT, nb=args.longclip_batch, steps=3, dtype=dtype, sync_learner=None,
-                                                  label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step")
+                                                  label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step", use_graph=not args.no_graph)
         extras["finetune"] = bench_finetune_core(dev, world, rank, timed, nb=64, steps=10, dtype=dtype, use_graph=not args.no_graph)
 
     if rank == 0:
@@ -507,7 +507,7 @@ def make_timed(world, dev):
     return timed
 
 
-def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, label):
+def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, label, use_graph=True):
     """A pre-training step at another clip length (same path as the headline: front-end, masks, fwd, loss, bwd, all-reduce, Adam)."""
     import torch
     from sarssl_b200 import ops
@@ -531,17 +531,26 @@ def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, 
     host_sig = sig.cpu().pin_memory()
     opt = FusedAdam(model, lr=1e-3)
 
-    def step():
+    def step_eager():
         x, = L.data_preprocess(sig)
         loss, _, _ = model(x)
         loss.backward()
         opt.step(1e-3, grad_scale=sync.all_reduce() if sync is not None else 1.0, zero_grad=True)
 
     for _ in range(3):
-        step()
+        step_eager()
+    L._eager_pretrain_steps = 1
+    gstep = L.graphed_pretrain_step(sig, opt) if use_graph else None
+
+    def step():
+        if gstep is None:
+            return step_eager()
+        gstep.run(sig, 1e-3)
+
+    step()
     l0 = model.engine.k.launches + opt.k.launches
     ms = timed(step, steps)
-    launches = model.engine.k.launches + opt.k.launches - l0 + steps
+    launches = (model.engine.k.launches + opt.k.launches - l0 + steps) if gstep is None else steps * (gstep.launches_per_replay + 1)
     e2e_steps = max(steps, 4)
     L.pretrain_epoch([[host_sig]] * 2, lr=1e-3, epoch=1)
     e2e_ms = timed(lambda: L.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1), 1)
@@ -552,7 +561,7 @@ def bench_pretrain_shape(dev, world, timed, nt, nb, steps, dtype, sync_learner, 
             "ms_per_step": ms / steps, "per_gpu_batch": nb, "nt": nt, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
             "e2e": {"value": nb * world * e2e_steps / (e2e_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": int(host_sig.numel() * 4 + nb * nt + nb * 4),
                     "d2h_bytes_per_step": 8},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "cuda_graph": gstep is not None,
             "roofline": {"bound": "tensor", "achieved": v / world * flop / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": v / world * flop / 1e12 / pk["bf16_tflops_sustained"], "what": "whole step: algorithmic fwd+bwd FLOPs per clip x clips/s per GPU "
                          "against the sustained bf16 peak", "flop_per_clip": flop, "peak_source": pk["source"]}}
@@ -668,7 +677,7 @@ def run_sub_workload(args):
                                     "sample": "8 clips/step x 2 steps, oracle port (torch CPU fp32, dropout on)"}
     else:
         line = bench_pretrain_shape(dev, world, timed, nt=LC_NT, nb=args.longclip_batch, steps=args.steps, dtype=dtype, sync_learner=None,
-                                    label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step")
+                                    label="configs[4]: 16.4 s clips (262,400 samples, nt = 1024), bf16 pre-training step", use_graph=not args.no_graph)
     line.update({"warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": line["workload"], "parallelism": f"dp{world}"}})
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -97,6 +97,61 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _graph_worker(rank, world, port, out):
+    """The data-parallel step replayed as a CUDA graph (the NCCL all-reduce is captured on its side stream): replicas stay bit-identical and
+    the trained weights equal the eager data-parallel epoch's.  (Collectives of torch's communicator and of the library's own are never left
+    in flight together: two NCCL communicators running concurrently on one GPU may dead-lock, hence the synchronisations.)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from oracle import sarssl_oracle as O
+        from sarssl_b200 import ops
+        from sarssl_b200.learner import STFTLearner
+        from sarssl_b200.model import SARSSL
+        nb, nt = 2, 16
+        finals = {}
+        for mode in (False, None):
+            m3 = SARSSL(sig_shape=(256, nt, 2, 2), device=dev)
+            m3.load_state_dict(O.synthetic_state_dict(7))
+            m3.to(dev)
+            m3.set_dropout(0.1)
+            m3.set_compute_dtype(torch.bfloat16)
+            m3.rng_state = ops.mt_seed(99)
+            m3.train()
+            L3 = STFTLearner(m3, 512, 0.5, 512, 1, 16000)
+            L3.device = dev
+            L3.mul_gpu()
+            data = [[O.synthetic_waveforms(nb * world, (nt + 1) * 256, 2, seed=70 + i)[rank * nb:(rank + 1) * nb]] for i in range(4)]
+            launches0 = m3._engine().k.launches
+            L3.pretrain_epoch(data, lr=1e-3, epoch=1, use_graph=mode)
+            eager_launches = m3.engine.k.launches - launches0
+            torch.cuda.synchronize()
+            flat = [torch.empty_like(m3.store.flat) for _ in range(world)]
+            dist.all_gather(flat, m3.store.flat)
+            torch.cuda.synchronize()
+            assert all(torch.equal(flat[0], f) for f in flat), mode
+            finals[mode] = (m3.store.flat.clone(), eager_launches)
+        assert finals[None][1] <= 0.6 * finals[False][1]                   # one eager step + one recording pass of launches; steps 2-4 were replays
+        gerr = float((finals[None][0] - finals[False][0]).norm() / finals[False][0].norm())
+        assert gerr < 2e-3, gerr
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_graph_replay_two_gpus():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_data_parallel_step_two_gpus():
     world = 2
