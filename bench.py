@@ -304,7 +304,14 @@ def run_ours(args):
         g = graph_state["step"]
         if g is None:
             return step_eager()
-        loss, _, _ = g.run(sig, 1e-3)
+        try:
+            loss, _, _ = g.run(sig, 1e-3)
+        except RuntimeError as e:                 # a step that cannot be recorded on this box: say so and measure the eager step
+            if g.graph is not None:
+                raise
+            sys.stderr.write(f"bench: CUDA-graph capture failed ({e}); running the step eagerly\n")
+            graph_state["step"] = None
+            return step_eager()
         losses.append(loss)
 
     step_eager()
