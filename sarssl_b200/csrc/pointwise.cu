@@ -210,6 +210,11 @@ __global__ void attn_unshift_kernel(const T* __restrict__ dscore, T* __restrict_
 // S' = [dscore row r-1 | dscore row r]; the rows are staged in (dynamic) shared memory as fp32 with one pad word every 8 (lane stride
 // 9 words: conflict-free for both the chunked stores and the windowed loads).
 __device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
+__device__ __forceinline__ float ex2_approx(float x) {          // 2^x, flush-to-zero (no denormal fix-up code around the MUFU)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 constexpr int kScoreMaxT = 1024;
 static inline int score_row_floats(int Tn) { return Tn + Tn / 8 + 8; }
 
@@ -221,15 +226,19 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __re
     extern __shared__ float score_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rowf = Tn + Tn / 8 + 8;
-    float* win0 = score_smem + (size_t)w * 2 * rowf;
-    float* win1 = win0 + rowf;
+    float* win0 = score_smem + (size_t)w * rowf;                  // this warp's staged (already shifted) positional row
     const long long row = (long long)blockIdx.x * 8 + w;
     if (row >= (long long)B * H * Tn) return;
     const int i = (int)(row % Tn);
     const long long bh = row / Tn;
     const int h = (int)(bh % H), b = (int)(bh / H);
     const T* pbase = pos + ((long long)h * B + b) * Tn * Tn;
+    // The shift is applied while STAGING: source column s of pos row i lands at score column j = s - (T-1-i) (the j <= i part), source column s
+    // of row i+1 at j = s + i + 2 (the j > i+1 part), column i+1 is zero.  The staged row is then read back by its owner lane at compile-time
+    // offsets (9 c + e: conflict-free), with no per-element index arithmetic or selects.
     float v[NCH][8];
+    const int sh0 = Tn - 1 - i, sh1 = i + 2;
+    if (lane == 0 && i + 1 < Tn) win0[pad8(i + 1)] = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
         const int c = lane + 32 * k;
@@ -237,16 +246,23 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __re
             float t[8];
             Vec8<T>::load(pbase + (long long)i * Tn + c * 8, t);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) win0[c * 9 + e] = t[e];
+            for (int e = 0; e < 8; ++e) {
+                const int j = c * 8 + e - sh0;
+                if (j >= 0) win0[pad8(j)] = t[e];
+            }
             if (i + 1 < Tn) {
                 Vec8<T>::load(pbase + (long long)(i + 1) * Tn + c * 8, t);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) win1[c * 9 + e] = t[e];
+                for (int e = 0; e < 8; ++e) {
+                    const int j = c * 8 + e + sh1;
+                    if (j < Tn) win0[pad8(j)] = t[e];
+                }
             }
             Vec8<T>::load(content + row * Tn + c * 8, v[k]);
         }
     }
     __syncwarp();
+    const float scale2 = scale * 1.4426950408889634f;              // scores in units of log2: softmax through ex2 without a multiply per element
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -254,9 +270,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __re
         if (c * 8 < Tn) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int idx = Tn - 1 - i + c * 8 + e;
-                const float ps = idx < Tn ? win0[pad8(idx)] : (idx == Tn ? 0.f : win1[pad8(idx - Tn - 1)]);
-                v[k][e] = (v[k][e] + ps) * scale;
+                v[k][e] = (v[k][e] + win0[c * 9 + e]) * scale2;
                 mx = fmaxf(mx, v[k][e]);
             }
         }
@@ -267,7 +281,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_vec_kernel(const T* __re
     for (int k = 0; k < NCH; ++k) {
         if ((lane + 32 * k) * 8 < Tn) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { v[k][e] = __expf(v[k][e] - mx); sum += v[k][e]; }
+            for (int e = 0; e < 8; ++e) { v[k][e] = ex2_approx(v[k][e] - mx); sum += v[k][e]; }
         }
     }
     sum = warp_sum(sum);
@@ -492,7 +506,7 @@ extern "C" int sarssl_attn_softmax_fwd(const void* content, const void* pos, voi
     SARSSL_CHECK_ARG(content && pos && prob && B > 0 && H > 0 && T_ > 0, "attn_softmax_fwd: bad arguments");
     const long long rows = (long long)B * H * T_;
     if (T_ % 8 == 0 && T_ <= kScoreMaxT) {
-        const size_t smem = (size_t)8 * 2 * score_row_floats(T_) * sizeof(float);
+        const size_t smem = (size_t)8 * score_row_floats(T_) * sizeof(float);
 #define SCORE_FWD(NCH)                                                                                                                           \
         do {                                                                                                                                     \
             static bool set_f = false, set_h = false;                                                                                            \
