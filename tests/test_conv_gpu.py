@@ -76,6 +76,11 @@ def test_tc_conv3x3_vs_torch_fp32(B, H, W):
     mean, var = o.mean(0), o.var(0, unbiased=False)
     assert torch.allclose(stats[:64], mean, rtol=1e-3, atol=1e-4) and torch.allclose(stats[64:128], torch.rsqrt(var + 1e-5), rtol=2e-3)
     assert int(nbt) == 1 and torch.allclose(rm, 0.1 * mean, rtol=1e-3, atol=1e-4)
+    # without statistics (the data-gradient use) the epilogue stores straight from registers instead of staging a TMA store: same bits
+    out2 = torch.full((B, H, W, 64), -3.0, device=DEV, dtype=torch.bfloat16)
+    k.conv3x3_tc(x, wp, out2, B, H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 1, 64), (2, 16, 256), (1, 40, 256), (3, 33, 200), (2, 70, 64), (8, 256, 256)])
