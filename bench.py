@@ -335,7 +335,7 @@ def run_ours(args):
     loss_first, loss_last = float(losses[0]), float(losses[-1])
 
     # ---------------- end to end through the reference-facing API, host buffers
-    e2e_steps = max(args.steps, 10) * accum       # one epoch call; long enough that its fixed costs (fresh Adam, first un-overlapped copy, final read-back) stay small
+    e2e_steps = max(args.steps, 30) * accum       # one epoch call; long enough that its fixed costs (fresh Adam, first un-overlapped copy, final read-back) stay small
     learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1, accum_steps=accum)          # warm-up epoch of the same length (allocator / pinned pools at their steady size)
     e2e_ms = timed(lambda: learner.pretrain_epoch([[host_sig]] * e2e_steps, lr=1e-3, epoch=1, accum_steps=accum), 1)
     e2e_value = nb * world * e2e_steps / (e2e_ms * 1e-3)

@@ -251,19 +251,22 @@ __global__ void __launch_bounds__(XF ? kConvXfThreads : kConvFwdThreads, 1) conv
                                    a2 = ring_lo + (uint32_t)sl[2] * (CBOXB >> 4), a3 = ring_lo + (uint32_t)sl[3] * (CBOXB >> 4);
                     const bool last = t == npair - 1;
                     if (celect_one()) {
-                        // weight slot (dw, dh) = dw*3 + (1 - dh) (dw, dh as 0..2 / -1..1); the first instruction initialises all 128 columns.
-                        // Rows h-1 and h die with this pair: their instructions go first and their slots are released half a pair early, which
-                        // is the lead the producer (and, with XF, the operand transform behind it) needs on a ring that cannot be deeper.
+                        // weight slot (dw, dh) = dw*3 + (1 - dh) (dw, dh as 0..2 / -1..1).  A tcgen05.mma that accumulates into the columns its predecessor
+                        // wrote waits ~43 clk for it (scripts/micro/umma_rate.cu), so the two N = 64 streams - input row h-1 into columns 0-63, input row
+                        // h+2 into columns 64-127 - are issued ALTERNATELY (independent accumulators: 48 clk each instead of 92); their first instructions
+                        // initialise the 128 columns.  Rows h-1 and h die with this pair: their slots are released before row h+1's instructions.
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                cumma2(d, a0 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 2) * 512 + k * 2, hi, idesc64, (uint32_t)((dw | k) != 0));       // row h-1: dh = -1
+                                cumma2(d + 64, a3 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc64, (uint32_t)((dw | k) != 0));  // row h+2: dh = +1
+                            }
 #pragma unroll
                         for (int dw = 0; dw < 3; ++dw)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h:   dh = 0 for output row h | dh = -1 for output row h+1
-                                cumma2(d, a1 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 1) * 512 + k * 2, hi, idesc128, (uint32_t)((dw | k) != 0));
-#pragma unroll
-                        for (int dw = 0; dw < 3; ++dw)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)         // input row h-1: dh = -1, output row h only (columns 0-63)
-                                cumma2(d, a0 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 2) * 512 + k * 2, hi, idesc64, 1u);
+                                cumma2(d, a1 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 1) * 512 + k * 2, hi, idesc128, 1u);
                         ccommit(&empty[sl[0]]);
                         ccommit(&empty[sl[1]]);
 #pragma unroll
@@ -271,11 +274,6 @@ __global__ void __launch_bounds__(XF ? kConvXfThreads : kConvFwdThreads, 1) conv
 #pragma unroll
                             for (int k = 0; k < 4; ++k)         // input row h+1: dh = +1 for output row h | dh = 0 for output row h+1
                                 cumma2(d, a2 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc128, 1u);
-#pragma unroll
-                        for (int dw = 0; dw < 3; ++dw)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)         // input row h+2: dh = +1, output row h+1 only (columns 64-127)
-                                cumma2(d + 64, a3 + dw * 8 + k * 2, hi, w_lo + (dw * 3 + 0) * 512 + k * 2, hi, idesc64, 1u);
                         if (last) { ccommit(&empty[sl[2]]); ccommit(&empty[sl[3]]); }
                         ccommit(&tfull[acc]);
                     }
