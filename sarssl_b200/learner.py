@@ -51,7 +51,8 @@ class Learner(CheckpointMixin, ABC):
     def device_batches(self, dataset):
         """Input pipeline step in front of the path (the reference leaves it to DataLoader + a blocking `.to(device)` inside
         data_preprocess, learner.py:530): host tensors of batch i+1 are copied to the device on a side stream while batch i is
-        being computed, so the H2D transfer (134 MB for 256 clips) never sits on the compute stream.  Items keep their structure
+        being computed (the copy is enqueued right after the consumer has launched batch i), so the H2D transfer (134 MB for 256 clips)
+        never sits on the compute stream.  Items keep their structure
         (list / tuple / dict of tensors); pinned host tensors copy asynchronously, pageable ones still overlap with the device work
         already queued.  Device tensors pass through untouched."""
         dev = torch.device(self.device)
@@ -85,23 +86,27 @@ class Learner(CheckpointMixin, ABC):
             ev.record(copy_stream)
             return out, moved, ev
 
+        # Order matters on the device: a CUDA-graph launch uploads its launch data through the same copy engine, so a 134 MB host-to-device copy enqueued
+        # just BEFORE the step's launch delays that step by the copy's whole duration (measured: +2.4 ms per step, scripts/e2e_ab.py).  The next batch
+        # is therefore staged AFTER the consumer has launched its work on the current one (when it asks for the next item): the copy then runs while
+        # the device computes.
         it = iter(dataset)
         try:
-            nxt = stage(next(it))
+            cur = stage(next(it))
         except StopIteration:
             return
-        while nxt is not None:
-            cur = nxt
-            try:
-                nxt = stage(next(it))            # enqueue the next copy before handing out the current batch
-            except StopIteration:
-                nxt = None
+        while cur is not None:
             out, moved, ev = cur
             compute = torch.cuda.current_stream(dev)
             compute.wait_event(ev)
             for t in moved:
                 t.record_stream(compute)         # allocated on the copy stream, consumed on the compute stream
             yield out
+            del out, moved
+            try:
+                cur = stage(next(it))            # the consumer's work on the previous batch is already queued: this copy overlaps it
+            except StopIteration:
+                cur = None
 
     def pretrain_epoch(self, dataset, lr=0.0001, epoch=None, return_diff=True, accum_steps=1, use_graph=None):
         """learner.py:76-131: one epoch of pre-training.  A fresh Adam (moments reset) per epoch like the reference; loss / diff
