@@ -106,12 +106,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int NS>
+template <int BN, int NS, int EPI = 0>
 struct TcSmem {
     static constexpr int kABytes = TBM * TBK * 2, kBBytes = BN * TBK * 2;
-    static constexpr int kStageC = (BN / 64) * (TBM * 128);       // bf16 output tile, 128B-swizzled boxes of 64 columns
-    static constexpr int kBytes = NS * (kABytes + kBBytes) + 2 * kStageC + 1024 /*align slack*/ + 256 /*barriers*/;
+    // bf16 output tile, 128B-swizzled boxes of 64 columns (C and the pre-activation).  BN = 256: the fp32 weight-gradient variant (EPI 0) stages nothing
+    // (partial sums go from registers to red.global); the bf16 variants stage ONE half tile (two boxes) and store the tile in two rounds - the room
+    // pays for the fourth 48 KB stage.
+    static constexpr int kStageC = BN == 256 ? 2 * (TBM * 128) : (BN / 64) * (TBM * 128);
+    static constexpr int kNStage = BN == 256 ? (EPI != 0 ? 1 : 0) : 2;
+    static constexpr int kBytes = NS * (kABytes + kBBytes) + kNStage * kStageC + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
 
 // A_MN / B_MN: operand is MN-major (rows of the global matrix run along the contraction dimension), used by weight gradients.
 // NS = pipeline stages: 3 for long K; 2 for K <= 512 (4-8 k-blocks), which lets three CTAs share an SM so that more epilogue warps
@@ -121,13 +126,14 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                                                            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpi p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kA = TcSmem<BN, NS>::kABytes, kB = TcSmem<BN, NS>::kBBytes, kSC = TcSmem<BN, NS>::kStageC;
+    constexpr int kA = TcSmem<BN, NS, EPI>::kABytes, kB = TcSmem<BN, NS, EPI>::kBBytes, kSC = TcSmem<BN, NS, EPI>::kStageC;
+    constexpr bool WIDE_ST = BN == 256 && EPI != 0;      // bf16 output of a 128 x 256 tile: staged and stored in two halves of 128 columns
     constexpr int kStages = NS;
     unsigned char* sA = smem;
     unsigned char* sB = smem + kStages * kA;
     unsigned char* stC = smem + kStages * (kA + kB);              // staged C tile
     unsigned char* stP = stC + kSC;                               // staged pre-activation tile
-    uint64_t* full = reinterpret_cast<uint64_t*>(stP + kSC);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stC + TcSmem<BN, NS, EPI>::kNStage * kSC);
     uint64_t* empty = full + kStages;
     uint64_t* tfull = empty + kStages;                            // [2] accumulator ready
     uint64_t* tempty = tfull + 2;                                 // [2] accumulator drained (every epilogue warp arrives)
@@ -183,7 +189,10 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         }
     } else if (warp == 1) {
         {   // the whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane issues
-            constexpr uint32_t idesc = make_idesc(TBM, BN, A_MN, B_MN);
+            // BN = 256: two N = 128 instructions per k step into the two halves of the accumulator.  Instructions that accumulate into the columns
+            // their predecessor wrote wait for it (scripts/micro/umma_rate.cu: one N = 256 accumulator 171 clk per step, two alternating N = 128
+            // halves 128 clk); the point of the wide tile is the A operand, which is fetched from L2 once per 256 output columns instead of twice.
+            constexpr uint32_t idesc = make_idesc(TBM, BN == 256 ? 128 : BN, A_MN, B_MN);
             // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per 16-element k step inside the 128 B swizzle atom.
             // MN-major: 64-element MN groups 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 2048 B per k step.
             constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -208,7 +217,11 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     const uint32_t a_lo = a_lo0 + (uint32_t)s * (kA >> 4), b_lo = b_lo0 + (uint32_t)s * (kB >> 4);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < TBK / 16; ++k) umma_bf16_w(d, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
+                        for (int k = 0; k < TBK / 16; ++k) {
+                            umma_bf16_w(d, a_lo + k * a_step, hi, b_lo + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
+                            if (BN == 256)      // columns 128-255: B rows (K-major) or the two 64-column groups (MN-major) 16 KB further
+                                umma_bf16_w(d + 128, a_lo + k * a_step, hi, b_lo + (16384u >> 4) + k * b_step, hi, idesc, (uint32_t)((i | k) != 0));
+                        }
                         umma_commit(&empty[s]);             // stage reusable once these MMAs have read it
                         if (i == num_kb - 1) umma_commit(&tfull[acc]);     // accumulator complete
                     }
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
         // (pre-activation) output, bit 4 dropout, bit 5 residual; bf16 C through the TMA store, alpha = 1, no split-K): the flag tests
         // below fold away and each instantiation is straight-line code.  EPI == 0 keeps every test at run time.
         constexpr bool FAST = EPI != 0;
-        const bool f_tma = FAST ? true : (p.tma_store != 0);
+        const bool f_tma = BN == 256 ? WIDE_ST : (FAST ? true : (p.tma_store != 0));
         const bool f_vec = FAST ? true : (p.vec_ok != 0);
         const bool f_bf16 = FAST ? true : (p.c_is_bf16 != 0);
         const bool f_bias = FAST ? ((EPI & 1) != 0) : (p.bias != nullptr);
@@ -254,6 +267,11 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
             const long long zoff = (long long)z1 * p.sCb1 + (long long)z2 * p.sCb2;
 #pragma unroll 1
             for (int c0 = cpart * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
+                if (WIDE_ST && c0 >= 128) {           // second half: the first half's store must have left the staging boxes
+                    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                }
+                const int sb = WIDE_ST ? ((c0 & 127) >> 6) : (c0 >> 6);      // staging box of this chunk
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
                 const int nb = n0 + c0;
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     }
                     if (f_pre) {
                         if (f_bf16) {
-                            unsigned char* sbox = stP + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
+                            unsigned char* sbox = stP + sb * (TBM * 128) + (q * 32 + lane) * 128;
                             uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.pre) + off);
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                         for (int j = 0; j < 32; ++j) v[j] *= p.beta;
                     }
                     if (f_bf16) {
-                        unsigned char* sbox = stC + (c0 >> 6) * (TBM * 128) + (q * 32 + lane) * 128;
+                        unsigned char* sbox = stC + sb * (TBM * 128) + (q * 32 + lane) * 128;
                         uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + off);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -356,6 +374,22 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
+                    if (WIDE_ST) {                    // this half (128 columns = two boxes) is staged: store it; the accumulator is free after the second
+                        if (c0 >= 128) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[acc]);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                        if (warp == 2 && lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(&tmC),
+                                             "r"(n0 + (c0 & 128) + 64 * j), "r"(m0), "r"(z2), "r"(z1), "r"(smem_u32(stC + j * (TBM * 128))) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                     }
                     continue;
@@ -385,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(const __grid_consta
                     }
                 }
             }
+            if (WIDE_ST) continue;                    // released and stored half by half above
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -453,7 +488,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 template <int BN, bool A_MN, bool B_MN, int NS, int EPI = 0>
 static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, cudaStream_t stream) {
     static bool configured = false;
-    const int smem = TcSmem<BN, NS>::kBytes;
+    const int smem = TcSmem<BN, NS, EPI>::kBytes;
     if (!configured) {
         SARSSL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, NS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -467,6 +502,20 @@ static int launch_tc_ns(const CUtensorMap& ma, const CUtensorMap& mb, const CUte
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mp, const TcEpi& e, cudaStream_t stream) {
     return launch_tc_ns<BN, A_MN, B_MN, 4>(ma, mb, mc, mp, e, stream);
+}
+
+// SARSSL_GEMM_WIDE=0 keeps the 128 x 128 tiles everywhere (A/B measurements)
+static bool wide_tiles_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SARSSL_GEMM_WIDE"); on = e ? (atoi(e) != 0) : 1; }
+    return on != 0;
+}
+
+// SARSSL_GEMM_WIDE_MIN_K: shortest K for which the bf16 GEMMs use the wide tile (A/B measurements; default 256: in-step 43.15 ms against 43.32 ms at 512)
+static int wide_min_k() {
+    static int k = -1;
+    if (k < 0) { const char* e = getenv("SARSSL_GEMM_WIDE_MIN_K"); k = e ? atoi(e) : 256; }
+    return k;
 }
 
 }  // namespace sarssl
@@ -502,7 +551,21 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
                (!a->resid || aligned16(a->resid)) && (!a->bias || aligned16(a->bias));
     (void)esz;
     const bool bn64 = a->N <= 64;
-    const int BN = bn64 ? 64 : 128;
+    // 128 x 256 tiles for the split-K weight gradients (both operands MN-major, fp32 partial sums): the tall operand is read from L2 once per 256
+    // output columns; these GEMMs move 32 KB of operands per 128 x 128 x 64 block and are bound by that traffic.  Measured at K = 32768: 2048 x 512
+    // 768 -> 865 TFLOP/s, 1024 x 3072 856 -> 1078, 512 x 1024 659 -> 825; 1024 x 256 alone loses at that K (twice the split-K slices: 603 -> 499) but
+    // inside the step (K = 65536) wide tiles for every shape from 1024 x 256 up gave -0.43 ms per step against -0.18 ms when those were excluded.
+    const bool bn256 = a_mn && b_mn && a->N % 256 == 0 && (long long)a->M * a->N >= 256LL * 1024 && a->accumulate && a->c_dtype != SARSSL_BF16 && !a->pre_out && !a->resid && !a->bias && a->act == 0 &&
+                       a->drop_p == 0.f && wide_tiles_enabled();
+    // ... and for the bf16 GEMMs of the layer types below when N is a multiple of 256 and K is long enough for the operand traffic to matter
+    // (forward linears without a second output, data gradients): the tile is staged and stored in two halves
+    const int fast_flags = 64 | (a->bias ? 1 : 0) | ((a->act & 3) << 1) | (a->pre_out ? 8 : 0) | (a->drop_p > 0.f ? 16 : 0) | (a->resid ? 32 : 0);
+    const bool fast_shape = e.c_is_bf16 && e.vec_ok && a->alpha == 1.0f && !a->accumulate && (a->resid || a->beta == 1.0f);
+    const bool wide_fast = fast_shape && a->N % 256 == 0 && a->K >= wide_min_k() && wide_tiles_enabled() &&
+                           ((a_k && b_k && (fast_flags == 64 || fast_flags == (64 | 1) || fast_flags == (64 | 1 | 2) || fast_flags == (64 | 1 | 16 | 32) ||
+                                            fast_flags == (64 | 1 | 32))) ||
+                            (a_k && b_mn && fast_flags == 64));
+    const int BN = bn64 ? 64 : ((bn256 || wide_fast) ? 256 : 128);
     // split-K: weight gradients (fp32 accumulate, plain epilogue) have few output tiles and a very long K
     const int num_kb = (a->K + TBK - 1) / TBK;
     int splitk = 1;
@@ -533,6 +596,16 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     if ((rc = b_k ? make_map(&mb, a->B, a->N, a->K, ldb, TBK, BN, a->nb1, a->sBb1, a->nb2, a->sBb2)
                   : make_map(&mb, a->B, a->K, a->N, ldb, 64, TBK, a->nb1, a->sBb1, a->nb2, a->sBb2))) return rc;
     // compile-time epilogue variants for the layer types of the model (everything else runs the generic epilogue)
+    if (wide_fast) {
+        if (a_k && b_mn) return launch_tc_ns<256, false, true, 4, 64>(ma, mb, mc, mp, e, stream);
+        switch (fast_flags) {
+            case 64: return launch_tc_ns<256, false, false, 4, 64>(ma, mb, mc, mp, e, stream);
+            case 64 | 1: return launch_tc_ns<256, false, false, 4, 64 | 1>(ma, mb, mc, mp, e, stream);
+            case 64 | 1 | 2: return launch_tc_ns<256, false, false, 4, 64 | 1 | 2>(ma, mb, mc, mp, e, stream);
+            case 64 | 1 | 16 | 32: return launch_tc_ns<256, false, false, 4, 64 | 1 | 16 | 32>(ma, mb, mc, mp, e, stream);
+            default: return launch_tc_ns<256, false, false, 4, 64 | 1 | 32>(ma, mb, mc, mp, e, stream);
+        }
+    }
     if (!bn64 && e.tma_store && e.splitk == 1 && a->alpha == 1.0f && !a->accumulate) {
         const int flags = 64 | (a->bias ? 1 : 0) | ((a->act & 3) << 1) | (a->pre_out ? 8 : 0) | (a->drop_p > 0.f ? 16 : 0) | (a->resid ? 32 : 0);
         const bool beta_ok = a->resid || a->beta == 1.0f;
@@ -553,5 +626,6 @@ extern "C" int sarssl_gemm_tc(const sarssl_gemm_args* a, cudaStream_t stream) {
     if (a_k && b_k) return bn64 ? launch_tc<64, false, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, false>(ma, mb, mc, mp, e, stream);
     if (a_k && b_mn) return bn64 ? launch_tc<64, false, true>(ma, mb, mc, mp, e, stream) : launch_tc<128, false, true>(ma, mb, mc, mp, e, stream);
     if (a_mn && b_k) return bn64 ? launch_tc<64, true, false>(ma, mb, mc, mp, e, stream) : launch_tc<128, true, false>(ma, mb, mc, mp, e, stream);
+    if (bn256) return launch_tc<256, true, true>(ma, mb, mc, mp, e, stream);
     return bn64 ? launch_tc<64, true, true>(ma, mb, mc, mp, e, stream) : launch_tc<128, true, true>(ma, mb, mc, mp, e, stream);
 }

@@ -1,5 +1,5 @@
 """ms per graph-replayed pre-training step (B = 256, nt = 256, bf16) - for same-box A/B runs of environment switches:
-    for v in 0 1 0 1; do SOME_SWITCH=$v python scripts/step_ab.py; done"""
+    for v in 0 1 0 1; do SARSSL_GEMM_WIDE=$v python scripts/step_ab.py; done"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sarssl_b200 import ops

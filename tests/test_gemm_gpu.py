@@ -107,9 +107,9 @@ def test_tc_gemm_k_major_vs_torch_fp32(M, N, K):
     assert rel(outb.float(), mm32(A, B)) < 3e-3
 
 
-def test_tc_gemm_epilogue_vs_torch_fp32():
+@pytest.mark.parametrize("M,N,K", [(384, 256, 192), (1000, 512, 1024)])      # the second shape takes the 128 x 256 tiles (N % 256 == 0, K >= 512)
+def test_tc_gemm_epilogue_vs_torch_fp32(M, N, K):
     k = KernelSet(DEV, torch.bfloat16)
-    M, N, K = 384, 256, 192
     g = torch.Generator(device=DEV).manual_seed(3)
     A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
     B = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
@@ -127,7 +127,9 @@ def test_tc_gemm_epilogue_vs_torch_fp32():
     assert 0.85 < float(kept.float().mean()) < 0.95
     want = R.float() + 0.5 * (u * torch.sigmoid(u)) / 0.9
     assert rel(out.float()[kept], want[kept]) < 5e-3
-    assert torch.equal(out == R, ref == R)                     # identical dropout pattern as the CUDA-core kernel (same counter-based generator)
+    # identical dropout pattern as the CUDA-core kernel (same counter-based generator); a kept entry whose update is below half a bf16 ulp of the
+    # residual also reads "== R", in either kernel, so a handful of the 10^5..10^6 entries may differ
+    assert float(((out == R) != (ref == R)).float().mean()) < 1e-3
     assert rel(pre.float(), pre_ref.float()) < 1e-3 and rel(out.float(), ref.float()) < 5e-3
     # every compile-time epilogue variant of the model's layer types, without dropout, against torch
     for kw2, fn in ((dict(bias=bias), lambda u0: u0 + bias), (dict(bias=bias, act=ACT_RELU), lambda u0: torch.relu(u0 + bias)),
@@ -136,9 +138,16 @@ def test_tc_gemm_epilogue_vs_torch_fp32():
         _tc(k, A, B, o2, M, N, K, (K, 1), (K, 1), N, **kw2)
         torch.cuda.synchronize()
         assert rel(o2.float(), fn(mm32(A, B))) < 3e-3, kw2.keys()
+    # bias + dropout + residual without a second output (FFN 2 / attention output): same dropout pattern and values as the CUDA-core kernel
+    kw3 = dict(bias=bias, resid=R, ldr=N, beta=0.5, drop=(0.1, 9))
+    o3, r3 = k.empty(M, N), k.empty(M, N)
+    _tc(k, A, B, o3, M, N, K, (K, 1), (K, 1), N, **kw3)
+    k.linear(A, B, r3, M, N, K, **kw3)                       # k.use_tc is False here
+    torch.cuda.synchronize()
+    assert float(((o3 == R) != (r3 == R)).float().mean()) < 1e-3 and rel(o3.float(), r3.float()) < 5e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 256, 4096), (200, 72, 1000), (1024, 64, 8192), (2048, 512, 65536 // 4)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (512, 256, 4096), (200, 72, 1000), (1024, 64, 8192), (2048, 512, 65536 // 4), (1000, 1024, 3000), (256, 768, 8200)])
 def test_tc_gemm_mn_major_weight_gradient(M, N, K):
     """dW[M][N] (+)= sum_k dY[k][M] * X[k][N]: both operands stored with the contraction on the slow axis."""
     k = KernelSet(DEV, torch.bfloat16)
@@ -153,7 +162,7 @@ def test_tc_gemm_mn_major_weight_gradient(M, N, K):
     assert rel(out, 2 * ref) < 5e-5, rel(out, 2 * ref)      # fp32 accumulation-order noise only
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 520, 2048), (512, 64, 256)])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 192), (1000, 520, 2048), (512, 64, 256), (1000, 512, 2048)])
 def test_tc_gemm_data_gradient_mixed_majors(M, N, K):
     """dX[M][N] = dY[M][K] @ W[K][N]: A K-major, B with the contraction on the slow axis."""
     k = KernelSet(DEV, torch.bfloat16)
@@ -166,8 +175,11 @@ def test_tc_gemm_data_gradient_mixed_majors(M, N, K):
     Wt, dYt = W.T.contiguous(), dY.T.contiguous()
     out2 = k.empty(M, N, dtype=torch.float32)
     _tc(k, dYt, Wt, out2, M, N, K, (1, M), (K, 1), N)              # A MN-major, B K-major
+    out_bf = k.empty(M, N)                                        # bf16 output: the TMA-store epilogue (and, for N % 256 == 0, the wide tile)
+    _tc(k, dY, W, out_bf, M, N, K, (K, 1), (1, N), N)
     torch.cuda.synchronize()
     assert rel(out, ref) < 5e-5 and rel(out2, ref) < 5e-5
+    assert rel(out_bf.float(), ref) < 3e-3
 
 
 def test_tc_gemm_batched_attention_shapes_vs_torch_fp32():
